@@ -1,0 +1,441 @@
+/* mythos_b200.h -- plain C-ABI of the B200-native oxDNA-family energy / force / theta-gradient path.
+ *
+ * This is the drop-in boundary: every entry point takes device pointers, sizes and a CUDA stream, enqueues
+ * work on that stream and returns; no host synchronisation, no allocation inside a call (scratch comes from a
+ * caller-provided workspace), no torch / XLA types in any signature.  The XLA-FFI shim
+ * (mythos_b200/csrc/xla_ffi_shim.cc) and the ctypes host layer (mythos_b200/_lib.py) are thin adapters over it.
+ *
+ * Reference interfaces each entry point stands in for (paths relative to the reference repo):
+ *   mythos_b200_energy_*        ComposedEnergyFunction.compute_terms / __call__  mythos/energy/base.py:312-319
+ *                               (all BaseEnergyFunction.compute_energy of dna1/dna2/rna2/na1),
+ *                               EnergyFunction.map (batched frames)               mythos/energy/base.py:90-93,
+ *                               and their jax.grad / jax.value_and_grad           simulators/jax_md/jaxmd.py:70-73,
+ *                                                                                 optimization/objective.py:235
+ *   mythos_b200_nl_build_*      get_neighbor_list_fn -> jax_md.partition.neighbor_list(OrderedSparse)
+ *                                                                                 mythos/utils/neighbors.py:12-59
+ *   mythos_b200_langevin_*      step_fn of the user-supplied simulator_init (jax_md.simulate.nvt_langevin on
+ *                               RigidBody)                                        simulators/jax_md/jaxmd.py:73,82-94
+ *   mythos_b200_difftre_*       energy_fn.map(reference_states) + value_and_grad(compute_loss) w.r.t. params
+ *                                                                                 optimization/objective.py:224-235,345-364
+ *   mythos_b200_weights_neff_*  compute_weights_and_neff                          optimization/objective.py:139-163
+ *
+ * Conventions: center is (F,N,3), quat is (F,N,4) = (w,x,y,z), row-major, contiguous; integer arrays are int32;
+ * `pairs` is (2,capacity) with i = pairs[0][k] < j = pairs[1][k] and padding entries >= N (masked as the
+ * reference does with `op_i < N`); per-term outputs use the oxDNA split_energy column order MB_TERM_*.
+ */
+#ifndef MYTHOS_B200_H
+#define MYTHOS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------------------- */
+enum mb_status {
+  MB_OK = 0,
+  MB_EINVAL_SHAPE = 1, /* a size / pointer combination that cannot be a valid call          */
+  MB_EINVAL_MODEL = 2, /* unknown model form / bank count                                    */
+  MB_ECAPACITY = 3,    /* workspace or static capacity too small (data-independent)          */
+  MB_ECUDA = 4         /* a CUDA runtime call failed; see mythos_b200_last_error()           */
+};
+
+/* ---- energy terms (oxDNA split_energy.dat column order) -------------------------------------------------- */
+enum mb_term {
+  MB_TERM_FENE = 0,
+  MB_TERM_BEXC = 1,
+  MB_TERM_STACK = 2,
+  MB_TERM_UEXC = 3,
+  MB_TERM_HB = 4,
+  MB_TERM_CROSS = 5,
+  MB_TERM_COAX = 6,
+  MB_TERM_DEBYE = 7,
+  MB_N_TERMS = 8
+};
+#define MB_BONDED_TERMS 0x07u
+#define MB_UNBONDED_TERMS 0xF8u
+#define MB_ALL_TERMS 0xFFu
+
+/* ---- kernel-level parameter bank --------------------------------------------------------------------------
+ * One bank = MB_P_COUNT reals in the order below ("<term>.<reference parameter name>").  These are the
+ * *dependent-inclusive* parameters the reference's interaction functions receive: the
+ * theta -> bank chain (init_params, smoothing solvers) stays on the host side of the call.
+ * oxDNA1 / oxDNA2 / RNA2 use one bank; NA1 uses three (DNA, RNA, DNA-RNA hybrid) laid out back to back. */
+#define MB_PARAM_LIST(X) \
+  X(FENE_EPS, "fene.eps_backbone") \
+  X(FENE_R0, "fene.r0_backbone") \
+  X(FENE_DELTA, "fene.delta_backbone") \
+  X(FENE_FMAX, "fene.fmax") \
+  X(FENE_FINF, "fene.finf") \
+  X(BEXC_EPS, "bonded_excluded_volume.eps_exc") \
+  X(BEXC_BASE_RSTAR, "bonded_excluded_volume.dr_star_base") \
+  X(BEXC_BASE_SIGMA, "bonded_excluded_volume.sigma_base") \
+  X(BEXC_BASE_B, "bonded_excluded_volume.b_base") \
+  X(BEXC_BASE_RC, "bonded_excluded_volume.dr_c_base") \
+  X(BEXC_BACK_BASE_RSTAR, "bonded_excluded_volume.dr_star_back_base") \
+  X(BEXC_BACK_BASE_SIGMA, "bonded_excluded_volume.sigma_back_base") \
+  X(BEXC_BACK_BASE_B, "bonded_excluded_volume.b_back_base") \
+  X(BEXC_BACK_BASE_RC, "bonded_excluded_volume.dr_c_back_base") \
+  X(BEXC_BASE_BACK_RSTAR, "bonded_excluded_volume.dr_star_base_back") \
+  X(BEXC_BASE_BACK_SIGMA, "bonded_excluded_volume.sigma_base_back") \
+  X(BEXC_BASE_BACK_B, "bonded_excluded_volume.b_base_back") \
+  X(BEXC_BASE_BACK_RC, "bonded_excluded_volume.dr_c_base_back") \
+  X(UEXC_EPS, "unbonded_excluded_volume.eps_exc") \
+  X(UEXC_BASE_RSTAR, "unbonded_excluded_volume.dr_star_base") \
+  X(UEXC_BASE_SIGMA, "unbonded_excluded_volume.sigma_base") \
+  X(UEXC_BASE_B, "unbonded_excluded_volume.b_base") \
+  X(UEXC_BASE_RC, "unbonded_excluded_volume.dr_c_base") \
+  X(UEXC_BACK_BASE_RSTAR, "unbonded_excluded_volume.dr_star_back_base") \
+  X(UEXC_BACK_BASE_SIGMA, "unbonded_excluded_volume.sigma_back_base") \
+  X(UEXC_BACK_BASE_B, "unbonded_excluded_volume.b_back_base") \
+  X(UEXC_BACK_BASE_RC, "unbonded_excluded_volume.dr_c_back_base") \
+  X(UEXC_BASE_BACK_RSTAR, "unbonded_excluded_volume.dr_star_base_back") \
+  X(UEXC_BASE_BACK_SIGMA, "unbonded_excluded_volume.sigma_base_back") \
+  X(UEXC_BASE_BACK_B, "unbonded_excluded_volume.b_base_back") \
+  X(UEXC_BASE_BACK_RC, "unbonded_excluded_volume.dr_c_base_back") \
+  X(UEXC_BACKBONE_RSTAR, "unbonded_excluded_volume.dr_star_backbone") \
+  X(UEXC_BACKBONE_SIGMA, "unbonded_excluded_volume.sigma_backbone") \
+  X(UEXC_BACKBONE_B, "unbonded_excluded_volume.b_backbone") \
+  X(UEXC_BACKBONE_RC, "unbonded_excluded_volume.dr_c_backbone") \
+  X(STACK_RLOW, "stacking.dr_low_stack") \
+  X(STACK_RHIGH, "stacking.dr_high_stack") \
+  X(STACK_RCLOW, "stacking.dr_c_low_stack") \
+  X(STACK_RCHIGH, "stacking.dr_c_high_stack") \
+  X(STACK_A, "stacking.a_stack") \
+  X(STACK_R0, "stacking.dr0_stack") \
+  X(STACK_RC, "stacking.dr_c_stack") \
+  X(STACK_BLOW, "stacking.b_low_stack") \
+  X(STACK_BHIGH, "stacking.b_high_stack") \
+  X(STACK_T4_TH0, "stacking.theta0_stack_4") \
+  X(STACK_T4_DSTAR, "stacking.delta_theta_star_stack_4") \
+  X(STACK_T4_DC, "stacking.delta_theta_stack_4_c") \
+  X(STACK_T4_A, "stacking.a_stack_4") \
+  X(STACK_T4_B, "stacking.b_stack_4") \
+  X(STACK_T5_TH0, "stacking.theta0_stack_5") \
+  X(STACK_T5_DSTAR, "stacking.delta_theta_star_stack_5") \
+  X(STACK_T5_DC, "stacking.delta_theta_stack_5_c") \
+  X(STACK_T5_A, "stacking.a_stack_5") \
+  X(STACK_T5_B, "stacking.b_stack_5") \
+  X(STACK_T6_TH0, "stacking.theta0_stack_6") \
+  X(STACK_T6_DSTAR, "stacking.delta_theta_star_stack_6") \
+  X(STACK_T6_DC, "stacking.delta_theta_stack_6_c") \
+  X(STACK_T6_A, "stacking.a_stack_6") \
+  X(STACK_T6_B, "stacking.b_stack_6") \
+  X(STACK_T9_TH0, "stacking.theta0_stack_9") \
+  X(STACK_T9_DSTAR, "stacking.delta_theta_star_stack_9") \
+  X(STACK_T9_DC, "stacking.delta_theta_stack_9_c") \
+  X(STACK_T9_A, "stacking.a_stack_9") \
+  X(STACK_T9_B, "stacking.b_stack_9") \
+  X(STACK_T10_TH0, "stacking.theta0_stack_10") \
+  X(STACK_T10_DSTAR, "stacking.delta_theta_star_stack_10") \
+  X(STACK_T10_DC, "stacking.delta_theta_stack_10_c") \
+  X(STACK_T10_A, "stacking.a_stack_10") \
+  X(STACK_T10_B, "stacking.b_stack_10") \
+  X(STACK_PHI1_XSTAR, "stacking.neg_cos_phi1_star_stack") \
+  X(STACK_PHI1_XC, "stacking.neg_cos_phi1_c_stack") \
+  X(STACK_PHI1_A, "stacking.a_stack_1") \
+  X(STACK_PHI1_B, "stacking.b_neg_cos_phi1_stack") \
+  X(STACK_PHI2_XSTAR, "stacking.neg_cos_phi2_star_stack") \
+  X(STACK_PHI2_XC, "stacking.neg_cos_phi2_c_stack") \
+  X(STACK_PHI2_A, "stacking.a_stack_2") \
+  X(STACK_PHI2_B, "stacking.b_neg_cos_phi2_stack") \
+  X(STACK_W00, "stacking.eps_stack[0,0]") \
+  X(STACK_W01, "stacking.eps_stack[0,1]") \
+  X(STACK_W02, "stacking.eps_stack[0,2]") \
+  X(STACK_W03, "stacking.eps_stack[0,3]") \
+  X(STACK_W10, "stacking.eps_stack[1,0]") \
+  X(STACK_W11, "stacking.eps_stack[1,1]") \
+  X(STACK_W12, "stacking.eps_stack[1,2]") \
+  X(STACK_W13, "stacking.eps_stack[1,3]") \
+  X(STACK_W20, "stacking.eps_stack[2,0]") \
+  X(STACK_W21, "stacking.eps_stack[2,1]") \
+  X(STACK_W22, "stacking.eps_stack[2,2]") \
+  X(STACK_W23, "stacking.eps_stack[2,3]") \
+  X(STACK_W30, "stacking.eps_stack[3,0]") \
+  X(STACK_W31, "stacking.eps_stack[3,1]") \
+  X(STACK_W32, "stacking.eps_stack[3,2]") \
+  X(STACK_W33, "stacking.eps_stack[3,3]") \
+  X(HB_RLOW, "hydrogen_bonding.dr_low_hb") \
+  X(HB_RHIGH, "hydrogen_bonding.dr_high_hb") \
+  X(HB_RCLOW, "hydrogen_bonding.dr_c_low_hb") \
+  X(HB_RCHIGH, "hydrogen_bonding.dr_c_high_hb") \
+  X(HB_A, "hydrogen_bonding.a_hb") \
+  X(HB_R0, "hydrogen_bonding.dr0_hb") \
+  X(HB_RC, "hydrogen_bonding.dr_c_hb") \
+  X(HB_BLOW, "hydrogen_bonding.b_low_hb") \
+  X(HB_BHIGH, "hydrogen_bonding.b_high_hb") \
+  X(HB_T1_TH0, "hydrogen_bonding.theta0_hb_1") \
+  X(HB_T1_DSTAR, "hydrogen_bonding.delta_theta_star_hb_1") \
+  X(HB_T1_DC, "hydrogen_bonding.delta_theta_hb_1_c") \
+  X(HB_T1_A, "hydrogen_bonding.a_hb_1") \
+  X(HB_T1_B, "hydrogen_bonding.b_hb_1") \
+  X(HB_T2_TH0, "hydrogen_bonding.theta0_hb_2") \
+  X(HB_T2_DSTAR, "hydrogen_bonding.delta_theta_star_hb_2") \
+  X(HB_T2_DC, "hydrogen_bonding.delta_theta_hb_2_c") \
+  X(HB_T2_A, "hydrogen_bonding.a_hb_2") \
+  X(HB_T2_B, "hydrogen_bonding.b_hb_2") \
+  X(HB_T3_TH0, "hydrogen_bonding.theta0_hb_3") \
+  X(HB_T3_DSTAR, "hydrogen_bonding.delta_theta_star_hb_3") \
+  X(HB_T3_DC, "hydrogen_bonding.delta_theta_hb_3_c") \
+  X(HB_T3_A, "hydrogen_bonding.a_hb_3") \
+  X(HB_T3_B, "hydrogen_bonding.b_hb_3") \
+  X(HB_T4_TH0, "hydrogen_bonding.theta0_hb_4") \
+  X(HB_T4_DSTAR, "hydrogen_bonding.delta_theta_star_hb_4") \
+  X(HB_T4_DC, "hydrogen_bonding.delta_theta_hb_4_c") \
+  X(HB_T4_A, "hydrogen_bonding.a_hb_4") \
+  X(HB_T4_B, "hydrogen_bonding.b_hb_4") \
+  X(HB_T7_TH0, "hydrogen_bonding.theta0_hb_7") \
+  X(HB_T7_DSTAR, "hydrogen_bonding.delta_theta_star_hb_7") \
+  X(HB_T7_DC, "hydrogen_bonding.delta_theta_hb_7_c") \
+  X(HB_T7_A, "hydrogen_bonding.a_hb_7") \
+  X(HB_T7_B, "hydrogen_bonding.b_hb_7") \
+  X(HB_T8_TH0, "hydrogen_bonding.theta0_hb_8") \
+  X(HB_T8_DSTAR, "hydrogen_bonding.delta_theta_star_hb_8") \
+  X(HB_T8_DC, "hydrogen_bonding.delta_theta_hb_8_c") \
+  X(HB_T8_A, "hydrogen_bonding.a_hb_8") \
+  X(HB_T8_B, "hydrogen_bonding.b_hb_8") \
+  X(HB_W00, "hydrogen_bonding.eps_hb_weights[0,0]") \
+  X(HB_W01, "hydrogen_bonding.eps_hb_weights[0,1]") \
+  X(HB_W02, "hydrogen_bonding.eps_hb_weights[0,2]") \
+  X(HB_W03, "hydrogen_bonding.eps_hb_weights[0,3]") \
+  X(HB_W10, "hydrogen_bonding.eps_hb_weights[1,0]") \
+  X(HB_W11, "hydrogen_bonding.eps_hb_weights[1,1]") \
+  X(HB_W12, "hydrogen_bonding.eps_hb_weights[1,2]") \
+  X(HB_W13, "hydrogen_bonding.eps_hb_weights[1,3]") \
+  X(HB_W20, "hydrogen_bonding.eps_hb_weights[2,0]") \
+  X(HB_W21, "hydrogen_bonding.eps_hb_weights[2,1]") \
+  X(HB_W22, "hydrogen_bonding.eps_hb_weights[2,2]") \
+  X(HB_W23, "hydrogen_bonding.eps_hb_weights[2,3]") \
+  X(HB_W30, "hydrogen_bonding.eps_hb_weights[3,0]") \
+  X(HB_W31, "hydrogen_bonding.eps_hb_weights[3,1]") \
+  X(HB_W32, "hydrogen_bonding.eps_hb_weights[3,2]") \
+  X(HB_W33, "hydrogen_bonding.eps_hb_weights[3,3]") \
+  X(CROSS_RLOW, "cross_stacking.dr_low_cross") \
+  X(CROSS_RHIGH, "cross_stacking.dr_high_cross") \
+  X(CROSS_RCLOW, "cross_stacking.dr_c_low_cross") \
+  X(CROSS_RCHIGH, "cross_stacking.dr_c_high_cross") \
+  X(CROSS_K, "cross_stacking.k_cross") \
+  X(CROSS_R0, "cross_stacking.r0_cross") \
+  X(CROSS_RC, "cross_stacking.dr_c_cross") \
+  X(CROSS_BLOW, "cross_stacking.b_low_cross") \
+  X(CROSS_BHIGH, "cross_stacking.b_high_cross") \
+  X(CROSS_T1_TH0, "cross_stacking.theta0_cross_1") \
+  X(CROSS_T1_DSTAR, "cross_stacking.delta_theta_star_cross_1") \
+  X(CROSS_T1_DC, "cross_stacking.delta_theta_cross_1_c") \
+  X(CROSS_T1_A, "cross_stacking.a_cross_1") \
+  X(CROSS_T1_B, "cross_stacking.b_cross_1") \
+  X(CROSS_T2_TH0, "cross_stacking.theta0_cross_2") \
+  X(CROSS_T2_DSTAR, "cross_stacking.delta_theta_star_cross_2") \
+  X(CROSS_T2_DC, "cross_stacking.delta_theta_cross_2_c") \
+  X(CROSS_T2_A, "cross_stacking.a_cross_2") \
+  X(CROSS_T2_B, "cross_stacking.b_cross_2") \
+  X(CROSS_T3_TH0, "cross_stacking.theta0_cross_3") \
+  X(CROSS_T3_DSTAR, "cross_stacking.delta_theta_star_cross_3") \
+  X(CROSS_T3_DC, "cross_stacking.delta_theta_cross_3_c") \
+  X(CROSS_T3_A, "cross_stacking.a_cross_3") \
+  X(CROSS_T3_B, "cross_stacking.b_cross_3") \
+  X(CROSS_T4_TH0, "cross_stacking.theta0_cross_4") \
+  X(CROSS_T4_DSTAR, "cross_stacking.delta_theta_star_cross_4") \
+  X(CROSS_T4_DC, "cross_stacking.delta_theta_cross_4_c") \
+  X(CROSS_T4_A, "cross_stacking.a_cross_4") \
+  X(CROSS_T4_B, "cross_stacking.b_cross_4") \
+  X(CROSS_T7_TH0, "cross_stacking.theta0_cross_7") \
+  X(CROSS_T7_DSTAR, "cross_stacking.delta_theta_star_cross_7") \
+  X(CROSS_T7_DC, "cross_stacking.delta_theta_cross_7_c") \
+  X(CROSS_T7_A, "cross_stacking.a_cross_7") \
+  X(CROSS_T7_B, "cross_stacking.b_cross_7") \
+  X(CROSS_T8_TH0, "cross_stacking.theta0_cross_8") \
+  X(CROSS_T8_DSTAR, "cross_stacking.delta_theta_star_cross_8") \
+  X(CROSS_T8_DC, "cross_stacking.delta_theta_cross_8_c") \
+  X(CROSS_T8_A, "cross_stacking.a_cross_8") \
+  X(CROSS_T8_B, "cross_stacking.b_cross_8") \
+  X(COAX_RLOW, "coaxial_stacking.dr_low_coax") \
+  X(COAX_RHIGH, "coaxial_stacking.dr_high_coax") \
+  X(COAX_RCLOW, "coaxial_stacking.dr_c_low_coax") \
+  X(COAX_RCHIGH, "coaxial_stacking.dr_c_high_coax") \
+  X(COAX_K, "coaxial_stacking.k_coax") \
+  X(COAX_R0, "coaxial_stacking.dr0_coax") \
+  X(COAX_RC, "coaxial_stacking.dr_c_coax") \
+  X(COAX_BLOW, "coaxial_stacking.b_low_coax") \
+  X(COAX_BHIGH, "coaxial_stacking.b_high_coax") \
+  X(COAX_T4_TH0, "coaxial_stacking.theta0_coax_4") \
+  X(COAX_T4_DSTAR, "coaxial_stacking.delta_theta_star_coax_4") \
+  X(COAX_T4_DC, "coaxial_stacking.delta_theta_coax_4_c") \
+  X(COAX_T4_A, "coaxial_stacking.a_coax_4") \
+  X(COAX_T4_B, "coaxial_stacking.b_coax_4") \
+  X(COAX_T1_TH0, "coaxial_stacking.theta0_coax_1") \
+  X(COAX_T1_DSTAR, "coaxial_stacking.delta_theta_star_coax_1") \
+  X(COAX_T1_DC, "coaxial_stacking.delta_theta_coax_1_c") \
+  X(COAX_T1_A, "coaxial_stacking.a_coax_1") \
+  X(COAX_T1_B, "coaxial_stacking.b_coax_1") \
+  X(COAX_T5_TH0, "coaxial_stacking.theta0_coax_5") \
+  X(COAX_T5_DSTAR, "coaxial_stacking.delta_theta_star_coax_5") \
+  X(COAX_T5_DC, "coaxial_stacking.delta_theta_coax_5_c") \
+  X(COAX_T5_A, "coaxial_stacking.a_coax_5") \
+  X(COAX_T5_B, "coaxial_stacking.b_coax_5") \
+  X(COAX_T6_TH0, "coaxial_stacking.theta0_coax_6") \
+  X(COAX_T6_DSTAR, "coaxial_stacking.delta_theta_star_coax_6") \
+  X(COAX_T6_DC, "coaxial_stacking.delta_theta_coax_6_c") \
+  X(COAX_T6_A, "coaxial_stacking.a_coax_6") \
+  X(COAX_T6_B, "coaxial_stacking.b_coax_6") \
+  X(COAX_PHI3_XSTAR, "coaxial_stacking.cos_phi3_star_coax") \
+  X(COAX_PHI3_XC, "coaxial_stacking.cos_phi3_c_coax") \
+  X(COAX_PHI3_A, "coaxial_stacking.a_coax_3p") \
+  X(COAX_PHI3_B, "coaxial_stacking.b_cos_phi3_coax") \
+  X(COAX_PHI4_XSTAR, "coaxial_stacking.cos_phi4_star_coax") \
+  X(COAX_PHI4_XC, "coaxial_stacking.cos_phi4_c_coax") \
+  X(COAX_PHI4_A, "coaxial_stacking.a_coax_4p") \
+  X(COAX_PHI4_B, "coaxial_stacking.b_cos_phi4_coax") \
+  X(COAX_F6_A, "coaxial_stacking.a_coax_1_f6") \
+  X(COAX_F6_B, "coaxial_stacking.b_coax_1_f6") \
+  X(DEBYE_KAPPA, "debye.kappa") \
+  X(DEBYE_PREF, "debye.prefactor") \
+  X(DEBYE_SMOOTH, "debye.smoothing_coeff") \
+  X(DEBYE_RCUT, "debye.r_cut") \
+  X(DEBYE_RHIGH, "debye.r_high")
+
+enum mb_param_index {
+#define MB_X_ENUM(id, name) MB_P_##id,
+  MB_PARAM_LIST(MB_X_ENUM)
+#undef MB_X_ENUM
+  MB_P_COUNT_RAW
+};
+#define MB_P_COUNT 232 /* MB_P_COUNT_RAW (231) padded to a multiple of 8 */
+#define MB_MAX_BANKS 3
+enum mb_bank { MB_BANK_DNA = 0, MB_BANK_RNA = 1, MB_BANK_DRH = 2 };
+
+/* ---- model description (not differentiated; host memory, copied by value at launch) ---------------------- */
+typedef struct mb_flavour_geom {
+  double back[3];     /* backbone site  = c + back[0]*a1 + back[1]*a2 + back[2]*a3                          */
+  double back_stack;  /* a1 offset of the backbone site the stacking term uses when use_back_stack (oxDNA2) */
+  double stack;       /* stacking site  = c + stack*a1                                                      */
+  double base;        /* base (HB) site = c + base*a1                                                       */
+  double stack3[2];   /* RNA 3' stacking site = c + stack3[0]*a1 + stack3[1]*a2                             */
+  double stack5[2];   /* RNA 5' stacking site                                                               */
+  double p3[3];       /* RNA backbone direction vectors (a1,a2,a3 coefficients)                             */
+  double p5[3];
+  int32_t use_back_stack;
+  int32_t _pad;
+} mb_flavour_geom;
+
+enum mb_stack_form { MB_STACK_DNA = 0, MB_STACK_RNA = 1 };  /* theta4,5,6 | theta5,6,9,10                   */
+enum mb_cross_form { MB_CROSS_DNA1 = 0, MB_CROSS_RNA2 = 1 }; /* with | without the theta4 factor             */
+enum mb_coax_form { MB_COAX_DNA1 = 0, MB_COAX_DNA2 = 1 };    /* phi3,phi4 + f4(2pi-theta1) | f6(theta1)      */
+
+typedef struct mb_bank_forms {
+  int32_t stack_form, cross_form, coax_form, has_debye;
+} mb_bank_forms;
+
+typedef struct mb_model {
+  int32_t n_banks;            /* 1 (dna1, dna2, rna2) or 3 (na1: DNA, RNA, DRH)                              */
+  int32_t half_charged_ends;  /* Debye: halve the charge of strand-end nucleotides                           */
+  mb_flavour_geom geom[2];    /* [0] the only flavour, or DNA; [1] RNA (na1 only)                            */
+  mb_bank_forms forms[MB_MAX_BANKS];
+  double box[3];              /* periodic box; all zero = free space                                         */
+} mb_model;
+
+/* ---- energy / forces / parameter gradient ----------------------------------------------------------------- */
+typedef struct mb_energy_args {
+  const mb_model* model;
+  int32_t n;              /* nucleotides per frame                                                           */
+  int32_t n_frames;       /* F (1 for a single rigid body)                                                   */
+  const void* center;     /* (F,N,3)                                                                         */
+  const void* quat;       /* (F,N,4)                                                                         */
+  const int32_t* seq;     /* (N) 0..3                                                                        */
+  const int32_t* nt_type; /* (N) 1 = DNA, 2 = RNA; may be NULL when n_banks == 1                             */
+  const int32_t* nt_type_stack; /* (N) nt_type seen by the stacking term; NULL = nt_type                     */
+  const int32_t* is_end;  /* (N) strand-end flags; may be NULL when !half_charged_ends                       */
+  const int32_t* bonded;  /* (B,2)                                                                           */
+  int32_t n_bonded;
+  const int32_t* pairs;   /* (2,capacity) per list                                                           */
+  int64_t pair_capacity;
+  int64_t pair_frame_stride; /* elements between the lists of consecutive frames; 0 = one list for all frames */
+  const void* params;     /* (n_banks*MB_P_COUNT) reals                                                      */
+  const void* cot;        /* (F,8) cotangent / weight of each term; NULL = ones; used by the gradient outputs */
+  uint32_t term_mask;     /* which MB_TERM_* to evaluate                                                     */
+  uint32_t flags;         /* MB_FLAG_*                                                                       */
+  void* terms;            /* out (F,8), or NULL                                                              */
+  void* d_center;         /* out (F,N,3) = d(sum_t cot_t E_t)/d center, or NULL                              */
+  void* d_quat;           /* out (F,N,4), or NULL                                                            */
+  void* d_params;         /* out (n_banks*MB_P_COUNT) per row, or NULL                                       */
+  int64_t d_params_frame_stride; /* elements between rows of consecutive frames; 0 = one row summed over frames */
+} mb_energy_args;
+#define MB_FLAG_ACCUMULATE 0x1u /* add into the outputs instead of zeroing them first */
+
+int mythos_b200_energy_f64(void* cuda_stream, const mb_energy_args* a);
+int mythos_b200_energy_f32(void* cuda_stream, const mb_energy_args* a);
+
+/* ---- cell-list neighbour build -------------------------------------------------------------------------------
+ * Pair set (bit-exact contract): all i<j with i,j not listed in `bonded`, and
+ *   d2 = dx*dx + dy*dy + dz*dz < (r_cutoff + dr_threshold)^2   (strict, evaluated in the positions' dtype,
+ *   dx = xi - xj wrapped to [-L/2, L/2) when the box is periodic, no FMA contraction).
+ * Output per frame: pairs (2,capacity), sorted by i then j, padded with N; count = pairs found (may exceed
+ * capacity, in which case *overflow is set and the list is truncated -- jax_md's did_buffer_overflow). */
+typedef struct mb_nl_args {
+  int32_t n, n_frames;
+  const void* center;     /* (F,N,3) */
+  const int32_t* bonded;  /* (B,2) pairs to exclude */
+  int32_t n_bonded;
+  double box[3];
+  double r_cutoff, dr_threshold;
+  int32_t* pairs;         /* out (F,2,capacity) */
+  int64_t capacity;
+  int32_t* count;         /* out (F) */
+  int32_t* overflow;      /* out (1), OR-ed */
+  void* workspace;
+  size_t workspace_bytes;
+} mb_nl_args;
+size_t mythos_b200_nl_workspace_bytes(int32_t n, int32_t n_frames);
+int mythos_b200_nl_build_f64(void* cuda_stream, const mb_nl_args* a);
+int mythos_b200_nl_build_f32(void* cuda_stream, const mb_nl_args* a);
+
+/* ---- rigid-body Langevin (BAOAB) step -------------------------------------------------------------------------
+ * One call = B(dt/2) A(dt/2) O A(dt/2) on the state, i.e. everything of a step up to the force evaluation, or
+ * the closing B(dt/2) kick; the caller evaluates the new force (mythos_b200_energy_*) in between. */
+typedef struct mb_langevin_args {
+  int32_t n;
+  void* center;           /* (N,3) in/out */
+  void* quat;             /* (N,4) in/out */
+  void* p_center;         /* (N,3) linear momentum in/out */
+  void* p_quat;           /* (N,4) quaternion-conjugate momentum in/out */
+  const void* d_center;   /* (N,3) dE/dcenter at the current state */
+  const void* d_quat;     /* (N,4) dE/dquat   at the current state */
+  double dt, kT, gamma_center, gamma_quat, mass, inertia[3];
+  double box[3];
+  uint64_t seed, step;    /* counter-based RNG: noise = philox(seed, step, nucleotide) */
+  const void* noise;      /* optional (N,6) standard normals (3 linear + 3 angular) overriding the RNG */
+  int32_t phase;          /* 0 = B A O A (first part), 1 = closing B, 2 = closing B of the previous step fused with 0 */
+  int32_t _pad;
+} mb_langevin_args;
+int mythos_b200_langevin_f64(void* cuda_stream, const mb_langevin_args* a);
+int mythos_b200_langevin_f32(void* cuda_stream, const mb_langevin_args* a);
+
+/* ---- DiffTRe reweighting ------------------------------------------------------------------------------------- */
+typedef struct mb_weights_args {
+  int32_t n_frames;
+  const void* beta;        /* (F) 1/kT per frame */
+  const void* e_new;       /* (F) */
+  const void* e_ref;       /* (F) */
+  void* weights;           /* out (F) softmax(-beta (e_new - e_ref)) */
+  void* sums;              /* out (4): max exponent, sum exp, sum w ln w, n_eff */
+} mb_weights_args;
+int mythos_b200_weights_neff_f64(void* cuda_stream, const mb_weights_args* a);
+int mythos_b200_weights_neff_f32(void* cuda_stream, const mb_weights_args* a);
+
+/* ---- introspection ------------------------------------------------------------------------------------------- */
+int mythos_b200_abi_version(void);
+int mythos_b200_param_count(void);                 /* MB_P_COUNT                              */
+const char* mythos_b200_param_name(int index);     /* "<term>.<name>" or NULL                 */
+int mythos_b200_param_index(const char* name);     /* -1 if unknown                           */
+const char* mythos_b200_last_error(void);          /* thread-local message of the last failure */
+size_t mythos_b200_sizeof_model(void);
+size_t mythos_b200_sizeof_energy_args(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MYTHOS_B200_H */

@@ -1,0 +1,266 @@
+// energy_kernels.cu -- fused per-pair energy / force / parameter-gradient kernels and their C-ABI entry.
+//
+// Launch shape: grid = (pair blocks, frames).  One thread owns one listed pair and evaluates every enabled term
+// of that pair in one pass from the two nucleotides' (center, quaternion) -- the body axes and interaction
+// sites are rebuilt in registers, never materialised in HBM (the reference re-derives and stores them once
+// per term, mythos/energy/base.py:205-208).  Per-term energies are reduced warp -> block -> one atomic per
+// block and term; nucleotide gradients go out as (dE/dcenter, dE/dquat) atomics; parameter gradients are
+// warp-reduced into a shared-memory bank image and flushed once per block.
+#include "common.cuh"
+#include "oxdna_device.cuh"
+
+namespace mb {
+
+constexpr int kBlock = 128;
+constexpr unsigned kFull = 0xffffffffu;
+
+template <class T>
+struct EnergyDev {
+  ModelT<T> M;
+  int n, n_frames, n_bonded;
+  const T* center;
+  const T* quat;
+  const int32_t* seq;
+  const int32_t* nt_type;
+  const int32_t* nt_type_stack;
+  const int32_t* is_end;
+  const int32_t* bonded;
+  const int32_t* pairs;
+  long long pair_capacity, pair_frame_stride;
+  const T* params;
+  const T* cot;
+  unsigned mask;
+  T* terms;
+  T* d_center;
+  T* d_quat;
+  T* d_params;
+  long long d_params_frame_stride;
+};
+
+// Parameter-gradient accumulator: warp-reduce, then one shared-memory atomic per warp and parameter.
+// With several banks (NA1) lanes of one warp may address different banks, so those go out as per-lane
+// shared atomics instead.
+template <class T>
+struct SmemAcc {
+  T* sh;
+  bool per_lane;
+  __device__ __forceinline__ void add(int bank, int idx, T v) {
+    if (per_lane) {
+      if (v != T(0)) atomicAdd(&sh[bank * MB_P_COUNT + idx], v);
+      return;
+    }
+    if (!__any_sync(kFull, v != T(0))) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sh[idx], v);
+  }
+  __device__ __forceinline__ void add_scatter(int bank, int idx, T v, bool pred) {
+    if (pred && v != T(0)) atomicAdd(&sh[bank * MB_P_COUNT + idx], v);
+  }
+};
+
+template <class T>
+__device__ __forceinline__ Nuc<T> load_nuc(const T* __restrict__ center, const T* __restrict__ quat, long long idx,
+                                           T q[4]) {
+  Nuc<T> n;
+  n.c = v3<T>(center[3 * idx], center[3 * idx + 1], center[3 * idx + 2]);
+  q[0] = quat[4 * idx];
+  q[1] = quat[4 * idx + 1];
+  q[2] = quat[4 * idx + 2];
+  q[3] = quat[4 * idx + 3];
+  axes_from_quat(q[0], q[1], q[2], q[3], n.a1, n.a2, n.a3);
+  return n;
+}
+
+template <class T>
+__device__ __forceinline__ void scatter_nuc_grad(const EnergyDev<T>& a, long long idx, const NucGrad<T>& g,
+                                                 const T q[4]) {
+  if (a.d_center) {
+    atomicAdd(&a.d_center[3 * idx], g.c.x);
+    atomicAdd(&a.d_center[3 * idx + 1], g.c.y);
+    atomicAdd(&a.d_center[3 * idx + 2], g.c.z);
+  }
+  if (a.d_quat) {
+    T dq[4];
+    quat_grad(g, q[0], q[1], q[2], q[3], dq);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) atomicAdd(&a.d_quat[4 * idx + c], dq[c]);
+  }
+}
+
+// block-reduce the 8 per-term energies and add them to terms[frame]
+template <class T>
+__device__ __forceinline__ void reduce_terms(T e[MB_N_TERMS], T* sE, T* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < MB_N_TERMS; ++t) {
+    T v = e[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    if (lane == 0) sE[warp * MB_N_TERMS + t] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < MB_N_TERMS && out) {
+    T v = 0;
+    for (int w = 0; w < kBlock / 32; ++w) v += sE[w * MB_N_TERMS + threadIdx.x];
+    if (v != T(0)) atomicAdd(&out[threadIdx.x], v);
+  }
+}
+
+template <class T, bool WF, bool WP, bool BONDED>
+__global__ void __launch_bounds__(kBlock) k_pairs(const EnergyDev<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int np = a.M.n_banks * MB_P_COUNT;
+  T* sP = reinterpret_cast<T*>(smem_raw);
+  T* sE = sP + np;
+  T* sAcc = sE + (kBlock / 32) * MB_N_TERMS;
+  for (int k = threadIdx.x; k < np; k += kBlock) {
+    sP[k] = a.params[k];
+    if (WP) sAcc[k] = T(0);
+  }
+  __syncthreads();
+
+  const int frame = blockIdx.y;
+  const long long k = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const long long fbase = (long long)frame * a.n;
+  int i = 0, j = 0;
+  bool valid;
+  if (BONDED) {
+    valid = k < a.n_bonded;
+    if (valid) {
+      i = a.bonded[2 * k];
+      j = a.bonded[2 * k + 1];
+    }
+  } else {
+    valid = k < a.pair_capacity;
+    if (valid) {
+      const int32_t* pl = a.pairs + (long long)frame * a.pair_frame_stride;
+      i = pl[k];
+      j = pl[a.pair_capacity + k];
+      valid = (i >= 0 && j >= 0 && i < a.n && j < a.n);
+      if (!valid) i = j = 0;
+    }
+  }
+  T cot[MB_N_TERMS];
+#pragma unroll
+  for (int t = 0; t < MB_N_TERMS; ++t) cot[t] = a.cot ? a.cot[(long long)frame * MB_N_TERMS + t] : T(1);
+
+  T e[MB_N_TERMS];
+#pragma unroll
+  for (int t = 0; t < MB_N_TERMS; ++t) e[t] = T(0);
+  T qi[4], qj[4];
+  const Nuc<T> ni = load_nuc(a.center, a.quat, fbase + i, qi);
+  const Nuc<T> nj = load_nuc(a.center, a.quat, fbase + j, qj);
+  NucGrad<T> Gi, Gj;
+  Gi.zero();
+  Gj.zero();
+  SmemAcc<T> acc{sAcc, a.M.n_banks > 1};
+  const int nti = a.nt_type ? a.nt_type[i] : 1, ntj = a.nt_type ? a.nt_type[j] : 1;
+  if (BONDED) {
+    const int32_t* snt = a.nt_type_stack ? a.nt_type_stack : a.nt_type;
+    const int si = snt ? snt[i] : 1, sj = snt ? snt[j] : 1;
+    bonded_pair<T, WF, WP>(a.M, sP, valid, ni, nj, a.seq[i], a.seq[j], nti, ntj, si, sj, a.mask, cot, e, Gi, Gj, acc);
+  } else {
+    T m = T(1);
+    if (a.M.half_charged_ends && a.is_end) m = (a.is_end[i] ? T(0.5) : T(1)) * (a.is_end[j] ? T(0.5) : T(1));
+    unbonded_pair<T, WF, WP>(a.M, sP, valid, ni, nj, a.seq[i], a.seq[j], nti, ntj, m, a.mask, cot, e, Gi, Gj, acc);
+  }
+  if (WF && valid) {
+    scatter_nuc_grad(a, fbase + i, Gi, qi);
+    scatter_nuc_grad(a, fbase + j, Gj, qj);
+  }
+  reduce_terms(e, sE, a.terms ? a.terms + (long long)frame * MB_N_TERMS : nullptr);
+  if (WP) {
+    __syncthreads();
+    T* out = a.d_params + (long long)frame * a.d_params_frame_stride;
+    for (int p = threadIdx.x; p < np; p += kBlock) {
+      const T v = sAcc[p];
+      if (v != T(0)) atomicAdd(&out[p], v);
+    }
+  }
+}
+
+template <class T, bool WF, bool WP>
+static int launch_pairs(cudaStream_t s, const EnergyDev<T>& a) {
+  const size_t smem = sizeof(T) * (size_t)(a.M.n_banks * MB_P_COUNT * (WP ? 2 : 1) + (kBlock / 32) * MB_N_TERMS);
+  if ((a.mask & MB_BONDED_TERMS) && a.n_bonded > 0) {
+    dim3 grid(ceil_div(a.n_bonded, kBlock), a.n_frames);
+    k_pairs<T, WF, WP, true><<<grid, kBlock, smem, s>>>(a);
+    MB_CUDA_CHECK(cudaGetLastError());
+  }
+  if ((a.mask & MB_UNBONDED_TERMS) && a.pair_capacity > 0) {
+    dim3 grid(ceil_div(a.pair_capacity, kBlock), a.n_frames);
+    k_pairs<T, WF, WP, false><<<grid, kBlock, smem, s>>>(a);
+    MB_CUDA_CHECK(cudaGetLastError());
+  }
+  return MB_OK;
+}
+
+template <class T>
+static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
+  MB_REQUIRE(x && x->model, MB_EINVAL_SHAPE, "energy: null args / model");
+  const mb_model& m = *x->model;
+  MB_REQUIRE(m.n_banks == 1 || m.n_banks == 3, MB_EINVAL_MODEL, "energy: n_banks must be 1 or 3");
+  MB_REQUIRE(x->n > 0 && x->n_frames > 0, MB_EINVAL_SHAPE, "energy: n and n_frames must be positive");
+  MB_REQUIRE(x->n_frames <= 65535, MB_EINVAL_SHAPE, "energy: at most 65535 frames per call");
+  MB_REQUIRE(x->center && x->quat && x->seq && x->params, MB_EINVAL_SHAPE, "energy: center/quat/seq/params required");
+  MB_REQUIRE(m.n_banks == 1 || x->nt_type, MB_EINVAL_SHAPE, "energy: nt_type required for the 3-bank (NA1) model");
+  MB_REQUIRE(x->n_bonded == 0 || x->bonded, MB_EINVAL_SHAPE, "energy: bonded list missing");
+  MB_REQUIRE(x->pair_capacity == 0 || x->pairs, MB_EINVAL_SHAPE, "energy: pair list missing");
+  MB_REQUIRE(x->terms || x->d_center || x->d_quat || x->d_params, MB_EINVAL_SHAPE, "energy: no output requested");
+  for (int b = 0; b < m.n_banks; ++b) {
+    MB_REQUIRE(m.forms[b].stack_form >= 0 && m.forms[b].stack_form <= 1 && m.forms[b].cross_form >= 0 &&
+                   m.forms[b].cross_form <= 1 && m.forms[b].coax_form >= 0 && m.forms[b].coax_form <= 1,
+               MB_EINVAL_MODEL, "energy: unknown term form");
+  }
+  EnergyDev<T> a;
+  a.M.load(m);
+  a.n = x->n;
+  a.n_frames = x->n_frames;
+  a.n_bonded = x->n_bonded;
+  a.center = static_cast<const T*>(x->center);
+  a.quat = static_cast<const T*>(x->quat);
+  a.seq = x->seq;
+  a.nt_type = x->nt_type;
+  a.nt_type_stack = x->nt_type_stack;
+  a.is_end = x->is_end;
+  a.bonded = x->bonded;
+  a.pairs = x->pairs;
+  a.pair_capacity = x->pair_capacity;
+  a.pair_frame_stride = x->pair_frame_stride;
+  a.params = static_cast<const T*>(x->params);
+  a.cot = static_cast<const T*>(x->cot);
+  a.mask = x->term_mask;
+  a.terms = static_cast<T*>(x->terms);
+  a.d_center = static_cast<T*>(x->d_center);
+  a.d_quat = static_cast<T*>(x->d_quat);
+  a.d_params = static_cast<T*>(x->d_params);
+  a.d_params_frame_stride = x->d_params_frame_stride;
+
+  const size_t np = (size_t)m.n_banks * MB_P_COUNT;
+  if (!(x->flags & MB_FLAG_ACCUMULATE)) {
+    const size_t F = x->n_frames, N = x->n;
+    if (a.terms) MB_CUDA_CHECK(cudaMemsetAsync(a.terms, 0, sizeof(T) * F * MB_N_TERMS, s));
+    if (a.d_center) MB_CUDA_CHECK(cudaMemsetAsync(a.d_center, 0, sizeof(T) * F * N * 3, s));
+    if (a.d_quat) MB_CUDA_CHECK(cudaMemsetAsync(a.d_quat, 0, sizeof(T) * F * N * 4, s));
+    if (a.d_params) {
+      const size_t rows = x->d_params_frame_stride ? F : 1;
+      const size_t stride = x->d_params_frame_stride ? (size_t)x->d_params_frame_stride : np;
+      MB_CUDA_CHECK(cudaMemsetAsync(a.d_params, 0, sizeof(T) * ((rows - 1) * stride + np), s));
+    }
+  }
+  const bool wf = a.d_center || a.d_quat, wp = a.d_params != nullptr;
+  if (wf && wp) return launch_pairs<T, true, true>(s, a);
+  if (wf) return launch_pairs<T, true, false>(s, a);
+  if (wp) return launch_pairs<T, false, true>(s, a);
+  return launch_pairs<T, false, false>(s, a);
+}
+
+}  // namespace mb
+
+extern "C" int mythos_b200_energy_f64(void* stream, const mb_energy_args* a) {
+  return mb::energy_impl<double>(static_cast<cudaStream_t>(stream), a);
+}
+extern "C" int mythos_b200_energy_f32(void* stream, const mb_energy_args* a) {
+  return mb::energy_impl<float>(static_cast<cudaStream_t>(stream), a);
+}

@@ -1,0 +1,216 @@
+// langevin.cu -- fused rigid-body Langevin (BAOAB) step, one thread per nucleotide, state kept in registers.
+//
+// Stands in for the step_fn of jax_md.simulate.nvt_langevin specialised to jax_md.rigid_body.RigidBody
+// (third party, jax_md==0.2.28, not vendored in the reference; call site mythos/simulators/jax_md/jaxmd.py:73,82-94).
+// The algorithm restated here:
+//   B  p_c -= h * dE/dc ;  p_q -= h * dE/dq                       (force = -grad E, h = dt/2)
+//   A  c  <- shift(c, h * p_c / m);  quaternion free-rotor splitting (Miller et al. 2002): rotations about the
+//      body axes in the order 3,2,1,2,3 with steps h/2,h/2,h,h/2,h/2 and angle zeta_k = step * (p . P_k q)/(4 I_k)
+//   O  p_c <- c1 p_c + sqrt(kT (1-c1^2) m) xi;   L = (S(q)^T p)/2 (body-frame angular momentum, 3 components)
+//      L_k <- c1' L_k + sqrt(kT (1-c1'^2) I_k) xi_k;  p_q <- 2 S(q) [0, L]
+// Noise: counter-based Philox4x32-10 keyed by (seed, step, nucleotide), Box-Muller; or caller-injected normals
+// (used by the parity tests, since jax's threefry stream cannot be reproduced).
+#include "common.cuh"
+
+namespace mb {
+
+struct Philox {
+  uint32_t c[4], k[2];
+  __device__ __forceinline__ void round_() {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+    c[0] = n0;
+    c[1] = n1;
+    c[2] = n2;
+    c[3] = n3;
+  }
+  __device__ __forceinline__ void run() {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      round_();
+      k[0] += 0x9E3779B9u;
+      k[1] += 0xBB67AE85u;
+    }
+  }
+};
+
+// six standard normals for (seed, step, nucleotide)
+__device__ __forceinline__ void normals6(uint64_t seed, uint64_t step, uint32_t idx, double z[6]) {
+  uint32_t u[8];
+  for (int blk = 0; blk < 2; ++blk) {
+    Philox p;
+    p.c[0] = idx;
+    p.c[1] = uint32_t(step);
+    p.c[2] = uint32_t(step >> 32);
+    p.c[3] = uint32_t(blk);
+    p.k[0] = uint32_t(seed);
+    p.k[1] = uint32_t(seed >> 32);
+    p.run();
+    for (int k = 0; k < 4; ++k) u[4 * blk + k] = p.c[k];
+  }
+  // 3 Box-Muller pairs from 6 of the 8 words (53-bit mantissas are not needed for thermal noise)
+  for (int k = 0; k < 3; ++k) {
+    const double u1 = (double(u[2 * k]) + 1.0) * (1.0 / 4294967296.0);  // (0,1]
+    const double u2 = double(u[2 * k + 1]) * (1.0 / 4294967296.0);
+    const double r = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    z[2 * k] = r * c;
+    z[2 * k + 1] = r * s;
+  }
+}
+
+template <class T>
+struct LangevinDev {
+  int n, phase;
+  T* center;
+  T* quat;
+  T* p_center;
+  T* p_quat;
+  const T* d_center;
+  const T* d_quat;
+  const T* noise;
+  T dt, kT, gamma_c, gamma_q, mass, inertia[3], box[3];
+  uint64_t seed, step;
+};
+
+template <class T>
+__device__ __forceinline__ void perm(int k, const T q[4], T o[4]) {
+  // P_k q = column k of S(q)
+  if (k == 1) {
+    o[0] = -q[1]; o[1] = q[0]; o[2] = q[3]; o[3] = -q[2];
+  } else if (k == 2) {
+    o[0] = -q[2]; o[1] = -q[3]; o[2] = q[0]; o[3] = q[1];
+  } else {
+    o[0] = -q[3]; o[1] = q[2]; o[2] = -q[1]; o[3] = q[0];
+  }
+}
+template <class T>
+__device__ __forceinline__ void free_rotor(int k, T step, T Ik, T q[4], T p[4]) {
+  T pq[4], pp[4];
+  perm(k, q, pq);
+  perm(k, p, pp);
+  const T zeta = step * (p[0] * pq[0] + p[1] * pq[1] + p[2] * pq[2] + p[3] * pq[3]) / (T(4) * Ik);
+  T s, c;
+  sincos(zeta, &s, &c);
+  for (int a = 0; a < 4; ++a) {
+    q[a] = c * q[a] + s * pq[a];
+    p[a] = c * p[a] + s * pp[a];
+  }
+}
+
+template <class T>
+__device__ __forceinline__ T shift1(T x, T L) {
+  if (L > T(0)) {
+    x = fmod(x, L);
+    if (x < T(0)) x += L;
+  }
+  return x;
+}
+
+template <class T>
+__global__ void k_langevin(LangevinDev<T> a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  T c[3], q[4], pc[3], pq[4];
+  for (int d = 0; d < 3; ++d) {
+    c[d] = a.center[3 * i + d];
+    pc[d] = a.p_center[3 * i + d];
+  }
+  for (int d = 0; d < 4; ++d) {
+    q[d] = a.quat[4 * i + d];
+    pq[d] = a.p_quat[4 * i + d];
+  }
+  const T h = T(0.5) * a.dt;
+  // B: phase 0 and 1 kick by dt/2, phase 2 (closing kick of the previous step + opening kick of this one) by dt
+  const T kick = (a.phase == 2) ? a.dt : h;
+  for (int d = 0; d < 3; ++d) pc[d] -= kick * a.d_center[3 * i + d];
+  for (int d = 0; d < 4; ++d) pq[d] -= kick * a.d_quat[4 * i + d];
+  if (a.phase != 1) {
+    for (int half = 0; half < 2; ++half) {
+      // A(dt/2)
+      for (int d = 0; d < 3; ++d) c[d] = shift1(c[d] + h * pc[d] / a.mass, a.box[d]);
+      free_rotor(3, T(0.5) * h, a.inertia[2], q, pq);
+      free_rotor(2, T(0.5) * h, a.inertia[1], q, pq);
+      free_rotor(1, h, a.inertia[0], q, pq);
+      free_rotor(2, T(0.5) * h, a.inertia[1], q, pq);
+      free_rotor(3, T(0.5) * h, a.inertia[2], q, pq);
+      if (half == 0) {
+        // O(dt)
+        double z[6];
+        if (a.noise) {
+          for (int k = 0; k < 6; ++k) z[k] = double(a.noise[6 * i + k]);
+        } else {
+          normals6(a.seed, a.step, uint32_t(i), z);
+        }
+        const T c1 = exp(-a.gamma_c * a.dt);
+        const T c2 = sqrt(a.kT * (T(1) - c1 * c1) * a.mass);
+        for (int d = 0; d < 3; ++d) pc[d] = c1 * pc[d] + c2 * T(z[d]);
+        const T r1 = exp(-a.gamma_q * a.dt);
+        T L[3];
+        for (int k = 1; k <= 3; ++k) {
+          T pk[4];
+          perm(k, q, pk);
+          const T Lk = T(0.5) * (pq[0] * pk[0] + pq[1] * pk[1] + pq[2] * pk[2] + pq[3] * pk[3]);
+          L[k - 1] = r1 * Lk + sqrt(a.kT * (T(1) - r1 * r1) * a.inertia[k - 1]) * T(z[2 + k]);
+        }
+        // p = 2 S(q) [0, L] = 2 sum_k L_k P_k q
+        for (int d = 0; d < 4; ++d) pq[d] = T(0);
+        for (int k = 1; k <= 3; ++k) {
+          T pk[4];
+          perm(k, q, pk);
+          for (int d = 0; d < 4; ++d) pq[d] += T(2) * L[k - 1] * pk[d];
+        }
+      }
+    }
+    for (int d = 0; d < 3; ++d) a.center[3 * i + d] = c[d];
+    for (int d = 0; d < 4; ++d) a.quat[4 * i + d] = q[d];
+  }
+  for (int d = 0; d < 3; ++d) a.p_center[3 * i + d] = pc[d];
+  for (int d = 0; d < 4; ++d) a.p_quat[4 * i + d] = pq[d];
+}
+
+template <class T>
+static int langevin_impl(cudaStream_t s, const mb_langevin_args* x) {
+  MB_REQUIRE(x && x->n > 0, MB_EINVAL_SHAPE, "langevin: bad n");
+  MB_REQUIRE(x->center && x->quat && x->p_center && x->p_quat && x->d_center && x->d_quat, MB_EINVAL_SHAPE,
+             "langevin: missing state buffers");
+  MB_REQUIRE(x->phase >= 0 && x->phase <= 2, MB_EINVAL_SHAPE, "langevin: phase must be 0, 1 or 2");
+  MB_REQUIRE(x->mass > 0 && x->inertia[0] > 0 && x->inertia[1] > 0 && x->inertia[2] > 0, MB_EINVAL_SHAPE,
+             "langevin: mass and inertia must be positive");
+  LangevinDev<T> a;
+  a.n = x->n;
+  a.phase = x->phase;
+  a.center = static_cast<T*>(x->center);
+  a.quat = static_cast<T*>(x->quat);
+  a.p_center = static_cast<T*>(x->p_center);
+  a.p_quat = static_cast<T*>(x->p_quat);
+  a.d_center = static_cast<const T*>(x->d_center);
+  a.d_quat = static_cast<const T*>(x->d_quat);
+  a.noise = static_cast<const T*>(x->noise);
+  a.dt = T(x->dt);
+  a.kT = T(x->kT);
+  a.gamma_c = T(x->gamma_center);
+  a.gamma_q = T(x->gamma_quat);
+  a.mass = T(x->mass);
+  for (int d = 0; d < 3; ++d) {
+    a.inertia[d] = T(x->inertia[d]);
+    a.box[d] = T(x->box[d]);
+  }
+  a.seed = x->seed;
+  a.step = x->step;
+  k_langevin<T><<<ceil_div(x->n, 128), 128, 0, s>>>(a);
+  MB_CUDA_CHECK(cudaGetLastError());
+  return MB_OK;
+}
+
+}  // namespace mb
+
+extern "C" int mythos_b200_langevin_f64(void* stream, const mb_langevin_args* a) {
+  return mb::langevin_impl<double>(static_cast<cudaStream_t>(stream), a);
+}
+extern "C" int mythos_b200_langevin_f32(void* stream, const mb_langevin_args* a) {
+  return mb::langevin_impl<float>(static_cast<cudaStream_t>(stream), a);
+}

@@ -1,0 +1,233 @@
+"""From a list of energy-term objects to one fused kernel launch: model description, parameter bank, device inputs.
+
+The reference gives every term its own traced sub-graph (``mythos/energy/base.py:312-314``).  Here the terms of a
+composition are folded into a ``Plan``:
+
+* ``mb_model`` -- flavour geometry (from the term's ``transform_fn``), per-bank functional forms (from the term
+  classes), box (from ``displacement_fn``), half-charged-ends flag (from the Debye configuration);
+* the kernel-level parameter bank(s) -- every configuration packed by name into the ``MB_PARAM_LIST`` order; the
+  pack is a ``torch.stack`` of the configuration's scalars so autograd chains d/dparams back to theta;
+* int32 device copies of ``seq``, bonds, ``nt_type``, ``is_end`` and the unbonded pair list (cached per device).
+"""
+
+from __future__ import annotations
+
+import dataclasses as dc
+import re
+from functools import lru_cache
+from typing import Any
+
+import torch
+
+from mythos_b200 import _lib, space
+from mythos_b200.energy import functional
+from mythos_b200.energy.base_smoothing_functions import as_t
+
+STACK_DNA, STACK_RNA = 0, 1
+CROSS_DNA1, CROSS_RNA2 = 0, 1
+COAX_DNA1, COAX_DNA2 = 0, 1
+BANKS = ("dna", "rna", "drh")
+
+
+# --------------------------------------------------------------------------------------------- bank layout
+@lru_cache(maxsize=1)
+def bank_layout() -> dict[str, list[tuple[int, str, tuple[int, int] | None]]]:
+    """term -> [(bank index, configuration field, (row, col) or None)] parsed from the library's name table."""
+    out: dict[str, list] = {}
+    pat = re.compile(r"^([a-z_]+)\.([A-Za-z0-9_]+)(?:\[(\d),(\d)\])?$")
+    for idx, name in enumerate(_lib.param_names()):
+        m = pat.match(name)
+        if not m:
+            raise _lib.MythosB200Error(f"unparseable kernel parameter name {name!r}")
+        sub = (int(m.group(3)), int(m.group(4))) if m.group(3) is not None else None
+        out.setdefault(m.group(1), []).append((idx, m.group(2), sub))
+    return out
+
+
+def pack_bank(configs: list[Any]) -> torch.Tensor:
+    """One parameter bank (P,) float64 on the host from initialised term configurations (missing slots = 0)."""
+    P = _lib.param_count()
+    zero = torch.zeros((), dtype=torch.float64)
+    vals = [zero] * P
+    layout = bank_layout()
+    for cfg in configs:
+        for idx, field, sub in layout.get(cfg.term, ()):
+            v = getattr(cfg, field, None) if field in cfg else None
+            if v is None:
+                continue
+            v = as_t(v).to(torch.float64)
+            vals[idx] = v[sub] if sub is not None else v.reshape(())
+    return torch.stack(vals)
+
+
+# --------------------------------------------------------------------------------------------- geometry
+def geometry_of(transform_fn) -> tuple[str, list[_lib.FlavourGeom]]:
+    """(kind, flavour geometries) of a ``functools.partial(Nucleotide.from_rigid_body, **constants)``."""
+    func = getattr(transform_fn, "func", transform_fn)
+    cls = getattr(func, "nucleotide_cls", None)
+    if cls is None:
+        raise _lib.MythosB200Error(
+            "transform_fn must be functools.partial(<Nucleotide>.from_rigid_body, ...) of a mythos_b200 nucleotide class"
+        )
+    kw = dict(getattr(transform_fn, "keywords", {}) or {})
+    return cls.KIND, cls.kernel_geometry(**{k: float(as_t(v)) for k, v in kw.items()})
+
+
+# --------------------------------------------------------------------------------------------- caches
+_TOPO_CACHE: dict[tuple, tuple[tuple, Any]] = {}
+
+
+def _cached(key: tuple, keep: tuple, make):
+    hit = _TOPO_CACHE.get(key)
+    if hit is not None and all(a is b for a, b in zip(hit[0], keep)):
+        return hit[1]
+    if len(_TOPO_CACHE) > 64:
+        _TOPO_CACHE.pop(next(iter(_TOPO_CACHE)))
+    val = make()
+    _TOPO_CACHE[key] = (keep, val)
+    return val
+
+
+def device_pairs(pairs, device) -> torch.Tensor | None:
+    """(2,U) or (F,2,U) int32 on the device; accepts numpy / lists / tensors, (U,2) is NOT transposed here."""
+    if pairs is None:
+        return None
+    if isinstance(pairs, torch.Tensor) and pairs.device == device and pairs.dtype == torch.int32 and pairs.is_contiguous():
+        return pairs
+    return _cached(("pairs", id(pairs), str(device)), (pairs,), lambda: functional._as_i32(pairs, device))
+
+
+# --------------------------------------------------------------------------------------------- plan
+@dc.dataclass
+class Plan:
+    fns: list
+    model: _lib.Model
+    term_mask: int
+    hybrid: bool
+
+    def params_vector(self) -> torch.Tensor:
+        """(n_banks*P,) float64 host vector, differentiable w.r.t. any tensor inside the configurations."""
+        if not self.hybrid:
+            return pack_bank([fn.params for fn in self.fns])
+        banks = []
+        for b in BANKS:
+            cfgs = [getattr(fn.params, f"{b}_config") for fn in self.fns if f"{b}_config" in fn.params]
+            banks.append(pack_bank([c for c in cfgs if c is not None]))
+        return torch.cat(banks)
+
+    def device_params(self, device, dtype) -> torch.Tensor:
+        vec = self.params_vector()
+        if vec.requires_grad:
+            return vec.to(device=device, dtype=dtype)
+        key = ("params", tuple(id(fn.params) for fn in self.fns), str(device), str(dtype))
+        return _cached(key, tuple(fn.params for fn in self.fns), lambda: vec.to(device=device, dtype=dtype))
+
+    def topology(self, n: int, device) -> functional.DeviceTopology:
+        f0 = self.fns[0]
+        extra: dict[str, Any] = {}
+        for fn in self.fns:
+            for k, v in fn.extra_topology().items():
+                extra.setdefault(k, v)
+        # the stacking term may carry its own nt_type (na1/tests/test_integration.py:252 does exactly that)
+        stack_nt = None
+        for fn in self.fns:
+            if fn.TERM == 2 and "nt_type" in fn.params and fn.params.nt_type is not None:
+                stack_nt = fn.params.nt_type
+        keep = (f0.seq, f0.bonded_neighbors, extra.get("nt_type"), stack_nt, extra.get("is_end"))
+        key = ("topo", tuple(id(k) for k in keep), str(device))
+        return _cached(
+            key,
+            keep,
+            lambda: functional.make_device_topology(
+                n, f0.seq, f0.bonded_neighbors, device, nt_type=extra.get("nt_type"), nt_type_stack=stack_nt,
+                is_end=extra.get("is_end"),
+            ),
+        )
+
+    def pairs(self, device) -> torch.Tensor | None:
+        if not (self.term_mask & _lib.UNBONDED_TERMS):
+            return None
+        ub = next(fn.unbonded_neighbors for fn in self.fns if fn.TERM >= 3)
+        return device_pairs(ub, device)
+
+    def evaluate(self, center: torch.Tensor, quat: torch.Tensor) -> torch.Tensor:
+        """(F,8) per-term energies; differentiable in center, quat and the configurations' tensors."""
+        _lib.require_cuda(center, "RigidBody.center")
+        dev, dtype = center.device, center.dtype
+        topo = self.topology(center.shape[1], dev)
+        pairs = self.pairs(dev)
+        stride = 0
+        if pairs is not None and pairs.dim() == 3:
+            stride = 2 * pairs.shape[-1]
+        return functional.energy_terms(
+            self.model, topo, center, quat, self.device_params(dev, dtype), pairs, self.term_mask, stride
+        )
+
+
+def _prop_key(fn) -> tuple:
+    box = space.box_of(fn.displacement_fn)
+    return (id(getattr(fn.transform_fn, "func", fn.transform_fn)), tuple(sorted((getattr(fn.transform_fn, "keywords", {}) or {}).items(), key=lambda kv: kv[0])).__repr__(), box, id(fn.seq), id(fn.bonded_neighbors), id(fn.unbonded_neighbors), fn.HYBRID)
+
+
+def fusable_groups(fns: list) -> list[list[int]]:
+    """Partition term indices into groups that can share one fused launch (same inputs, distinct kernel terms)."""
+    groups: list[tuple[tuple, set, list[int]]] = []
+    for k, fn in enumerate(fns):
+        key = _prop_key(fn)
+        for gkey, used, members in groups:
+            if gkey == key and fn.TERM not in used:
+                used.add(fn.TERM)
+                members.append(k)
+                break
+        else:
+            groups.append((key, {fn.TERM}, [k]))
+    return [g[2] for g in groups]
+
+
+def plan_for(fns: list) -> Plan:
+    """Build the launch plan of a fusable group of term objects."""
+    f0 = fns[0]
+    if f0.transform_fn is None:
+        raise _lib.MythosB200Error("energy functions need transform_fn (the nucleotide geometry) to run")
+    kind, geoms = geometry_of(f0.transform_fn)
+    hybrid = any(fn.HYBRID for fn in fns)
+    if hybrid != all(fn.HYBRID for fn in fns):
+        raise _lib.MythosB200Error("cannot mix NA1 (hybrid) and single-model terms in one launch")
+    if hybrid and kind != "na1":
+        raise _lib.MythosB200Error("NA1 terms need the HybridNucleotide transform_fn")
+    m = _lib.Model()
+    m.n_banks = 3 if hybrid else 1
+    for k, g in enumerate(geoms[:2]):
+        m.geom[k] = g
+    box = space.box_of(f0.displacement_fn)
+    for d in range(3):
+        m.box[d] = box[d]
+    mask = 0
+    for fn in fns:
+        if fn.TERM < 0:
+            raise _lib.MythosB200Error(f"{type(fn).__name__} has no kernel term")
+        mask |= 1 << fn.TERM
+    if hybrid:
+        forms = (
+            (STACK_DNA, CROSS_DNA1, COAX_DNA2),  # DNA bank: dna2 stacking / dna1 cross / dna2 coax (na1/*.py)
+            (STACK_RNA, CROSS_RNA2, COAX_DNA1),  # RNA bank
+            (STACK_DNA, CROSS_DNA1, COAX_DNA1),  # hybrid bank (no bonded terms)
+        )
+        for b, (s, c, x) in enumerate(forms):
+            m.forms[b].stack_form, m.forms[b].cross_form, m.forms[b].coax_form, m.forms[b].has_debye = s, c, x, 1
+        m.geom[0].use_back_stack = 1  # na1 stacking uses dna2.Stacking for the DNA bank (na1/stacking.py:203)
+    else:
+        form = {"stack_form": STACK_DNA, "cross_form": CROSS_DNA1, "coax_form": COAX_DNA1, "use_back_stack": 0}
+        for fn in fns:
+            form.update(fn.FORM)
+        m.forms[0].stack_form = form["stack_form"]
+        m.forms[0].cross_form = form["cross_form"]
+        m.forms[0].coax_form = form["coax_form"]
+        m.forms[0].has_debye = 1 if mask & (1 << 7) else 0
+        m.geom[0].use_back_stack = 1 if (form["use_back_stack"] and kind == "dna2") else 0
+    hce = 0
+    for fn in fns:
+        if fn.TERM == 7:
+            hce = 1 if bool(fn.params.half_charged_ends) else 0
+    m.half_charged_ends = hce
+    return Plan(fns=list(fns), model=m, term_mask=mask, hybrid=hybrid)
