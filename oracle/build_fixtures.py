@@ -189,6 +189,7 @@ def main() -> int:
             payload.update(read_seq_dep(base / extra["seq_dep"]))
         np.savez_compressed(OUT / f"{name}.npz", **payload)
         print(f"{name}: frames={nf} N={center.shape[1]} box={box}")
+
     return 0
 
 
