@@ -426,6 +426,11 @@ typedef struct mb_weights_args {
 int mythos_b200_weights_neff_f64(void* cuda_stream, const mb_weights_args* a);
 int mythos_b200_weights_neff_f32(void* cuda_stream, const mb_weights_args* a);
 
+/* ---- roofline denominators: FMA issue-rate micro-benchmark (blocks x 256 threads x iters x 8 FMA); time it with
+ * CUDA events on `cuda_stream`; flops = blocks*256*iters*16.  scratch: blocks*256 reals. */
+int mythos_b200_fma_peak_f64(void* cuda_stream, void* scratch, int blocks, int iters);
+int mythos_b200_fma_peak_f32(void* cuda_stream, void* scratch, int blocks, int iters);
+
 /* ---- introspection ------------------------------------------------------------------------------------------- */
 int mythos_b200_abi_version(void);
 int mythos_b200_param_count(void);                 /* MB_P_COUNT                              */

@@ -263,6 +263,16 @@ class ComposedEnergyFunction(EnergyFunction):
         return self._combine(self.compute_terms(body))
 
     def map(self, body_sequence: RigidBody) -> torch.Tensor:
+        """(F,) energies.  When the whole composition fuses into one launch group the weighted sum and the
+        parameter-gradient rows come out of a single pass (``functional._FrameEnergy``, the DiffTRe shape)."""
+        c, q, _ = _frames(body_sequence)
+        groups = kmodel.fusable_groups(self.energy_fns)
+        if len(groups) == 1:
+            w = torch.zeros(_lib.N_TERMS, dtype=torch.float64)
+            wt = torch.ones(len(self.energy_fns), dtype=torch.float64) if self.weights is None else torch.as_tensor(self.weights, dtype=torch.float64).cpu()
+            for k, fn in enumerate(self.energy_fns):
+                w[fn.TERM] = wt[k]
+            return kmodel.plan_for(self.energy_fns).evaluate_total(c, q, w)
         return self._combine(self.compute_terms_frames(body_sequence))
 
     def without_terms(self, *terms: list[str | type]) -> "ComposedEnergyFunction":

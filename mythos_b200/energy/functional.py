@@ -122,80 +122,188 @@ def _launch(
     return terms, d_center, d_quat, d_params
 
 
+@dc.dataclass(frozen=True)
+class StaticPairs:
+    """An explicit unbonded list: (2,U) shared by all frames, or (F,2,U) one list per frame."""
+
+    pairs: torch.Tensor | None
+
+    def chunk(self, sl: slice, center: torch.Tensor):
+        if self.pairs is None or self.pairs.numel() == 0:
+            return None, 0
+        if self.pairs.dim() == 3:
+            return self.pairs[sl], 2 * self.pairs.shape[-1]
+        return self.pairs, 0
+
+
+@dc.dataclass
+class CellListPairs:
+    """All-pairs semantics (the reference's ``topology.unbonded_neighbors``) realised per frame on the device.
+
+    Every unbonded term has compact support, so evaluating the pairs inside ``r_cutoff`` (the interaction range of
+    the current parameters, ``mythos_b200.energy.model.interaction_range``) gives the same energies as the
+    reference's N(N-1)/2 list.  The list is rebuilt per frame by the cell-list kernels and never leaves the GPU.
+    """
+
+    bonded: torch.Tensor
+    box: tuple[float, float, float]
+    r_cutoff: float
+    capacity: int = 0  # 0 = size from the first frame
+    workspace: torch.Tensor | None = None
+    max_count: int = 0
+    _pending: list = dc.field(default_factory=list)
+
+    def chunk(self, sl: slice, center: torch.Tensor):
+        """Enqueue the build for one chunk of frames; overflow is checked once per pass by ``verify`` (one host sync)."""
+        from mythos_b200.utils import neighbors
+
+        c = center.detach()
+        if self.capacity <= 0:
+            _, count, _, self.workspace = neighbors.build_pairs(c[:1], self.bonded, self.box, self.r_cutoff, 0.0, 1, self.workspace)
+            self.capacity = max(int(int(count.max().item()) * 1.15) + 64, 64)
+        pairs, count, overflow, self.workspace = neighbors.build_pairs(
+            c, self.bonded, self.box, self.r_cutoff, 0.0, self.capacity, self.workspace
+        )
+        self._pending.append((count, overflow))
+        return pairs, 2 * self.capacity
+
+    def verify(self) -> bool:
+        """True if every list built since the last call fitted its capacity; otherwise grows the capacity."""
+        if not self._pending:
+            return True
+        worst = int(torch.stack([c.max() for c, _ in self._pending]).max().item())
+        flags = int(torch.stack([o[0] for _, o in self._pending]).max().item())
+        self._pending.clear()
+        if flags & 2:
+            raise _lib.MythosB200Error("neighbour build: a nucleotide has more than 4 bonded partners")
+        self.max_count = max(self.max_count, worst)
+        if worst <= self.capacity:
+            return True
+        self.capacity = int(worst * 1.15) + 64  # jax_md would report did_buffer_overflow; here the pass re-runs
+        return False
+
+
+FRAME_CHUNK = 512  # frames per launch group: keeps a chunk's pair lists (~90 MB at N=2k) inside the 126 MB L2
+
+
+def _chunks(n_frames: int, source) -> list[slice]:
+    step = FRAME_CHUNK if isinstance(source, CellListPairs) else 65535
+    return [slice(lo, min(lo + step, n_frames)) for lo in range(0, n_frames, step)]
+
+
+def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, want_pos, want_par, per_frame_par):
+    """Chunked launch over frames; concatenates / sums the per-chunk outputs."""
+    while True:
+        outs = []
+        for sl in _chunks(center.shape[0], source):
+            pairs, stride = source.chunk(sl, center[sl])
+            outs.append(
+                _launch(model, topo, center[sl], quat[sl], params, pairs, stride, term_mask,
+                        None if cot is None else cot[sl], want_terms, want_pos, want_par, per_frame_par)
+            )
+        if not isinstance(source, CellListPairs) or source.verify():
+            break
+    if len(outs) == 1:
+        return outs[0]
+    terms = torch.cat([o[0] for o in outs]) if want_terms else None
+    d_center = torch.cat([o[1] for o in outs]) if want_pos else None
+    d_quat = torch.cat([o[2] for o in outs]) if want_pos else None
+    d_params = None
+    if want_par:
+        d_params = torch.cat([o[3] for o in outs]) if per_frame_par else torch.stack([o[3] for o in outs]).sum(0)
+    return terms, d_center, d_quat, d_params
+
+
 class _EnergyTerms(torch.autograd.Function):
+    """(center, quat, params) -> per-term energies (F,8); backward = second launch with the cotangent (remat)."""
+
     @staticmethod
-    def forward(ctx, center, quat, params, model, topo, pairs, pair_frame_stride, term_mask):
-        terms, _, _, _ = _launch(model, topo, center, quat, params, pairs, pair_frame_stride, term_mask, None, True, False, False)
+    def forward(ctx, center, quat, params, model, topo, source, term_mask):
+        terms, _, _, _ = _run(model, topo, center, quat, params, source, term_mask, None, True, False, False, False)
         ctx.save_for_backward(center, quat, params)
-        ctx.static = (model, topo, pairs, pair_frame_stride, term_mask)
+        ctx.static = (model, topo, source, term_mask)
         return terms
 
     @staticmethod
     def backward(ctx, g_terms):
         center, quat, params = ctx.saved_tensors
-        model, topo, pairs, stride, mask = ctx.static
+        model, topo, source, mask = ctx.static
         need_pos = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         need_par = ctx.needs_input_grad[2]
-        _, d_center, d_quat, d_params = _launch(
-            model, topo, center, quat, params, pairs, stride, mask, g_terms, False, need_pos, need_par
+        _, d_center, d_quat, d_params = _run(
+            model, topo, center, quat, params, source, mask, g_terms.contiguous(), False, need_pos, need_par, False
         )
         if d_params is not None:
             d_params = d_params.to(device=params.device, dtype=params.dtype)
-        return (
-            d_center if ctx.needs_input_grad[0] else None,
-            d_quat if ctx.needs_input_grad[1] else None,
-            d_params,
-            None,
-            None,
-            None,
-            None,
-            None,
+        return (d_center if ctx.needs_input_grad[0] else None, d_quat if ctx.needs_input_grad[1] else None, d_params,
+                None, None, None, None)
+
+
+class _FrameEnergy(torch.autograd.Function):
+    """(center, quat, params) -> weighted total energy per frame (F,), with dE/dparams rows produced in the SAME pass.
+
+    This is the DiffTRe shape: positions are constants, the loss needs ``E_k`` and ``sum_k g_k dE_k/dparams``.
+    When only ``params`` needs a gradient the forward launch also writes the Jacobian rows ``J (F, n_banks*P)``
+    (one fused energy + parameter-gradient pass over the pair list), and the backward is the tiny product ``g @ J``.
+    """
+
+    @staticmethod
+    def forward(ctx, center, quat, params, weights, model, topo, source, term_mask):
+        F = center.shape[0]
+        cot = weights.to(device=center.device, dtype=center.dtype).reshape(1, -1).expand(F, -1).contiguous()
+        jac_now = ctx.needs_input_grad[2] and not (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        terms, _, _, J = _run(model, topo, center, quat, params, source, term_mask, cot, True, False, jac_now, True)
+        ctx.jac_now = jac_now
+        if jac_now:
+            ctx.save_for_backward(J)
+        else:
+            ctx.save_for_backward(center, quat, params, cot)
+        ctx.static = (model, topo, source, term_mask, params.device, params.dtype)
+        return (terms * cot).sum(dim=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        model, topo, source, mask, pdev, pdtype = ctx.static
+        if ctx.jac_now:
+            (J,) = ctx.saved_tensors
+            return None, None, (g.to(J.dtype) @ J).to(device=pdev, dtype=pdtype), None, None, None, None, None
+        center, quat, params, cot = ctx.saved_tensors
+        need_pos = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        _, d_center, d_quat, d_params = _run(
+            model, topo, center, quat, params, source, mask, (cot * g.reshape(-1, 1)).contiguous(), False, need_pos,
+            ctx.needs_input_grad[2], False,
         )
+        if d_params is not None:
+            d_params = d_params.to(device=pdev, dtype=pdtype)
+        return (d_center if ctx.needs_input_grad[0] else None, d_quat if ctx.needs_input_grad[1] else None, d_params,
+                None, None, None, None, None)
 
 
-def energy_terms(
-    model: _lib.Model,
-    topo: DeviceTopology,
-    center: torch.Tensor,
-    quat: torch.Tensor,
-    params: torch.Tensor,
-    pairs: torch.Tensor | None,
-    term_mask: int = _lib.ALL_TERMS,
-    pair_frame_stride: int = 0,
-) -> torch.Tensor:
-    """Per-term energies ``(F, 8)`` for ``center (F,N,3)``, ``quat (F,N,4)``; differentiable in center, quat, params."""
+def _source_of(pairs) -> StaticPairs | CellListPairs:
+    return pairs if isinstance(pairs, (StaticPairs, CellListPairs)) else StaticPairs(pairs)
+
+
+def energy_terms(model, topo, center, quat, params, pairs, term_mask: int = _lib.ALL_TERMS) -> torch.Tensor:
+    """Per-term energies ``(F, 8)`` for ``center (F,N,3)``, ``quat (F,N,4)``; differentiable in center, quat, params.
+
+    ``pairs``: a (2,U) / (F,2,U) int32 device tensor, ``StaticPairs`` or ``CellListPairs``."""
     if center.dim() != 3 or quat.dim() != 3:
         raise _lib.MythosB200Error("center must be (F,N,3) and quat (F,N,4)")
-    out = []
-    for lo in range(0, center.shape[0], 65535):  # gridDim.y limit of one launch
-        sl = slice(lo, lo + 65535)
-        p = pairs
-        if pairs is not None and pair_frame_stride:
-            p = pairs[sl]
-        out.append(_EnergyTerms.apply(center[sl], quat[sl], params, model, topo, p, pair_frame_stride, term_mask))
-    return out[0] if len(out) == 1 else torch.cat(out)
+    return _EnergyTerms.apply(center, quat, params, model, topo, _source_of(pairs), term_mask)
 
 
-def energy_and_gradients(
-    model: _lib.Model,
-    topo: DeviceTopology,
-    center: torch.Tensor,
-    quat: torch.Tensor,
-    params: torch.Tensor,
-    pairs: torch.Tensor | None,
-    cot: torch.Tensor | None = None,
-    term_mask: int = _lib.ALL_TERMS,
-    pair_frame_stride: int = 0,
-    want_pos_grad: bool = True,
-    want_param_grad: bool = False,
-    per_frame_param_grad: bool = False,
-):
-    """One fused launch pair returning ``(terms, d_center, d_quat, d_params)`` without autograd bookkeeping.
+def frame_energies(model, topo, center, quat, params, pairs, weights: torch.Tensor, term_mask: int = _lib.ALL_TERMS) -> torch.Tensor:
+    """``sum_t weights[t] * E_t`` per frame, ``(F,)``; see ``_FrameEnergy`` for the fused parameter-gradient pass."""
+    if center.dim() != 3 or quat.dim() != 3:
+        raise _lib.MythosB200Error("center must be (F,N,3) and quat (F,N,4)")
+    return _FrameEnergy.apply(center, quat, params, weights, model, topo, _source_of(pairs), term_mask)
+
+
+def energy_and_gradients(model, topo, center, quat, params, pairs, cot=None, term_mask: int = _lib.ALL_TERMS,
+                         want_pos_grad: bool = True, want_param_grad: bool = False, per_frame_param_grad: bool = False):
+    """One fused pass returning ``(terms, d_center, d_quat, d_params)`` without autograd bookkeeping.
 
     This is the call the MD loop and the DiffTRe pass use: energies, forces and the parameter gradient of
-    ``sum_t cot[f,t] * E_t(frame f)`` come out of a single pass over the pair list.
-    """
-    return _launch(
-        model, topo, center, quat, params, pairs, pair_frame_stride, term_mask, cot, True, want_pos_grad, want_param_grad,
-        per_frame_param_grad,
-    )
+    ``sum_t cot[f,t] * E_t(frame f)`` come out of a single pass over the pair list."""
+    return _run(model, topo, center, quat, params.to(device=center.device, dtype=center.dtype), _source_of(pairs), term_mask,
+                cot, True, want_pos_grad, want_param_grad, per_frame_param_grad)

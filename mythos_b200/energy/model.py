@@ -144,24 +144,72 @@ class Plan:
             ),
         )
 
-    def pairs(self, device) -> torch.Tensor | None:
+    def pairs(self, device, topo: functional.DeviceTopology):
+        """The unbonded pair source: an explicit list, or per-frame cell lists for the all-pairs sentinel."""
         if not (self.term_mask & _lib.UNBONDED_TERMS):
-            return None
+            return functional.StaticPairs(None)
         ub = next(fn.unbonded_neighbors for fn in self.fns if fn.TERM >= 3)
-        return device_pairs(ub, device)
+        from mythos_b200.input.topology import AllPairs
+
+        if isinstance(ub, AllPairs):
+            box = tuple(self.model.box)
+            return functional.CellListPairs(bonded=topo.bonded, box=box, r_cutoff=interaction_range(self))
+        return functional.StaticPairs(device_pairs(ub, device))
 
     def evaluate(self, center: torch.Tensor, quat: torch.Tensor) -> torch.Tensor:
         """(F,8) per-term energies; differentiable in center, quat and the configurations' tensors."""
         _lib.require_cuda(center, "RigidBody.center")
         dev, dtype = center.device, center.dtype
         topo = self.topology(center.shape[1], dev)
-        pairs = self.pairs(dev)
-        stride = 0
-        if pairs is not None and pairs.dim() == 3:
-            stride = 2 * pairs.shape[-1]
         return functional.energy_terms(
-            self.model, topo, center, quat, self.device_params(dev, dtype), pairs, self.term_mask, stride
+            self.model, topo, center, quat, self.device_params(dev, dtype), self.pairs(dev, topo), self.term_mask
         )
+
+    def evaluate_total(self, center: torch.Tensor, quat: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+        """(F,) weighted total energies with the parameter-gradient rows produced in the same pass (DiffTRe shape)."""
+        _lib.require_cuda(center, "RigidBody.center")
+        dev, dtype = center.device, center.dtype
+        topo = self.topology(center.shape[1], dev)
+        return functional.frame_energies(
+            self.model, topo, center, quat, self.device_params(dev, dtype), self.pairs(dev, topo), weights, self.term_mask
+        )
+
+
+def interaction_range(plan: "Plan") -> float:
+    """Upper bound on the centre-of-mass distance at which any enabled unbonded term can be non-zero:
+    max over terms of (site-pair cutoff + both site offsets), over all banks / flavours (unit quaternions)."""
+    vec = plan.params_vector().detach()
+    P = _lib.param_count()
+    idx = {n: i for i, n in enumerate(_lib.param_names())}
+    n_fl = 2 if plan.hybrid else 1
+    off = {"back": 0.0, "base": 0.0, "stack": 0.0}
+    for k in range(n_fl):
+        g = plan.model.geom[k]
+        off["back"] = max(off["back"], float(sum(x * x for x in g.back) ** 0.5))
+        off["base"] = max(off["base"], abs(g.base))
+        off["stack"] = max(off["stack"], abs(g.stack))
+    reach = 0.0
+    for b in range(plan.model.n_banks):
+        v = vec[b * P:(b + 1) * P]
+
+        def p(name):
+            return float(v[idx[name]])
+
+        m = plan.term_mask
+        if m & (1 << 3):
+            reach = max(reach, p("unbonded_excluded_volume.dr_c_backbone") + 2 * off["back"],
+                        p("unbonded_excluded_volume.dr_c_base") + 2 * off["base"],
+                        p("unbonded_excluded_volume.dr_c_back_base") + off["back"] + off["base"],
+                        p("unbonded_excluded_volume.dr_c_base_back") + off["back"] + off["base"])
+        if m & (1 << 4):
+            reach = max(reach, p("hydrogen_bonding.dr_c_high_hb") + 2 * off["base"])
+        if m & (1 << 5):
+            reach = max(reach, p("cross_stacking.dr_c_high_cross") + 2 * off["base"])
+        if m & (1 << 6):
+            reach = max(reach, p("coaxial_stacking.dr_c_high_coax") + 2 * off["stack"])
+        if m & (1 << 7) and plan.model.forms[b].has_debye:
+            reach = max(reach, p("debye.r_cut") + 2 * off["back"])
+    return reach * (1.0 + 1e-9) + 1e-9
 
 
 def _prop_key(fn) -> tuple:

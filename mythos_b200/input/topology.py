@@ -19,12 +19,30 @@ import numpy as np
 
 NUCLEOTIDES_IDX = {"A": 0, "C": 1, "G": 2, "T": 3, "U": 3}
 ALL_PAIRS_LIMIT = 20000  # nucleotides; beyond this an all-pairs list is > 1.6 GB of int32 pairs
+ALL_PAIRS_EXPLICIT = 512  # above this Topology.unbonded_neighbors is the AllPairs sentinel
 
 
 class NucleotideType(IntEnum):
     UNSPECIFIED = 0
     DNA = 1
     RNA = 2
+
+
+class AllPairs:
+    """Sentinel for "every i<j that is not bonded" (what ``topology.unbonded_neighbors`` means in the reference,
+    ``topology.py:186-190``) without materialising the O(N^2) list.  Energy functions holding it evaluate the
+    unbonded terms over per-frame device cell lists at the interaction range of their parameters -- the same
+    energies, since every unbonded term has compact support."""
+
+    def __init__(self, n: int):
+        self.n = int(n)
+
+    @property
+    def T(self) -> "AllPairs":  # noqa: N802 - BaseEnergyFunction stores topology.unbonded_neighbors.T
+        return self
+
+    def __repr__(self) -> str:
+        return f"AllPairs(n={self.n})"
 
 
 def bonded_pairs(strand_counts, is_circular=None) -> np.ndarray:
@@ -77,9 +95,12 @@ class Topology:
             raise ValueError("Invalid discrete sequence")
 
     @cached_property
-    def unbonded_neighbors(self) -> np.ndarray:
+    def unbonded_neighbors(self):
+        """(U,2) all-pairs-minus-bonded list for small systems, the ``AllPairs`` sentinel beyond ``ALL_PAIRS_EXPLICIT``."""
         if self.unbonded_override is not None:
             return self.unbonded_override
+        if self.n_nucleotides > ALL_PAIRS_EXPLICIT:
+            return AllPairs(self.n_nucleotides)
         return unbonded_pairs(self.n_nucleotides, self.bonded_neighbors)
 
 

@@ -139,7 +139,6 @@ def assembly(n_dup: int, pitch: float = 2.6, seed: int = 0, gap: float = 1.0, ma
     top = Topology(
         n_nucleotides=n, strand_counts=np.array(strands, np.int32), bonded_neighbors=bonded_pairs(strands),
         seq=np.concatenate(seqs), is_end=is_end, nt_type=np.concatenate(nts),
-        unbonded_override=None if n <= 4096 else np.zeros((0, 2), np.int32),
     )
     return SyntheticSystem(center=center, quat=np.concatenate(quats), topology=top, box=box)
 

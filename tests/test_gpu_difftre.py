@@ -1,0 +1,142 @@
+"""DiffTRe pass on the GPU: all-pairs semantics via per-frame cell lists, fused E + dE/dparams, reweighting.
+
+Compares with the oracle on a small batch of frames of the benchmark system (N = 2040), and checks the
+size-independent properties the pass must have at full size (additivity over frames, weights sum to one,
+gradient of a frame-linear loss == g-weighted sum of per-frame gradients).
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from mythos_b200.energy import dna2
+from mythos_b200.optimization import objective
+from mythos_b200.rigid_body import Quaternion, RigidBody
+from mythos_b200.simulators.io import SimulatorTrajectory
+from mythos_b200.utils import synthetic
+from oracle import oxdna_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def workload():
+    s = synthetic.assembly(17, seed=1)
+    c, q = synthetic.rejittered_frames(s, 6)
+    return s, c, q
+
+
+def test_map_matches_oracle_and_theta_gradient(workload):
+    s, c, q = workload
+    top = s.topology
+    efn = dna2.create_default_energy_fn(top)
+    names = ["eps_backbone", "a_stack", "eps_hb", "k_cross", "q_eff", "lambda_factor", "sigma_backbone", "kt"]
+    base = efn.params_dict(include_dependent=False)
+    theta = {k: torch.tensor(float(base[k]), dtype=torch.float64, requires_grad=True) for k in names}
+    states = RigidBody(torch.tensor(c, device=DEV), Quaternion(torch.tensor(q, device=DEV)))
+    e = efn.with_params(theta).map(states)
+    g = torch.tensor(np.random.default_rng(0).standard_normal(len(c)), device=DEV)
+    (e * g).sum().backward()
+
+    th = orc.default_theta("dna2")
+    leaves = {}
+    for nm in names:
+        for term in th:
+            if nm in th[term]:
+                leaves.setdefault(nm, torch.tensor(float(th[term][nm]), dtype=torch.float64, requires_grad=True))
+                th[term][nm] = leaves[nm]
+    params = orc.init_all("dna2", th)
+    want = []
+    for f in range(len(c)):
+        pairs = orc.neighbor_pairs(c[f], top.bonded_neighbors, 3.3, 0.0)
+        want.append(orc.energy_terms("dna2", c[f], q[f], top.seq, top.bonded_neighbors, pairs, params, is_end=top.is_end).sum())
+    want = torch.stack(want)
+    (want * g.cpu()).sum().backward()
+    np.testing.assert_allclose(e.detach().cpu().numpy(), want.detach().numpy(), rtol=1e-9)
+    for nm in names:
+        assert np.isclose(float(theta[nm].grad), float(leaves[nm].grad), rtol=1e-6, atol=1e-9), nm
+
+
+def test_weights_and_neff_kats():
+    # mythos/optimization/tests/test_objective.py:187-205: equal energies -> uniform weights, n_eff = 1
+    e = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64, device=DEV)
+    w, neff = objective.compute_weights_and_neff(1.0, e, e)
+    np.testing.assert_allclose(w.cpu().numpy(), [1 / 3] * 3)
+    np.testing.assert_allclose(float(neff), 1.0)
+    # general case against the oracle's formula, including the gradient through weights and n_eff
+    rng = np.random.default_rng(1)
+    en = torch.tensor(rng.normal(size=257), dtype=torch.float64, device=DEV, requires_grad=True)
+    er = torch.tensor(rng.normal(size=257), dtype=torch.float64, device=DEV)
+    beta = torch.tensor(rng.uniform(5, 12, size=257), dtype=torch.float64, device=DEV)
+    w, neff = objective.compute_weights_and_neff(beta, en, er)
+    obs = torch.tensor(rng.normal(size=257), device=DEV)
+    ((w * obs).sum() + 0.3 * neff).backward()
+    en2 = en.detach().cpu().clone().requires_grad_(True)
+    w2, neff2 = orc.weights_and_neff(beta.cpu(), en2, er.cpu())
+    ((w2 * obs.cpu()).sum() + 0.3 * neff2).backward()
+    np.testing.assert_allclose(w.detach().cpu().numpy(), w2.detach().numpy(), rtol=1e-12)
+    np.testing.assert_allclose(float(neff), float(neff2), rtol=1e-12)
+    np.testing.assert_allclose(en.grad.cpu().numpy(), en2.grad.numpy(), rtol=1e-9, atol=1e-14)
+    # multi-temperature segments (test_objective.py:483-497)
+    temp = torch.tensor([0.1] * 100 + [0.11] * 157, dtype=torch.float64, device=DEV)
+    m = objective.compute_min_segment_neff(temp, en.detach(), er)
+    a = float(orc.weights_and_neff(torch.tensor(10.0), en2[:100].detach(), er.cpu()[:100])[1])
+    b = float(orc.weights_and_neff(torch.tensor(1 / 0.11), en2[100:].detach(), er.cpu()[100:])[1])
+    np.testing.assert_allclose(m, min(a, b), rtol=1e-10)
+
+
+def test_difftre_objective_state_machine_and_gradient(workload):
+    s, c, q = workload
+    efn = dna2.create_default_energy_fn(s.topology)
+    kT = float(dna2.default_configs()[0]["kT"])
+    F = len(c)
+    traj = SimulatorTrajectory(
+        center=torch.tensor(c, device=DEV), orientation=Quaternion(torch.tensor(q, device=DEV)),
+        temperature=torch.full((F,), kT, dtype=torch.float64, device=DEV))
+    obs = torch.tensor(np.random.default_rng(2).normal(size=F), device=DEV)
+
+    def loss_fn(ref_states, weights, energy_fn, opt_params, observables):
+        m = (weights * obs).sum()
+        return (m - 0.1) ** 2, (("obs", m), None)
+
+    objv = objective.DiffTReObjective(name="t", required_observables=("traj",), grad_or_loss_fn=loss_fn, energy_fn=efn,
+                                      min_n_eff_factor=0.5)
+    out = objv.calculate({}, {})
+    assert not out.is_ready and out.needs_update == ("traj",)
+    theta = {"eps_hb": torch.tensor(1.0678, dtype=torch.float64), "a_stack": torch.tensor(6.0, dtype=torch.float64)}
+    out = objv.calculate({"traj": traj}, theta)
+    assert out.is_ready and out.state["opt_steps"] == 1 and abs(out.observables["neff"] - 1.0) < 1e-12
+    # at theta == theta_ref the weights are uniform: dL/dtheta = 2 (m - 0.1) * d<O>_w/dtheta with
+    # d<O>_w/dtheta = -beta * Cov_uniform(O, dE/dtheta)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in theta.items()}
+    e = efn.with_params(leaves).map(traj)
+    m = float(obs.mean())
+    for k in theta:
+        (ge,) = torch.autograd.grad(e, leaves[k], grad_outputs=torch.eye(F, device=DEV, dtype=torch.float64)[0] * 0 + 1, retain_graph=True)
+        per = []
+        for f in range(F):
+            (gf,) = torch.autograd.grad(e[f], leaves[k], retain_graph=True)
+            per.append(float(gf))
+        per = np.array(per)
+        cov = float((obs.cpu().numpy() * per).mean() - obs.cpu().numpy().mean() * per.mean())
+        want = 2 * (m - 0.1) * (-(1 / kT) * cov)
+        assert np.isclose(float(out.grads[k]), want, rtol=1e-6, atol=1e-12), (k, float(out.grads[k]), want)
+    # a far-away reference makes n_eff collapse -> new trajectory requested
+    far = {"eps_hb": torch.tensor(1.4, dtype=torch.float64), "a_stack": torch.tensor(6.0, dtype=torch.float64)}
+    out2 = objective.DiffTReObjective(name="t", required_observables=("traj",), grad_or_loss_fn=loss_fn, energy_fn=efn,
+                                      min_n_eff_factor=0.95).calculate({"traj": traj}, far, reference_opt_params=theta)
+    assert not out2.is_ready and out2.state == {"opt_steps": 0}
+
+
+def test_frame_additivity_at_scale(workload):
+    """Size-independent property used at the benchmark size: the energies of a batch are those of its halves."""
+    s, _, _ = workload
+    c, q = synthetic.rejittered_frames(s, 700, seed0=5000)
+    efn = dna2.create_default_energy_fn(s.topology)
+    cd, qd = torch.tensor(c, device=DEV), torch.tensor(q, device=DEV)
+    e_all = efn.map(RigidBody(cd, Quaternion(qd)))
+    e_a = efn.map(RigidBody(cd[:333], Quaternion(qd[:333])))
+    e_b = efn.map(RigidBody(cd[333:], Quaternion(qd[333:])))
+    np.testing.assert_allclose(e_all.cpu().numpy(), torch.cat([e_a, e_b]).cpu().numpy(), rtol=1e-11)
+    assert torch.isfinite(e_all).all()

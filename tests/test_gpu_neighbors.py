@@ -1,0 +1,106 @@
+"""Neighbour build: the pair SET must equal the O(N^2) evaluation of the reference's accept test, bit for bit.
+
+The reference only checks that bonded pairs are absent on 3 particles (mythos/utils/tests/test_neighbors.py:18-41);
+here the set is compared on synthetic assemblies in free space and in periodic boxes, in both dtypes, batched, plus
+capacity overflow reporting and energy equality between the listed pairs and the all-pairs list.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from mythos_b200 import space
+from mythos_b200.energy import dna2
+from mythos_b200.rigid_body import Quaternion, RigidBody
+from mythos_b200.utils import neighbors, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def brute_force(center: np.ndarray, bonded: np.ndarray, cutoff: float, box, dtype):
+    """All i<j, not bonded, d2 < cutoff^2 with d2 accumulated as (dx*dx + dy*dy) + dz*dz in `dtype` (no FMA)."""
+    c = center.astype(dtype)
+    n = c.shape[0]
+    i, j = np.triu_indices(n, k=1)
+    d = c[i] - c[j]
+    if box is not None:
+        L = np.asarray(box, dtype=dtype)
+        s = np.fmod(d + dtype(0.5) * L, L)
+        s = np.where((s != 0) & (s < 0), s + L, s)
+        d = s - dtype(0.5) * L
+    d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    cut = dtype(cutoff)
+    keep = d2 < cut * cut
+    bset = {(min(a, b), max(a, b)) for a, b in bonded.tolist()}
+    return {(int(a), int(b)) for a, b in zip(i[keep], j[keep]) if (int(a), int(b)) not in bset}
+
+
+def to_set(pairs: torch.Tensor, n: int):
+    p = pairs.cpu().numpy()
+    valid = p[0] < n
+    assert np.all(p[1][~valid] == n), "padding must be N in both rows"
+    assert np.all(p[0][valid] < p[1][valid]), "OrderedSparse: i < j"
+    out = set(zip(p[0][valid].tolist(), p[1][valid].tolist()))
+    assert len(out) == int(valid.sum()), "duplicate pairs in the list"
+    return out
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("periodic", [False, True])
+@pytest.mark.parametrize("cutoff", [1.7, 3.45])
+def test_pair_set_bit_exact(dtype, periodic, cutoff):
+    s = synthetic.assembly(6, seed=3)
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    center = s.center.copy()
+    box = None
+    if periodic:
+        box = (9.5, 8.0, 26.0)  # smaller than the assembly: nucleotides interact through the boundary
+    frames = np.stack([center, center + 0.3, synthetic.jitter(center, s.quat, np.random.default_rng(5))[0]])
+    c = torch.tensor(frames, dtype=dtype, device=DEV)
+    pairs, count, overflow, _ = neighbors.build_pairs(
+        c, torch.tensor(s.topology.bonded_neighbors), box or (0.0, 0.0, 0.0), cutoff - 0.2, 0.2, 60000)
+    assert int(overflow.item()) == 0
+    n = center.shape[0]
+    for f in range(3):
+        want = brute_force(np.asarray(c[f].cpu()), s.topology.bonded_neighbors, npdt(npdt(cutoff - 0.2) + npdt(0.2)), box, npdt)
+        got = to_set(pairs[f], n)
+        assert got == want, (len(got), len(want), list(got ^ want)[:5])
+        assert int(count[f]) == len(want)
+
+
+def test_capacity_overflow_is_reported_and_list_truncated():
+    s = synthetic.assembly(2, seed=1)
+    c = torch.tensor(s.center[None], device=DEV)
+    pairs, count, overflow, _ = neighbors.build_pairs(c, torch.tensor(s.topology.bonded_neighbors), (0, 0, 0), 3.0, 0.2, 100)
+    assert int(overflow.item()) & 1 and int(count[0]) > 100
+    p = pairs[0].cpu().numpy()
+    assert np.all(p[0] < p[1]) and p.max() < s.center.shape[0]
+
+
+def test_listed_pairs_give_all_pairs_energy_and_update_protocol():
+    s = synthetic.assembly(2, seed=4)
+    top = s.topology
+    efn = dna2.create_default_energy_fn(top)  # N=240 < 512: explicit all-pairs list
+    body = RigidBody(torch.tensor(s.center, device=DEV), Quaternion(torch.tensor(s.quat, device=DEV)))
+    e_all = efn.compute_terms(body)
+    fns = neighbors.get_neighbor_list_fn(top.bonded_neighbors, top.n_nucleotides, space.free()[0], None, r_cutoff=3.3, dr_threshold=0.2)
+    nbrs = fns.allocate(body)
+    assert nbrs.idx.shape[0] == 2 and int(nbrs.did_buffer_overflow.item()) == 0
+    e_nl = efn.with_props(unbonded_neighbors=nbrs.idx).compute_terms(body)
+    np.testing.assert_allclose(e_nl.cpu().numpy(), e_all.cpu().numpy(), rtol=1e-12, atol=1e-12)
+    # small move: no rebuild (same object back); large move: rebuilt list, still exact
+    same = nbrs.update(body.center + 0.01)
+    assert same is nbrs
+    moved = RigidBody(body.center + torch.tensor([0.5, 0.0, 0.0], device=DEV) * (torch.arange(top.n_nucleotides, device=DEV) % 2).unsqueeze(1), body.orientation)
+    nbrs2 = nbrs.update(moved.center)
+    assert nbrs2 is not nbrs
+    e_all2 = efn.compute_terms(moved)
+    e_nl2 = efn.with_props(unbonded_neighbors=nbrs2.idx).compute_terms(moved)
+    if int(nbrs2.did_buffer_overflow.item()) == 0:
+        np.testing.assert_allclose(e_nl2.cpu().numpy(), e_all2.cpu().numpy(), rtol=1e-12, atol=1e-12)
+
+
+def test_invalid_bonded_index_raises():
+    with pytest.raises(ValueError):
+        neighbors.get_neighbor_list_fn(np.array([[0, 5]]), 3, space.free()[0], None)
