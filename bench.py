@@ -342,7 +342,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload_name(F), "frames_per_gpu": hi - lo, "n_nucleotides": n,
                    "l2": "inputs larger than L2 (frames 936 MB + per-chunk pair lists)", "n_theta": len(theta),
-                   "loss": float(loss), "n_eff": float(neff), "grad_norm": float(dp.norm())},
+                   "loss": float(loss.detach()), "n_eff": float(neff.detach()), "grad_norm": float(dp.norm())},
         "e2e": {"value": F / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": args.steps * (n_chunks * (11 + 2) + 1),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,

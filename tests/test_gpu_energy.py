@@ -104,7 +104,8 @@ def test_forces_and_theta_gradients_match_oracle(name):
     efn = energy_fn_of(c)
     theta = {}
     for nm in names:
-        theta[nm] = torch.tensor(float(efn.params_dict(include_dependent=False)[nm]), dtype=torch.float64, requires_grad=True)
+        val = next(getattr(fn.params, nm) for fn in efn.energy_fns if nm in fn.params and getattr(fn.params, nm) is not None)
+        theta[nm] = torch.tensor(float(val), dtype=torch.float64, requires_grad=True)
     efn_t = efn.with_params(theta)
     body = body_of(c, frame, requires_grad=True)
     terms = efn_t.compute_terms(body)
