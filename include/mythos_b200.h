@@ -363,8 +363,10 @@ typedef struct mb_energy_args {
   void* d_quat;           /* out (F,N,4), or NULL                                                            */
   void* d_params;         /* out (n_banks*MB_P_COUNT) per row, or NULL                                       */
   int64_t d_params_frame_stride; /* elements between rows of consecutive frames; 0 = one row summed over frames */
+  const int32_t* pair_count; /* (F) number of valid pairs at the head of each frame's list (as mb_nl_args.count), or NULL */
 } mb_energy_args;
 #define MB_FLAG_ACCUMULATE 0x1u /* add into the outputs instead of zeroing them first */
+#define MB_FLAG_GENERIC_KERNEL 0x2u /* force the one-thread-per-pair kernels even where the frame-resident kernel applies */
 
 int mythos_b200_energy_f64(void* cuda_stream, const mb_energy_args* a);
 int mythos_b200_energy_f32(void* cuda_stream, const mb_energy_args* a);

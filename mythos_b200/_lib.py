@@ -29,6 +29,7 @@ TERM_NAMES = (
 )
 BONDED_TERMS, UNBONDED_TERMS, ALL_TERMS = 0x07, 0xF8, 0xFF
 FLAG_ACCUMULATE = 0x1
+FLAG_GENERIC_KERNEL = 0x2
 MAX_BANKS = 3
 STATUS = {0: "MB_OK", 1: "MB_EINVAL_SHAPE", 2: "MB_EINVAL_MODEL", 3: "MB_ECAPACITY", 4: "MB_ECUDA"}
 
@@ -91,6 +92,7 @@ class EnergyArgs(C.Structure):
         ("d_quat", C.c_void_p),
         ("d_params", C.c_void_p),
         ("d_params_frame_stride", C.c_int64),
+        ("pair_count", C.c_void_p),
     ]
 
 

@@ -7,57 +7,11 @@
 // block and term; nucleotide gradients go out as (dE/dcenter, dE/dquat) atomics; parameter gradients are
 // warp-reduced into a shared-memory bank image and flushed once per block.
 #include "common.cuh"
-#include "oxdna_device.cuh"
+#include "energy_dev.cuh"
 
 namespace mb {
 
 constexpr int kBlock = 128;
-constexpr unsigned kFull = 0xffffffffu;
-
-template <class T>
-struct EnergyDev {
-  ModelT<T> M;
-  int n, n_frames, n_bonded;
-  const T* center;
-  const T* quat;
-  const int32_t* seq;
-  const int32_t* nt_type;
-  const int32_t* nt_type_stack;
-  const int32_t* is_end;
-  const int32_t* bonded;
-  const int32_t* pairs;
-  long long pair_capacity, pair_frame_stride;
-  const T* params;
-  const T* cot;
-  unsigned mask;
-  T* terms;
-  T* d_center;
-  T* d_quat;
-  T* d_params;
-  long long d_params_frame_stride;
-};
-
-// Parameter-gradient accumulator: warp-reduce, then one shared-memory atomic per warp and parameter.
-// With several banks (NA1) lanes of one warp may address different banks, so those go out as per-lane
-// shared atomics instead.
-template <class T>
-struct SmemAcc {
-  T* sh;
-  bool per_lane;
-  __device__ __forceinline__ void add(int bank, int idx, T v) {
-    if (per_lane) {
-      if (v != T(0)) atomicAdd(&sh[bank * MB_P_COUNT + idx], v);
-      return;
-    }
-    if (!__any_sync(kFull, v != T(0))) return;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&sh[idx], v);
-  }
-  __device__ __forceinline__ void add_scatter(int bank, int idx, T v, bool pred) {
-    if (pred && v != T(0)) atomicAdd(&sh[bank * MB_P_COUNT + idx], v);
-  }
-};
 
 template <class T>
 __device__ __forceinline__ Nuc<T> load_nuc(const T* __restrict__ center, const T* __restrict__ quat, long long idx,
@@ -228,6 +182,7 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
   a.pairs = x->pairs;
   a.pair_capacity = x->pair_capacity;
   a.pair_frame_stride = x->pair_frame_stride;
+  a.pair_count = x->pair_count;
   a.params = static_cast<const T*>(x->params);
   a.cot = static_cast<const T*>(x->cot);
   a.mask = x->term_mask;
@@ -250,6 +205,8 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
     }
   }
   const bool wf = a.d_center || a.d_quat, wp = a.d_params != nullptr;
+  // frame-resident path: one block per frame with the frame staged in shared memory (energies and dE/dparams only)
+  if (!wf && !(x->flags & MB_FLAG_GENERIC_KERNEL) && frame_kernel_eligible<T>(a)) return launch_frame_kernel<T>(s, a, wp);
   if (wf && wp) return launch_pairs<T, true, true>(s, a);
   if (wf) return launch_pairs<T, true, false>(s, a);
   if (wp) return launch_pairs<T, false, true>(s, a);

@@ -65,6 +65,8 @@ def _launch(
     want_pos_grad: bool,
     want_param_grad: bool,
     per_frame_param_grad: bool = False,
+    pair_count: torch.Tensor | None = None,
+    flags: int = 0,
 ):
     _lib.require_cuda(center, "center")
     F, N = center.shape[0], center.shape[1]
@@ -110,7 +112,8 @@ def _launch(
     a.params = params.data_ptr()
     a.cot = _lib.ptr(cot)
     a.term_mask = term_mask
-    a.flags = 0
+    a.flags = flags
+    a.pair_count = _lib.ptr(pair_count) if cap else None
     a.terms = _lib.ptr(terms)
     a.d_center = _lib.ptr(d_center)
     a.d_quat = _lib.ptr(d_quat)
@@ -130,10 +133,10 @@ class StaticPairs:
 
     def chunk(self, sl: slice, center: torch.Tensor):
         if self.pairs is None or self.pairs.numel() == 0:
-            return None, 0
+            return None, 0, None
         if self.pairs.dim() == 3:
-            return self.pairs[sl], 2 * self.pairs.shape[-1]
-        return self.pairs, 0
+            return self.pairs[sl], 2 * self.pairs.shape[-1], None
+        return self.pairs, 0, None
 
 
 @dc.dataclass
@@ -165,7 +168,7 @@ class CellListPairs:
             c, self.bonded, self.box, self.r_cutoff, 0.0, self.capacity, self.workspace
         )
         self._pending.append((count, overflow))
-        return pairs, 2 * self.capacity
+        return pairs, 2 * self.capacity, count
 
     def verify(self) -> bool:
         """True if every list built since the last call fitted its capacity; otherwise grows the capacity."""
@@ -191,15 +194,15 @@ def _chunks(n_frames: int, source) -> list[slice]:
     return [slice(lo, min(lo + step, n_frames)) for lo in range(0, n_frames, step)]
 
 
-def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, want_pos, want_par, per_frame_par):
+def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, want_pos, want_par, per_frame_par, flags=0):
     """Chunked launch over frames; concatenates / sums the per-chunk outputs."""
     while True:
         outs = []
         for sl in _chunks(center.shape[0], source):
-            pairs, stride = source.chunk(sl, center[sl])
+            pairs, stride, count = source.chunk(sl, center[sl])
             outs.append(
                 _launch(model, topo, center[sl], quat[sl], params, pairs, stride, term_mask,
-                        None if cot is None else cot[sl], want_terms, want_pos, want_par, per_frame_par)
+                        None if cot is None else cot[sl], want_terms, want_pos, want_par, per_frame_par, count, flags)
             )
         if not isinstance(source, CellListPairs) or source.verify():
             break
@@ -300,10 +303,11 @@ def frame_energies(model, topo, center, quat, params, pairs, weights: torch.Tens
 
 
 def energy_and_gradients(model, topo, center, quat, params, pairs, cot=None, term_mask: int = _lib.ALL_TERMS,
-                         want_pos_grad: bool = True, want_param_grad: bool = False, per_frame_param_grad: bool = False):
+                         want_pos_grad: bool = True, want_param_grad: bool = False, per_frame_param_grad: bool = False,
+                         flags: int = 0):
     """One fused pass returning ``(terms, d_center, d_quat, d_params)`` without autograd bookkeeping.
 
     This is the call the MD loop and the DiffTRe pass use: energies, forces and the parameter gradient of
     ``sum_t cot[f,t] * E_t(frame f)`` come out of a single pass over the pair list."""
     return _run(model, topo, center, quat, params.to(device=center.device, dtype=center.dtype), _source_of(pairs), term_mask,
-                cot, True, want_pos_grad, want_param_grad, per_frame_param_grad)
+                cot, True, want_pos_grad, want_param_grad, per_frame_param_grad, flags)
