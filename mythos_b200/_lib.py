@@ -8,13 +8,14 @@ the error is raised to the caller.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from functools import lru_cache
 from pathlib import Path
 
 import torch
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libmythos_b200.so"
+LIB_PATH = Path(os.environ.get("MYTHOS_B200_LIB", PKG / "libmythos_b200.so"))  # env override: kernel-variant experiments
 
 N_TERMS = 8
 TERM_NAMES = (

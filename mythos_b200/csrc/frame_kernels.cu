@@ -20,7 +20,10 @@
 
 namespace mb {
 
-constexpr int kFB = 512;              // threads per CTA (one CTA per SM: the frame fills most of shared memory)
+#ifndef MB_FRAME_THREADS
+#define MB_FRAME_THREADS 512
+#endif
+constexpr int kFB = MB_FRAME_THREADS;  // threads per CTA (one CTA per SM: the frame fills most of shared memory)
 constexpr int kFWarps = kFB / 32;
 constexpr int kQCap = 2 * kFB;
 
@@ -193,118 +196,8 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a) {
     bp_hi = fmax(bp_hi, sP[MB_P_CROSS_RCHIGH]);
   }
 
-  // ---- phase 3 bodies -------------------------------------------------------------------------------
-  auto process_bp = [&](int first, int count) {
-    const int t = threadIdx.x;
-    const bool valid = t < count;
-    const uint32_t pk = valid ? qBP[first + t] : 0u;
-    const int i = pk & 0xffff, j = pk >> 16;
-    const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
-    const V3<T> d = disp(site(nj, g.base, T(0), T(0)), site(ni, g.base, T(0), T(0)), M.box);
-    const T r = sqrt(dot(d, d));
-    const bool in_hb = valid && (mask & (1u << MB_TERM_HB)) && sP[MB_P_HB_RCLOW] < r && r < sP[MB_P_HB_RCHIGH];
-    const bool in_cr = valid && (mask & (1u << MB_TERM_CROSS)) && sP[MB_P_CROSS_RCLOW] < r && r < sP[MB_P_CROSS_RCHIGH];
-    const V3<T> dh = (valid && r > T(0)) ? (T(1) / r) * d : v3<T>(0, 0, 0);
-    HbAngles<T> A;
-    A.ready = false;
-    HbGrad<T> HG;
-    const int tab = (sF[i] & 3) * 4 + (sF[j] & 3);
-    if (mask & (1u << MB_TERM_HB)) {
-      if (WP)
-        e[MB_TERM_HB] += hb_term<T, false, true>(sP, 0, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, tab, cot[MB_TERM_HB], HG, sacc);
-      else
-        e[MB_TERM_HB] += hb_term<T, false, false>(sP, 0, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, tab, cot[MB_TERM_HB], HG, nacc);
-    }
-    if (mask & (1u << MB_TERM_CROSS)) {
-      if (WP)
-        e[MB_TERM_CROSS] += cross_term<T, false, true>(sP, 0, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, cot[MB_TERM_CROSS], HG, sacc);
-      else
-        e[MB_TERM_CROSS] += cross_term<T, false, false>(sP, 0, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, cot[MB_TERM_CROSS], HG, nacc);
-    }
-  };
-  auto process_cx = [&](int first, int count) {
-    const int t = threadIdx.x;
-    const bool valid = t < count;
-    const uint32_t pk = valid ? qCX[first + t] : 0u;
-    const int i = pk & 0xffff, j = pk >> 16;
-    const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
-    const V3<T> ds = disp(site(nj, g.stack, T(0), T(0)), site(ni, g.stack, T(0), T(0)), M.box);
-    const T rs = sqrt(dot(ds, ds));
-    const bool in = valid && sP[MB_P_COAX_RCLOW] < rs && rs < sP[MB_P_COAX_RCHIGH];
-    const V3<T> db = disp(site(nj, g.back[0], g.back[1], g.back[2]), site(ni, g.back[0], g.back[1], g.back[2]), M.box);
-    CoaxGrad<T> CG;
-    if (WP)
-      e[MB_TERM_COAX] += coax_term<T, false, true>(sP, 0, F.coax_form, in, ds, rs, db, ni.a1, nj.a1, ni.a3, nj.a3, cot[MB_TERM_COAX], CG, sacc);
-    else
-      e[MB_TERM_COAX] += coax_term<T, false, false>(sP, 0, F.coax_form, in, ds, rs, db, ni.a1, nj.a1, ni.a3, nj.a3, cot[MB_TERM_COAX], CG, nacc);
-  };
-  auto drain = [&](bool all) {
-    // run full CTA batches (and, when `all`, the partial tail) of BP and CX
-    while (true) {
-      const int nb = ctr[1];
-      if (nb >= kFB || (all && nb > 0)) {
-        const int cnt = nb >= kFB ? kFB : nb;
-        process_bp(nb - cnt, cnt);
-        __syncthreads();
-        if (threadIdx.x == 0) ctr[1] = nb - cnt;
-        __syncthreads();
-      } else {
-        break;
-      }
-    }
-    while (true) {
-      const int nc = ctr[2];
-      if (nc >= kFB || (all && nc > 0)) {
-        const int cnt = nc >= kFB ? kFB : nc;
-        process_cx(nc - cnt, cnt);
-        __syncthreads();
-        if (threadIdx.x == 0) ctr[2] = nc - cnt;
-        __syncthreads();
-      } else {
-        break;
-      }
-    }
-  };
-  // ---- phase 2 body ---------------------------------------------------------------------------------
-  auto process_sr = [&](int first, int count) {
-    const int t = threadIdx.x;
-    const bool valid = t < count;
-    const uint32_t pk = valid ? qSR[first + t] : 0u;
-    const int i = pk & 0xffff, j = pk >> 16;
-    const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
-    const V3<T> back_i = site(ni, g.back[0], g.back[1], g.back[2]), back_j = site(nj, g.back[0], g.back[1], g.back[2]);
-    const V3<T> base_i = site(ni, g.base, T(0), T(0)), base_j = site(nj, g.base, T(0), T(0));
-    const V3<T> d_base = disp(base_j, base_i, M.box);
-    if (mask & (1u << MB_TERM_UEXC)) {
-      const T c = cot[MB_TERM_UEXC];
-      V3<T> gs;
-      T ex = T(0);
-      if (WP) {
-        ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BACKBONE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_j, back_i, M.box), c, gs, xacc);
-        ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BASE_RSTAR, MB_P_UEXC_EPS, valid, d_base, c, gs, xacc);
-        ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BACK_BASE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_i, base_j, M.box), c, gs, xacc);
-        ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BASE_BACK_RSTAR, MB_P_UEXC_EPS, valid, disp(base_i, back_j, M.box), c, gs, xacc);
-      } else {
-        ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BACKBONE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_j, back_i, M.box), c, gs, nacc);
-        ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BASE_RSTAR, MB_P_UEXC_EPS, valid, d_base, c, gs, nacc);
-        ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BACK_BASE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_i, base_j, M.box), c, gs, nacc);
-        ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BASE_BACK_RSTAR, MB_P_UEXC_EPS, valid, disp(base_i, back_j, M.box), c, gs, nacc);
-      }
-      e[MB_TERM_UEXC] += ex;
-    }
-    const T r2 = dot(d_base, d_base);
-    const bool to_bp = valid && bp_hi > T(0) && r2 > bp_lo * bp_lo && r2 < bp_hi * bp_hi;
-    bool to_cx = false;
-    if (mask & (1u << MB_TERM_COAX)) {
-      const V3<T> ds = disp(site(nj, g.stack, T(0), T(0)), site(ni, g.stack, T(0), T(0)), M.box);
-      const T s2 = dot(ds, ds);
-      to_cx = valid && s2 > sP[MB_P_COAX_RCLOW] * sP[MB_P_COAX_RCLOW] && s2 < sP[MB_P_COAX_RCHIGH] * sP[MB_P_COAX_RCHIGH];
-    }
-    q_push(qBP, &ctr[1], wcnt, to_bp, pk);
-    q_push(qCX, &ctr[2], wcnt, to_cx, pk);
-  };
-
-  // ---- phase 1: stream the frame's pair list -----------------------------------------------------------
+  // ---- one scheduler loop; every phase body appears exactly once so it is inlined and its accumulators stay
+  // in registers.  All conditions are CTA-uniform (queue counters live in shared memory, read after barriers).
   if ((mask & MB_UNBONDED_TERMS) && a.pair_capacity > 0) {
     const int32_t* pl = a.pairs + (long long)frame * a.pair_frame_stride;
     long long count = a.pair_capacity;
@@ -312,50 +205,139 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a) {
       const long long c = a.pair_count[frame];
       count = c < count ? c : count;
     }
-    for (long long base = 0; base < count; base += kFB) {
-      const long long k = base + threadIdx.x;
-      int i = 0, j = 0;
-      bool valid = k < count;
-      if (valid) {
-        i = pl[k];
-        j = pl[a.pair_capacity + k];
-        valid = (i >= 0 && j >= 0 && i < n && j < n);
-        if (!valid) i = j = 0;
-      }
-      const V3<T> ci = v3<T>(sC[3 * i], sC[3 * i + 1], sC[3 * i + 2]), cj = v3<T>(sC[3 * j], sC[3 * j + 1], sC[3 * j + 2]);
-      const V3<T> dc = disp(cj, ci, M.box);
-      const T d2 = dot(dc, dc);
-      if (want_debye) {
-        // only when the backbone sites can be inside r_cut: |back_j - back_i| >= |dc| - 2|back offset|
+    long long base = 0;
+    bool flush = false;
+    while (true) {
+      const int n_sr = ctr[0], n_bp = ctr[1], n_cx = ctr[2];
+      __syncthreads();  // everyone has read the counters before anyone updates them
+      if (n_bp >= kFB || (flush && n_bp > 0)) {
+        // ---------------- phase 3a: hydrogen bonding + cross stacking on the BP queue
+        const int cnt = n_bp >= kFB ? kFB : n_bp;
+        const int t = threadIdx.x;
+        const bool valid = t < cnt;
+        const uint32_t pk = valid ? qBP[n_bp - cnt + t] : 0u;
+        const int i = pk & 0xffff, j = pk >> 16;
         const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
-        const V3<T> db = disp(site(nj, g.back[0], g.back[1], g.back[2]), site(ni, g.back[0], g.back[1], g.back[2]), M.box);
-        T m = T(1);
-        if (M.half_charged_ends) m = ((sF[i] & 4) ? T(0.5) : T(1)) * ((sF[j] & 4) ? T(0.5) : T(1));
-        V3<T> gd;
-        if (WP)
-          e[MB_TERM_DEBYE] += debye_term<T, false, true>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, dacc);
-        else
-          e[MB_TERM_DEBYE] += debye_term<T, false, false>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, nacc);
-      }
-      if (want_sr) {
-        q_push(qSR, &ctr[0], wcnt, valid && d2 < sr_cut2, uint32_t(i) | (uint32_t(j) << 16));
-        if (ctr[0] >= kFB) {
-          const int ns = ctr[0];
-          process_sr(ns - kFB, kFB);
-          if (threadIdx.x == 0) ctr[0] = ns - kFB;
-          __syncthreads();
-          drain(false);
+        const V3<T> d = disp(site(nj, g.base, T(0), T(0)), site(ni, g.base, T(0), T(0)), M.box);
+        const T r = sqrt(dot(d, d));
+        const bool in_hb = valid && (mask & (1u << MB_TERM_HB)) && sP[MB_P_HB_RCLOW] < r && r < sP[MB_P_HB_RCHIGH];
+        const bool in_cr = valid && (mask & (1u << MB_TERM_CROSS)) && sP[MB_P_CROSS_RCLOW] < r && r < sP[MB_P_CROSS_RCHIGH];
+        const V3<T> dh = (valid && r > T(0)) ? (T(1) / r) * d : v3<T>(0, 0, 0);
+        HbAngles<T> A;
+        A.ready = false;
+        HbGrad<T> HG;
+        const int tab = (sF[i] & 3) * 4 + (sF[j] & 3);
+        if (mask & (1u << MB_TERM_HB)) {
+          if (WP)
+            e[MB_TERM_HB] += hb_term<T, false, true>(sP, 0, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, tab, cot[MB_TERM_HB], HG, sacc);
+          else
+            e[MB_TERM_HB] += hb_term<T, false, false>(sP, 0, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, tab, cot[MB_TERM_HB], HG, nacc);
         }
-      }
-    }
-    if (want_sr) {
-      const int ns = ctr[0];
-      if (ns > 0) {
-        process_sr(0, ns);
-        if (threadIdx.x == 0) ctr[0] = 0;
+        if (mask & (1u << MB_TERM_CROSS)) {
+          if (WP)
+            e[MB_TERM_CROSS] += cross_term<T, false, true>(sP, 0, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, cot[MB_TERM_CROSS], HG, sacc);
+          else
+            e[MB_TERM_CROSS] += cross_term<T, false, false>(sP, 0, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, cot[MB_TERM_CROSS], HG, nacc);
+        }
+        if (threadIdx.x == 0) ctr[1] = n_bp - cnt;
         __syncthreads();
+        continue;
       }
-      drain(true);
+      if (n_cx >= kFB || (flush && n_cx > 0)) {
+        // ---------------- phase 3b: coaxial stacking on the CX queue
+        const int cnt = n_cx >= kFB ? kFB : n_cx;
+        const int t = threadIdx.x;
+        const bool valid = t < cnt;
+        const uint32_t pk = valid ? qCX[n_cx - cnt + t] : 0u;
+        const int i = pk & 0xffff, j = pk >> 16;
+        const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
+        const V3<T> ds = disp(site(nj, g.stack, T(0), T(0)), site(ni, g.stack, T(0), T(0)), M.box);
+        const T rs = sqrt(dot(ds, ds));
+        const bool in = valid && sP[MB_P_COAX_RCLOW] < rs && rs < sP[MB_P_COAX_RCHIGH];
+        const V3<T> db = disp(site(nj, g.back[0], g.back[1], g.back[2]), site(ni, g.back[0], g.back[1], g.back[2]), M.box);
+        CoaxGrad<T> CG;
+        if (WP)
+          e[MB_TERM_COAX] += coax_term<T, false, true>(sP, 0, F.coax_form, in, ds, rs, db, ni.a1, nj.a1, ni.a3, nj.a3, cot[MB_TERM_COAX], CG, sacc);
+        else
+          e[MB_TERM_COAX] += coax_term<T, false, false>(sP, 0, F.coax_form, in, ds, rs, db, ni.a1, nj.a1, ni.a3, nj.a3, cot[MB_TERM_COAX], CG, nacc);
+        if (threadIdx.x == 0) ctr[2] = n_cx - cnt;
+        __syncthreads();
+        continue;
+      }
+      if (n_sr >= kFB || (flush && n_sr > 0)) {
+        // ---------------- phase 2: excluded volume on the SR queue, radial windows feed BP / CX
+        const int cnt = n_sr >= kFB ? kFB : n_sr;
+        const int t = threadIdx.x;
+        const bool valid = t < cnt;
+        const uint32_t pk = valid ? qSR[n_sr - cnt + t] : 0u;
+        const int i = pk & 0xffff, j = pk >> 16;
+        const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
+        const V3<T> back_i = site(ni, g.back[0], g.back[1], g.back[2]), back_j = site(nj, g.back[0], g.back[1], g.back[2]);
+        const V3<T> base_i = site(ni, g.base, T(0), T(0)), base_j = site(nj, g.base, T(0), T(0));
+        const V3<T> d_base = disp(base_j, base_i, M.box);
+        if (mask & (1u << MB_TERM_UEXC)) {
+          const T c = cot[MB_TERM_UEXC];
+          V3<T> gs;
+          T ex = T(0);
+          if (WP) {
+            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BACKBONE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_j, back_i, M.box), c, gs, xacc);
+            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BASE_RSTAR, MB_P_UEXC_EPS, valid, d_base, c, gs, xacc);
+            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BACK_BASE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_i, base_j, M.box), c, gs, xacc);
+            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BASE_BACK_RSTAR, MB_P_UEXC_EPS, valid, disp(base_i, back_j, M.box), c, gs, xacc);
+          } else {
+            ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BACKBONE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_j, back_i, M.box), c, gs, nacc);
+            ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BASE_RSTAR, MB_P_UEXC_EPS, valid, d_base, c, gs, nacc);
+            ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BACK_BASE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_i, base_j, M.box), c, gs, nacc);
+            ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BASE_BACK_RSTAR, MB_P_UEXC_EPS, valid, disp(base_i, back_j, M.box), c, gs, nacc);
+          }
+          e[MB_TERM_UEXC] += ex;
+        }
+        const T r2 = dot(d_base, d_base);
+        const bool to_bp = valid && bp_hi > T(0) && r2 > bp_lo * bp_lo && r2 < bp_hi * bp_hi;
+        bool to_cx = false;
+        if (mask & (1u << MB_TERM_COAX)) {
+          const V3<T> ds = disp(site(nj, g.stack, T(0), T(0)), site(ni, g.stack, T(0), T(0)), M.box);
+          const T s2 = dot(ds, ds);
+          to_cx = valid && s2 > sP[MB_P_COAX_RCLOW] * sP[MB_P_COAX_RCLOW] && s2 < sP[MB_P_COAX_RCHIGH] * sP[MB_P_COAX_RCHIGH];
+        }
+        if (threadIdx.x == 0) ctr[0] = n_sr - cnt;
+        q_push(qBP, &ctr[1], wcnt, to_bp, pk);
+        q_push(qCX, &ctr[2], wcnt, to_cx, pk);
+        continue;
+      }
+      if (flush) break;
+      if (base >= count) {
+        flush = true;
+        continue;
+      }
+      // ---------------- phase 1: one tile of the frame's pair list: Debye-Hueckel, short-range filter
+      {
+        const long long k = base + threadIdx.x;
+        base += kFB;
+        int i = 0, j = 0;
+        bool valid = k < count;
+        if (valid) {
+          i = pl[k];
+          j = pl[a.pair_capacity + k];
+          valid = (i >= 0 && j >= 0 && i < n && j < n);
+          if (!valid) i = j = 0;
+        }
+        const V3<T> ci = v3<T>(sC[3 * i], sC[3 * i + 1], sC[3 * i + 2]), cj = v3<T>(sC[3 * j], sC[3 * j + 1], sC[3 * j + 2]);
+        const V3<T> dc = disp(cj, ci, M.box);
+        const T d2 = dot(dc, dc);
+        if (want_debye) {
+          const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
+          const V3<T> db = disp(site(nj, g.back[0], g.back[1], g.back[2]), site(ni, g.back[0], g.back[1], g.back[2]), M.box);
+          T m = T(1);
+          if (M.half_charged_ends) m = ((sF[i] & 4) ? T(0.5) : T(1)) * ((sF[j] & 4) ? T(0.5) : T(1));
+          V3<T> gd;
+          if (WP)
+            e[MB_TERM_DEBYE] += debye_term<T, false, true>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, dacc);
+          else
+            e[MB_TERM_DEBYE] += debye_term<T, false, false>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, nacc);
+        }
+        if (want_sr) q_push(qSR, &ctr[0], wcnt, valid && d2 < sr_cut2, uint32_t(i) | (uint32_t(j) << 16));
+      }
     }
   }
 

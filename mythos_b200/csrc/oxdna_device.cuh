@@ -137,11 +137,13 @@ struct Geom {
   T back[3], back_stack, stack, base, stack3[2], stack5[2], p3[3], p5[3];
   int use_back_stack;
   MB_HD void load(const mb_flavour_geom& g) {
+    #pragma unroll
     for (int k = 0; k < 3; ++k) {
       back[k] = T(g.back[k]);
       p3[k] = T(g.p3[k]);
       p5[k] = T(g.p5[k]);
     }
+    #pragma unroll
     for (int k = 0; k < 2; ++k) {
       stack3[k] = T(g.stack3[k]);
       stack5[k] = T(g.stack5[k]);
@@ -529,6 +531,7 @@ MB_HD T stack_term(const T* P, int bank, int form, bool act, const V3<T>& ds, co
   bool nz = false;
   const bool rna = (form == MB_STACK_RNA);
   const int b4[5] = {MB_P_STACK_T4_TH0, MB_P_STACK_T5_TH0, MB_P_STACK_T6_TH0, MB_P_STACK_T9_TH0, MB_P_STACK_T10_TH0};
+  #pragma unroll
   for (int k = 0; k < 7; ++k) {
     f[k] = T(1);
     df[k] = dth[k] = arg[k] = T(0);
@@ -568,6 +571,7 @@ MB_HD T stack_term(const T* P, int bank, int form, bool act, const V3<T>& ds, co
       arg[6] = dot(a2j, bh);
       f[6] = f5_val(arg[6], P + MB_P_STACK_PHI2_XSTAR, df[6]);
       T prod = f[0];
+      #pragma unroll
       for (int k = 1; k < 7; ++k) prod *= f[k];
       if (prod != T(0)) {
         nz = true;
@@ -582,7 +586,9 @@ MB_HD T stack_term(const T* P, int bank, int form, bool act, const V3<T>& ds, co
     T pre = nz ? cot * w : T(0);
     T suf[8];
     suf[7] = T(1);
+    #pragma unroll
     for (int k = 6; k >= 0; --k) suf[k] = suf[k + 1] * f[k];
+    #pragma unroll
     for (int k = 0; k < 7; ++k) {
       oth[k] = pre * suf[k + 1];
       pre *= f[k];
@@ -690,6 +696,7 @@ MB_HD T hb_term(const T* P, int bank, bool act, T r, const V3<T>& dh, const V3<T
   T e = 0, w = 0, fr = 0, dfr = 0;
   T f[6], df[6];
   bool nz = false;
+  #pragma unroll
   for (int k = 0; k < 6; ++k) {
     f[k] = T(1);
     df[k] = T(0);
@@ -701,6 +708,7 @@ MB_HD T hb_term(const T* P, int bank, bool act, T r, const V3<T>& dh, const V3<T
       if (fr != T(0)) {
         if (!A.ready) hb_angles(dh, a1i, a1j, a3i, a3j, A);
         T prod = fr;
+        #pragma unroll
         for (int k = 0; k < 6; ++k) {
           f[k] = f4_val(A.th[k], P + b4[k], df[k]);
           prod *= f[k];
@@ -718,9 +726,11 @@ MB_HD T hb_term(const T* P, int bank, bool act, T r, const V3<T>& dh, const V3<T
     T pre = nz ? cot * w : T(0);
     T suf[7];
     suf[6] = T(1);
+    #pragma unroll
     for (int k = 5; k >= 0; --k) suf[k] = suf[k + 1] * f[k];
     othr = pre * suf[0];
     pre *= fr;
+    #pragma unroll
     for (int k = 0; k < 6; ++k) {
       oth[k] = pre * suf[k + 1];
       pre *= f[k];
@@ -728,11 +738,13 @@ MB_HD T hb_term(const T* P, int bank, bool act, T r, const V3<T>& dh, const V3<T
   }
   if (WF && nz) {
     T gx[6];
+    #pragma unroll
     for (int k = 0; k < 6; ++k) gx[k] = oth[k] * df[k] * A.dth[k];
     hb_scatter(gx, dh, r, othr * dfr, a1i, a1j, a3i, a3j, G);
   }
   if (WP) {
     f1_par(r, P + MB_P_HB_RLOW, othr, bank, MB_P_HB_RLOW, acc);
+    #pragma unroll
     for (int k = 0; k < 6; ++k) {
       T g[4] = {T(0), T(0), T(0), T(0)};
       if (nz) f4_par_add(A.th[k], P + b4[k], oth[k], g);
@@ -754,6 +766,7 @@ MB_HD T cross_term(const T* P, int bank, int form, bool act, T r, const V3<T>& d
   T f[6], df[6];
   bool nz = false;
   const bool rna = (form == MB_CROSS_RNA2);
+  #pragma unroll
   for (int k = 0; k < 6; ++k) {
     f[k] = T(1);
     df[k] = T(0);
@@ -763,6 +776,7 @@ MB_HD T cross_term(const T* P, int bank, int form, bool act, T r, const V3<T>& d
     if (fr != T(0)) {
       if (!A.ready) hb_angles(dh, a1i, a1j, a3i, a3j, A);
       T prod = fr;
+      #pragma unroll
       for (int k = 0; k < 6; ++k) {
         if (k < 3) {
           f[k] = f4_val(A.th[k], P + b4[k], df[k]);
@@ -788,9 +802,11 @@ MB_HD T cross_term(const T* P, int bank, int form, bool act, T r, const V3<T>& d
     T pre = nz ? cot : T(0);
     T suf[7];
     suf[6] = T(1);
+    #pragma unroll
     for (int k = 5; k >= 0; --k) suf[k] = suf[k + 1] * f[k];
     othr = pre * suf[0];
     pre *= fr;
+    #pragma unroll
     for (int k = 0; k < 6; ++k) {
       oth[k] = pre * suf[k + 1];
       pre *= f[k];
@@ -798,11 +814,13 @@ MB_HD T cross_term(const T* P, int bank, int form, bool act, T r, const V3<T>& d
   }
   if (WF && nz) {
     T gx[6];
+    #pragma unroll
     for (int k = 0; k < 6; ++k) gx[k] = oth[k] * df[k] * A.dth[k];
     hb_scatter(gx, dh, r, othr * dfr, a1i, a1j, a3i, a3j, G);
   }
   if (WP) {
     f2_par(r, P + MB_P_CROSS_RLOW, othr, bank, MB_P_CROSS_RLOW, acc);
+    #pragma unroll
     for (int k = 0; k < 6; ++k) {
       T g[4] = {T(0), T(0), T(0), T(0)};
       if (nz && !(k == 3 && rna)) {
@@ -836,10 +854,12 @@ MB_HD T coax_term(const T* P, int bank, int form, bool act, const V3<T>& ds, T r
   T f[6], df[6], th[4], dth[4], cphi[2];
   V3<T> sh = v3<T>(0, 0, 0), bh = sh;
   bool nz = false;
+  #pragma unroll
   for (int k = 0; k < 6; ++k) {
     f[k] = T(1);
     df[k] = T(0);
   }
+  #pragma unroll
   for (int k = 0; k < 4; ++k) th[k] = dth[k] = T(0);
   cphi[0] = cphi[1] = T(0);
   if (act) {
@@ -873,6 +893,7 @@ MB_HD T coax_term(const T* P, int bank, int form, bool act, const V3<T>& ds, T r
         f[5] = f5_val(cphi[1], P + MB_P_COAX_PHI4_XSTAR, df[5]);
       }
       T prod = fr;
+      #pragma unroll
       for (int k = 0; k < 6; ++k) prod *= f[k];
       if (prod != T(0)) {
         nz = true;
@@ -886,9 +907,11 @@ MB_HD T coax_term(const T* P, int bank, int form, bool act, const V3<T>& ds, T r
     T pre = nz ? cot : T(0);
     T suf[7];
     suf[6] = T(1);
+    #pragma unroll
     for (int k = 5; k >= 0; --k) suf[k] = suf[k + 1] * f[k];
     othr = pre * suf[0];
     pre *= fr;
+    #pragma unroll
     for (int k = 0; k < 6; ++k) {
       oth[k] = pre * suf[k + 1];
       pre *= f[k];
@@ -942,6 +965,7 @@ MB_HD T coax_term(const T* P, int bank, int form, bool act, const V3<T>& ds, T r
       }
     }
     f4_par_flush(g, bank, b4[1], acc);
+    #pragma unroll
     for (int k = 2; k < 4; ++k) {
       g[0] = g[1] = g[2] = g[3] = T(0);
       if (nz) {
@@ -1021,6 +1045,7 @@ struct ModelT {
     geom[0].load(m.geom[0]);
     geom[1].load(m.geom[1]);
     for (int b = 0; b < MB_MAX_BANKS; ++b) forms[b] = m.forms[b];
+    #pragma unroll
     for (int k = 0; k < 3; ++k) box[k] = T(m.box[k]);
     n_banks = m.n_banks;
     half_charged_ends = m.half_charged_ends;
