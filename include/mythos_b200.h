@@ -411,7 +411,11 @@ typedef struct mb_langevin_args {
   uint64_t seed, step;    /* counter-based RNG: noise = philox(seed, step, nucleotide) */
   const void* noise;      /* optional (N,6) standard normals (3 linear + 3 angular) overriding the RNG */
   int32_t phase;          /* 0 = B A O A (first part), 1 = closing B, 2 = closing B of the previous step fused with 0 */
-  int32_t _pad;
+  int32_t advance_step;   /* after the step, add 1 to *step_ptr on the stream (one-node-per-step CUDA graphs)      */
+  const void* step_ptr;   /* optional device uint64 step counter: RNG counter and trajectory row; overrides `step` */
+  void* traj_center;      /* optional out (traj_rows,N,3): positions after this call's drift at row *step_ptr      */
+  void* traj_quat;        /* optional out (traj_rows,N,4)                                                          */
+  int64_t traj_rows;
 } mb_langevin_args;
 int mythos_b200_langevin_f64(void* cuda_stream, const mb_langevin_args* a);
 int mythos_b200_langevin_f32(void* cuda_stream, const mb_langevin_args* a);

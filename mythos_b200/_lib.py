@@ -136,7 +136,11 @@ class LangevinArgs(C.Structure):
         ("step", C.c_uint64),
         ("noise", C.c_void_p),
         ("phase", C.c_int32),
-        ("_pad", C.c_int32),
+        ("advance_step", C.c_int32),
+        ("step_ptr", C.c_void_p),
+        ("traj_center", C.c_void_p),
+        ("traj_quat", C.c_void_p),
+        ("traj_rows", C.c_int64),
     ]
 
 

@@ -74,6 +74,10 @@ struct LangevinDev {
   const T* noise;
   T dt, kT, gamma_c, gamma_q, mass, inertia[3], box[3];
   uint64_t seed, step;
+  const unsigned long long* step_ptr;  // device-side step counter (CUDA-graph replays), overrides `step`
+  T* traj_center;                      // optional (S,N,3): position after this step is stored at row *step_ptr
+  T* traj_quat;
+  long long traj_rows;
 };
 
 template <class T>
@@ -143,7 +147,7 @@ __global__ void k_langevin(LangevinDev<T> a) {
         if (a.noise) {
           for (int k = 0; k < 6; ++k) z[k] = double(a.noise[6 * i + k]);
         } else {
-          normals6(a.seed, a.step, uint32_t(i), z);
+          normals6(a.seed, a.step_ptr ? (uint64_t)(*a.step_ptr) : a.step, uint32_t(i), z);
         }
         const T c1 = exp(-a.gamma_c * a.dt);
         const T c2 = sqrt(a.kT * (T(1) - c1 * c1) * a.mass);
@@ -167,10 +171,19 @@ __global__ void k_langevin(LangevinDev<T> a) {
     }
     for (int d = 0; d < 3; ++d) a.center[3 * i + d] = c[d];
     for (int d = 0; d < 4; ++d) a.quat[4 * i + d] = q[d];
+    if (a.traj_center && a.step_ptr) {
+      const long long row = (long long)(*a.step_ptr);
+      if (row < a.traj_rows) {
+        for (int d = 0; d < 3; ++d) a.traj_center[(row * a.n + i) * 3 + d] = c[d];
+        for (int d = 0; d < 4; ++d) a.traj_quat[(row * a.n + i) * 4 + d] = q[d];
+      }
+    }
   }
   for (int d = 0; d < 3; ++d) a.p_center[3 * i + d] = pc[d];
   for (int d = 0; d < 4; ++d) a.p_quat[4 * i + d] = pq[d];
 }
+
+__global__ void k_advance(unsigned long long* p) { *p += 1ull; }
 
 template <class T>
 static int langevin_impl(cudaStream_t s, const mb_langevin_args* x) {
@@ -201,7 +214,13 @@ static int langevin_impl(cudaStream_t s, const mb_langevin_args* x) {
   }
   a.seed = x->seed;
   a.step = x->step;
+  a.step_ptr = static_cast<const unsigned long long*>(x->step_ptr);
+  a.traj_center = static_cast<T*>(x->traj_center);
+  a.traj_quat = static_cast<T*>(x->traj_quat);
+  a.traj_rows = x->traj_rows;
+  MB_REQUIRE(!x->traj_center || (x->traj_quat && x->step_ptr), MB_EINVAL_SHAPE, "langevin: trajectory output needs traj_quat and step_ptr");
   k_langevin<T><<<ceil_div(x->n, 128), 128, 0, s>>>(a);
+  if (x->step_ptr && x->advance_step) k_advance<<<1, 1, 0, s>>>(static_cast<unsigned long long*>(const_cast<void*>(x->step_ptr)));
   MB_CUDA_CHECK(cudaGetLastError());
   return MB_OK;
 }
