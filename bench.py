@@ -199,12 +199,7 @@ def main():
     ones = torch.ones((hi - lo, _lib.N_TERMS), dtype=torch.float64, device=dev)
 
     def gather(e_local):
-        if world == 1:
-            return e_local
-        sizes = [objective.shard_bounds(F, r, world) for r in range(world)]
-        chunks = [torch.empty(b - a, dtype=e_local.dtype, device=dev) for a, b in sizes]
-        dist.all_gather(chunks, e_local.contiguous())
-        return torch.cat(chunks)
+        return e_local if world == 1 else objective.gather_frames(e_local, F)
 
     def device_pass(e_ref):
         terms, _, _, J = functional.energy_and_gradients(

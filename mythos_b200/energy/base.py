@@ -110,7 +110,8 @@ class BaseEnergyFunction(EnergyFunction):
         if topology is not None:
             object.__setattr__(self, "seq", topology.seq)
             object.__setattr__(self, "bonded_neighbors", topology.bonded_neighbors)
-            object.__setattr__(self, "unbonded_neighbors", topology.unbonded_neighbors.T)
+            ub_t = getattr(topology, "unbonded_neighbors_t", None)
+            object.__setattr__(self, "unbonded_neighbors", topology.unbonded_neighbors.T if ub_t is None else ub_t)
         elif any(x is None for x in (self.seq, self.bonded_neighbors, self.unbonded_neighbors)):
             raise ValueError("Missing topology information")
 

@@ -103,6 +103,13 @@ class Topology:
             return AllPairs(self.n_nucleotides)
         return unbonded_pairs(self.n_nucleotides, self.bonded_neighbors)
 
+    @cached_property
+    def unbonded_neighbors_t(self):
+        """The (2,U) orientation the energy functions store -- one shared object, so that all terms built from this
+        topology are recognised as using the same list and fuse into one launch."""
+        ub = self.unbonded_neighbors
+        return ub if isinstance(ub, AllPairs) else np.ascontiguousarray(ub.T)
+
 
 def from_strands(sequences: list[str], nt_types: list[int] | None = None, circular: list[bool] | None = None) -> Topology:
     """Topology from per-strand sequences given in the internal 3'->5' order."""

@@ -144,6 +144,18 @@ def shard_bounds(n_frames: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def gather_frames(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """all_gather of contiguous per-rank blocks (sizes may differ by one: blocks are padded to the widest)."""
+    rank, world = _world()
+    sizes = [hi - lo for lo, hi in (shard_bounds(n_total, r, world) for r in range(world))]
+    width = max(sizes)
+    padded = torch.zeros(width, dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    chunks = [torch.empty(width, dtype=local.dtype, device=local.device) for _ in range(world)]
+    dist.all_gather(chunks, padded)
+    return torch.cat([c[:s] for c, s in zip(chunks, sizes)])
+
+
 class _GatherFrames(torch.autograd.Function):
     """all_gather of per-rank frame energies into the full (F,) vector; backward keeps this rank's slice of the
     cotangent (every rank evaluates the same loss on the same full vector, so no reduction is needed here)."""
@@ -152,10 +164,7 @@ class _GatherFrames(torch.autograd.Function):
     def forward(ctx, local, n_total):
         rank, world = _world()
         ctx.bounds = shard_bounds(n_total, rank, world)
-        sizes = [shard_bounds(n_total, r, world) for r in range(world)]
-        chunks = [torch.empty(hi - lo, dtype=local.dtype, device=local.device) for lo, hi in sizes]
-        dist.all_gather(chunks, local.contiguous())
-        return torch.cat(chunks)
+        return gather_frames(local, n_total)
 
     @staticmethod
     def backward(ctx, g):
