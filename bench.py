@@ -120,6 +120,44 @@ def workload_name(frames: int) -> str:
             f"({N_DUPLEX} duplexes, pitch {PITCH}), F={frames} frames, frame-sharded, float64")
 
 
+def md_benchmark(dev, n_steps: int = 10000):
+    """BASELINE.json configs[1]: oxDNA1 rigid-body Langevin MD of a 60-bp duplex (N = 120), 10^4 steps, all-pairs list
+    (as the reference example), float64, CUDA-graph replay of the fused step -> nucleotide-steps/s (device time)."""
+    from mythos_b200 import space
+    from mythos_b200.energy import dna1
+    from mythos_b200.input.topology import from_strands
+    from mythos_b200.rigid_body import Quaternion, RigidBody
+    from mythos_b200.simulators import md
+    from mythos_b200.utils import synthetic
+
+    c, q, _ = synthetic.ideal_duplex(60)
+    rng = np.random.default_rng(0)
+    seq1 = "".join("ACGT"[k] for k in rng.integers(0, 4, 60))
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    top = from_strands([seq1, "".join(comp[b] for b in reversed(seq1))])
+    c, q = synthetic.jitter(c, q, rng)
+    efn = dna1.create_default_energy_fn(top)
+    kT = 296.15 * 0.1 / 300.0
+    params = md.StaticSimulatorParams(
+        seq=top.seq, mass=RigidBody(torch.tensor(1.0), torch.tensor([1.0, 1.0, 1.0])),
+        gamma=RigidBody(torch.tensor(kT / 2.5), torch.tensor([kT / 7.5] * 3)), bonded_neighbors=top.bonded_neighbors,
+        checkpoint_every=0, dt=5e-3, kT=kT)
+    sim = md.MDSimulator(energy_fn=efn, simulator_params=params, space=space.free())
+    body = RigidBody(torch.tensor(c, device=dev), Quaternion(torch.tensor(q, device=dev)))
+    sim.run({}, body, 200, key=1)  # warm-up (allocator, graph machinery)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    traj = sim.run({}, body, n_steps, key=2)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    e_last = float(efn(RigidBody(traj.center[-1], Quaternion(traj.orientation.vec[-1]))))
+    return {"metric": "MD nucleotide-steps/s", "value": 120 * n_steps / (ms * 1e-3), "unit": "nucleotide-steps/s",
+            "workload": "configs[1]: oxDNA1 Langevin MD, 60-bp duplex (N=120), 10^4 steps, all-pairs list (U=7021), float64",
+            "ms_total": ms, "us_per_step": 1e3 * ms / n_steps, "final_energy_per_nt": e_last / 120}
+
+
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -330,6 +368,10 @@ def main():
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                         "sample": f"{args.cpu_frames} frames of the same workload (oracle: torch-f64 restatement of the reference algorithm, autograd for dE/dparams)"}
 
+    md_line = None
+    if world == 1:
+        md_line = md_benchmark(dev)
+
     n_chunks = -(-(hi - lo) // functional.FRAME_CHUNK)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -340,7 +382,7 @@ def main():
                    "loss": float(loss.detach()), "n_eff": float(neff.detach()), "grad_norm": float(dp.norm())},
         "e2e": {"value": F / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": args.steps * (n_chunks * (11 + 2) + 1),
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "md": md_line,
     }
     print(json.dumps(line))
     if world > 1:
