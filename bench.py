@@ -310,10 +310,11 @@ def main():
         return
 
     # ---- dominant kernel: unbonded pairs, E + dE/dparams, timed alone with CUDA events per launch ----
-    chunk = min(functional.FRAME_CHUNK, hi - lo)
+    chunk = min(1184, hi - lo)  # 8 waves of 148 CTAs
     cc, qq = c_dev[:chunk].contiguous(), q_dev[:chunk].contiguous()
     rng_cut = kmodel.interaction_range(plan)
-    cap = max(source.capacity, 64)
+    _, probe, _, _ = neighbors.build_pairs(cc[:8], topo.bonded, tuple(plan.model.box), rng_cut, 0.0, 1)
+    cap = int(int(probe.max()) * 1.1) + 64
     pairs, count, _, _ = neighbors.build_pairs(cc, topo.bonded, tuple(plan.model.box), rng_cut, 0.0, cap)
     u_nl = float(count.double().mean())
     i, j = pairs[:8, 0].long(), pairs[:8, 1].long()
@@ -326,12 +327,15 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(dev)
         e0.record()
-        functional._launch(plan.model, topo, cc, qq, params_dev, pairs, 2 * cap, _lib.UNBONDED_TERMS, ones[:chunk], True, False, True, True)
+        # the hot kernel exactly as the timed step runs it: all terms, all-pairs mode (in-kernel cell list), E + J rows
+        functional._launch(plan.model, topo, cc, qq, params_dev, None, 0, _lib.ALL_TERMS, ones[:chunk], True, False, True, True,
+                           None, 0, rng_cut)
         e1.record()
         torch.cuda.synchronize(dev)
         launches.append(e0.elapsed_time(e1))
     k_ms = float(np.median(launches[1:]))
-    slots_fwd = chunk * ((30 * u_nl + 65 * u_lr + 820 * u_sr) / 2 + S_LR * u_lr + S_SR * u_sr)
+    n_b = int(topo.bonded.shape[0])
+    slots_fwd = chunk * ((60 * n + 290 * n_b + 30 * u_nl + 65 * u_lr + 820 * u_sr) / 2 + S_BONDED * n_b + S_LR * u_lr + S_SR * u_sr)
     flop_eq = 2 * 2.5 * slots_fwd  # E + params-only backward = 2.5 x forward; 1 FMA slot = 2 flop
     achieved = flop_eq / (k_ms * 1e-3) / 1e12
 
@@ -348,9 +352,9 @@ def main():
         best = max(best, 148 * 32 * 256 * 4096 * 16 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    alg_bytes = chunk * (n * 7 * 8 + u_nl * 8 + 232 * 8 + 64)
+    alg_bytes = chunk * (n * 7 * 8 + 232 * 8 + 64)  # frame in, J row + terms row out; pair lists never exist in HBM
     roofline = {
-        "bound": "fp64", "kernel": "k_pairs<double,WF=0,WP=1,unbonded>", "achieved": achieved, "peak": best, "unit": "TFLOP/s",
+        "bound": "fp64", "kernel": "k_frame_energy<double,WP=1> (all terms, in-kernel cell list)", "achieved": achieved, "peak": best, "unit": "TFLOP/s",
         "frac": achieved / best if best else None, "traffic": None,
         "peak_source": "measured in this run (library FMA micro-benchmark, 148x32 blocks x 256 threads)",
         "kernel_ms_per_launch": k_ms, "frames_per_launch": chunk,
@@ -372,7 +376,7 @@ def main():
     if world == 1:
         md_line = md_benchmark(dev)
 
-    n_chunks = -(-(hi - lo) // functional.FRAME_CHUNK)
+    n_chunks = 1  # all-pairs mode: one frame-kernel launch covers the rank's whole block of frames
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -381,7 +385,7 @@ def main():
                    "l2": "inputs larger than L2 (frames 936 MB + per-chunk pair lists)", "n_theta": len(theta),
                    "loss": float(loss.detach()), "n_eff": float(neff.detach()), "grad_norm": float(dp.norm())},
         "e2e": {"value": F / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": args.steps * (n_chunks * (11 + 2) + 1),
+        "gpu_launches": args.steps * (n_chunks * 1 + 1),  # k_frame_energy + k_weights per step (torch glue not counted)
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "md": md_line,
     }
     print(json.dumps(line))

@@ -364,6 +364,11 @@ typedef struct mb_energy_args {
   void* d_params;         /* out (n_banks*MB_P_COUNT) per row, or NULL                                       */
   int64_t d_params_frame_stride; /* elements between rows of consecutive frames; 0 = one row summed over frames */
   const int32_t* pair_count; /* (F) number of valid pairs at the head of each frame's list (as mb_nl_args.count), or NULL */
+  double all_pairs_cutoff;   /* > 0: all-pairs semantics (topology.unbonded_neighbors, topology.py:186-190): `pairs` is
+                              * ignored and every non-bonded i<j whose centres are closer than this is evaluated, found by a
+                              * shared-memory cell list inside the kernel.  The caller passes the interaction range of its
+                              * parameters (all terms have compact support).  MB_ECAPACITY if the frame-resident kernel
+                              * does not apply (3 banks, position gradients requested, frame too large for shared memory) */
 } mb_energy_args;
 #define MB_FLAG_ACCUMULATE 0x1u /* add into the outputs instead of zeroing them first */
 #define MB_FLAG_GENERIC_KERNEL 0x2u /* force the one-thread-per-pair kernels even where the frame-resident kernel applies */

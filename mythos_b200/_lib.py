@@ -94,6 +94,7 @@ class EnergyArgs(C.Structure):
         ("d_params", C.c_void_p),
         ("d_params_frame_stride", C.c_int64),
         ("pair_count", C.c_void_p),
+        ("all_pairs_cutoff", C.c_double),
     ]
 
 
@@ -199,7 +200,9 @@ def lib() -> C.CDLL:
 def check(status: int, what: str) -> None:
     if status != 0:
         msg = lib().mythos_b200_last_error().decode()
-        raise MythosB200Error(f"{what}: {STATUS.get(status, status)}: {msg}")
+        err = MythosB200Error(f"{what}: {STATUS.get(status, status)}: {msg}")
+        err.status = status
+        raise err
 
 
 @lru_cache(maxsize=1)

@@ -22,6 +22,7 @@ struct EnergyDev {
   const int32_t* pairs;
   long long pair_capacity, pair_frame_stride;
   const int32_t* pair_count;  // (F) valid entries at the head of each list, or nullptr
+  T all_pairs_cutoff;         // > 0: ignore `pairs`; every non-bonded i<j closer than this (frame-resident kernel only)
   const T* params;
   const T* cot;
   unsigned mask;

@@ -161,6 +161,11 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
   MB_REQUIRE(m.n_banks == 1 || x->nt_type, MB_EINVAL_SHAPE, "energy: nt_type required for the 3-bank (NA1) model");
   MB_REQUIRE(x->n_bonded == 0 || x->bonded, MB_EINVAL_SHAPE, "energy: bonded list missing");
   MB_REQUIRE(x->pair_capacity == 0 || x->pairs, MB_EINVAL_SHAPE, "energy: pair list missing");
+  MB_REQUIRE(!(x->all_pairs_cutoff < 0), MB_EINVAL_SHAPE, "energy: all_pairs_cutoff must be >= 0");
+  {
+    const bool any = m.box[0] > 0 || m.box[1] > 0 || m.box[2] > 0, all = m.box[0] > 0 && m.box[1] > 0 && m.box[2] > 0;
+    MB_REQUIRE(!any || all, MB_EINVAL_MODEL, "energy: box must be all zero (free space) or all positive");
+  }
   MB_REQUIRE(x->terms || x->d_center || x->d_quat || x->d_params, MB_EINVAL_SHAPE, "energy: no output requested");
   for (int b = 0; b < m.n_banks; ++b) {
     MB_REQUIRE(m.forms[b].stack_form >= 0 && m.forms[b].stack_form <= 1 && m.forms[b].cross_form >= 0 &&
@@ -183,6 +188,7 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
   a.pair_capacity = x->pair_capacity;
   a.pair_frame_stride = x->pair_frame_stride;
   a.pair_count = x->pair_count;
+  a.all_pairs_cutoff = T(x->all_pairs_cutoff);
   a.params = static_cast<const T*>(x->params);
   a.cot = static_cast<const T*>(x->cot);
   a.mask = x->term_mask;
@@ -207,6 +213,9 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
   const bool wf = a.d_center || a.d_quat, wp = a.d_params != nullptr;
   // frame-resident path: one block per frame with the frame staged in shared memory (energies and dE/dparams only)
   if (!wf && !(x->flags & MB_FLAG_GENERIC_KERNEL) && frame_kernel_eligible<T>(a)) return launch_frame_kernel<T>(s, a, wp);
+  MB_REQUIRE(!(x->all_pairs_cutoff > 0), MB_ECAPACITY,
+             "energy: all_pairs_cutoff needs the frame-resident kernel (single bank, no position gradients, frame fits in "
+             "shared memory); build a neighbour list with mythos_b200_nl_build_* instead");
   if (wf && wp) return launch_pairs<T, true, true>(s, a);
   if (wf) return launch_pairs<T, true, false>(s, a);
   if (wp) return launch_pairs<T, false, true>(s, a);

@@ -1,21 +1,28 @@
 // frame_kernels.cu -- frame-resident energy + dE/dparams kernel (the DiffTRe / EnergyFunction.map shape).
 //
-// One CTA owns one stored frame.  The frame's (center, quaternion) rows are staged once in shared memory
-// (56 B per nucleotide in float64 -> 114 KB at N = 2040, inside the 227 KB a CTA may use on sm_100a), and every
-// pair of the frame is evaluated from there; nothing per-pair is ever written back to HBM.  Work is regrouped
-// so that each code region runs with (nearly) full warps -- the generic one-thread-per-pair kernel spent 93 % of
-// its issue slots waiting on instruction fetch because every lane wandered through a 229 KB instruction stream:
+// One CTA owns one stored frame.  The frame's (center, quaternion) rows -- and, when they fit, the backbone sites
+// -- are staged once in shared memory (56 + 24 B per nucleotide in float64: 163 KB at N = 2040, inside the 227 KB a
+// CTA may use on sm_100a), and every pair of the frame is found AND evaluated from there: in all-pairs mode
+// (the reference's `topology.unbonded_neighbors` semantics) the CTA bins its nucleotides into a shared-memory cell
+// list and walks cell pairs itself, so no pair list ever exists in HBM; with an explicit list the list is streamed.
 //
-//   phase B  bonded pairs (FENE, bonded excluded volume, stacking), one thread per bond
-//   phase 1  every listed pair: centre distance, Debye-Hueckel on the backbone sites; parameter gradients in
-//            REGISTERS; pairs inside the short-range cutoff are compacted into queue SR (shared memory)
-//   phase 2  when SR holds a CTA-full: excluded volume (4 site pairs), gradients in registers; pairs inside the
-//            hydrogen-bond / cross-stacking radial window go to queue BP, inside the coaxial window to queue CX
-//   phase 3  when BP / CX hold a CTA-full: the six-angle products with dense lanes; their parameter gradients are
-//            warp-reduced into the shared-memory bank image
-//   flush    partial queues, register accumulators -> bank image -> one J row, per-term energies -> one terms row
+// Work is regrouped so that each code region runs with (nearly) full warps -- the generic one-thread-per-pair
+// kernel spent 93 % of its issue slots waiting on instruction fetch because every lane wandered through a 229 KB
+// instruction stream (profiles/r01_v1_*):
 //
-// Queue order is made deterministic (block prefix over warp ballots), so results are bitwise repeatable.
+//   phase B   bonded pairs (FENE, bonded excluded volume, stacking), one thread per bond
+//   producer  all-pairs mode: each warp walks one (cell, half-shell neighbour cell) tile of the shared-memory cell list,
+//             lanes over the flattened member pairs; accepted pairs are staged per warp and merged in warp order
+//             (deterministic) into queue NL.   list mode: one tile of the frame's pair list goes into queue NL.
+//   phase 1   a CTA-full of queue NL: Debye-Hueckel on the (cached) backbone sites, parameter gradients in REGISTERS;
+//             pairs inside the short-range centre cutoff are compacted into queue SR
+//   phase 2   a CTA-full of SR: excluded volume (4 site pairs), gradients in registers; pairs inside the hydrogen-bond /
+//             cross-stacking radial window go to queue BP, inside the coaxial window to queue CX
+//   phase 3   a CTA-full of BP / CX: the six-angle products with dense lanes; their parameter gradients are
+//             warp-reduced into the shared-memory bank image
+//   flush     partial queues, register accumulators -> bank image -> one J row, per-term energies -> one terms row
+//
+// Every queue append is ordered (block prefix over warp ballots), so results are bitwise repeatable run to run.
 #include "energy_dev.cuh"
 
 namespace mb {
@@ -25,7 +32,14 @@ namespace mb {
 #endif
 constexpr int kFB = MB_FRAME_THREADS;  // threads per CTA (one CTA per SM: the frame fills most of shared memory)
 constexpr int kFWarps = kFB / 32;
-constexpr int kQCap = 2 * kFB;
+constexpr int kQCap = 2 * kFB;          // SR / BP / CX queues
+constexpr int kSlice = 8;               // candidates one thread examines per producer step (independent, unrolled)
+constexpr int kU1 = 2;                  // pairs per thread in one phase-1 batch (instruction-level parallelism)
+constexpr int kNlCap = kU1 * kFB + kFB * kSlice;
+constexpr int kSrCap = kFB + kU1 * kFB;
+constexpr int kMaxCells = 512;
+constexpr int kMaxRect = 5 * kMaxCells;  // (cell, half-shell row) rectangles of the all-pairs producer
+constexpr int kExcl = 2;                // bonded partners per nucleotide (as the reference's (N,2) dense mask)
 
 template <class T, int BASE, int COUNT>
 struct RegAcc {
@@ -39,31 +53,52 @@ struct RegAcc {
 };
 
 struct FrameSmem {
-  // byte offsets into dynamic shared memory
-  size_t c, q, p, acc, e, flags, q_sr, q_bp, q_cx, wcnt, ctr, total;
+  // byte offsets into dynamic shared memory; computed on the host and passed as a kernel parameter so that the
+  // kernel re-reads them from the constant bank instead of rematerialising the whole chain under register pressure
+  unsigned c, q, back, p, acc, e, flags, q_nl, q_sr, q_bp, q_cx, wcnt, ctr, rect, cstart, corder, excl, grid, total;
 };
 template <class T>
-__host__ __device__ inline FrameSmem frame_smem_layout(int n, bool wp) {
+inline FrameSmem frame_smem_layout(int n, bool wp, bool cache_back, bool cells) {
   FrameSmem L;
-  size_t off = 0;
+  unsigned off = 0;
   auto take = [&](size_t bytes) {
-    size_t o = off;
-    off += (bytes + 15) & ~size_t(15);
+    unsigned o = off;
+    off += (unsigned(bytes) + 15u) & ~15u;
     return o;
   };
   L.c = take(sizeof(T) * 3 * n);
   L.q = take(sizeof(T) * 4 * n);
+  L.back = take(cache_back ? sizeof(T) * 3 * n : 0);
   L.p = take(sizeof(T) * MB_P_COUNT);
   L.acc = take(wp ? sizeof(T) * MB_P_COUNT : 0);
   L.e = take(sizeof(T) * MB_N_TERMS * kFWarps);
   L.flags = take(n);
-  L.q_sr = take(sizeof(uint32_t) * kQCap);
+  L.q_nl = take(sizeof(uint32_t) * kNlCap);
+  L.q_sr = take(sizeof(uint32_t) * kSrCap);
   L.q_bp = take(sizeof(uint32_t) * kQCap);
   L.q_cx = take(sizeof(uint32_t) * kQCap);
   L.wcnt = take(sizeof(int) * (kFWarps + 1));
-  L.ctr = take(sizeof(int) * 4);
+  L.ctr = take(sizeof(int) * 8);
+  L.rect = take(cells ? sizeof(int) * (kMaxRect + 1) : 0);
+  L.cstart = take(cells ? sizeof(int) * (kMaxCells + 1) : 0);
+  L.corder = take(cells ? sizeof(uint16_t) * n : 0);
+  L.excl = take(cells ? sizeof(uint16_t) * kExcl * n : 0);
+  L.grid = take(sizeof(T) * 8 + sizeof(int) * 8);
   L.total = off;
   return L;
+}
+
+// exclusive prefix of the per-warp counts for `warp` (every lane gets it): one load + one shuffle scan
+__device__ __forceinline__ int warp_prefix(const int* wcnt, int warp, int lane) {
+  int x = (lane < kFWarps) ? wcnt[lane] : 0;
+#pragma unroll
+  for (int o = 1; o < kFWarps; o <<= 1) {
+    const int y = __shfl_up_sync(kFull, x, o);
+    if (lane >= o) x += y;
+  }
+  const int incl = __shfl_sync(kFull, x, warp);
+  const int own = __shfl_sync(kFull, (lane < kFWarps) ? wcnt[lane] : 0, warp);
+  return incl - own;
 }
 
 // deterministic block-wide append: entries keep (warp, lane) order
@@ -72,15 +107,35 @@ __device__ __forceinline__ void q_push(uint32_t* q, int* n, int* wcnt, bool pred
   const unsigned m = __ballot_sync(kFull, pred);
   if (lane == 0) wcnt[warp] = __popc(m);
   __syncthreads();
-  int base = *n;
-  for (int w = 0; w < warp; ++w) base += wcnt[w];
-  if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = val;
+  const int old = *n;
+  const int before = warp_prefix(wcnt, warp, lane);
+  if (pred) q[old + before + __popc(m & ((1u << lane) - 1u))] = val;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int w = 0; w < kFWarps; ++w) t += wcnt[w];
-    *n += t;
+  if (threadIdx.x == kFB - 1) *n = old + before + __popc(m);  // last warp: its prefix + own count = total
+  __syncthreads();
+}
+
+// ordered block-wide append of up to U entries per thread (bit u of `bits` selects vals[u]); order = (thread, u)
+template <int U>
+__device__ __forceinline__ void q_push_multi(uint32_t* q, int* n, int* wcnt, unsigned bits, const uint32_t vals[U]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mine = __popc(bits);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += y;
   }
+  if (lane == 31) wcnt[warp] = incl;
+  __syncthreads();
+  const int old = *n;
+  const int before = warp_prefix(wcnt, warp, lane);
+  int off = old + before + incl - mine;
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (bits & (1u << u)) q[off++] = vals[u];
+  __syncthreads();
+  if (threadIdx.x == kFB - 1) *n = old + before + incl;
   __syncthreads();
 }
 
@@ -93,31 +148,103 @@ __device__ __forceinline__ Nuc<T> smem_nuc(const T* sC, const T* sQ, int i) {
 }
 
 template <class T>
-__device__ __forceinline__ T block_sum_to(T v, T* dst) {
+__device__ __forceinline__ void block_sum_to(T v, T* dst) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   if ((threadIdx.x & 31) == 0 && v != T(0)) atomicAdd(dst, v);
-  return v;
 }
 
-template <class T, bool WP>
-__global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a) {
+
+// cell-grid description shared by the CTA (written by thread 0)
+template <class T>
+struct CellGrid {
+  T origin[3], inv[3];  // cell = (x - origin) * inv
+  int n[3], ncell;
+};
+
+// members of one forward-half-shell row of cell `cid`: cells that are neighbours along x have consecutive ids, so
+// the row is one contiguous run of the cell-ordered list (two runs when a periodic x wraps).  row 0 = own cell
+// (partners after p only: the first own_len entries) + the +x cell; rows 1..4 = (dy,dz) in
+// {(+1,0), (-1,+1), (0,+1), (+1,+1)} with x offsets -1..+1.
+struct RowRun {
+  int s0, len0, s1, len1, own_len;
+};
+template <class T>
+__device__ __forceinline__ RowRun row_run(const CellGrid<T>* grid, const int* sCstart, bool periodic, int cid, int row) {
+  RowRun r{0, 0, 0, 0, 0};
+  const int n0 = grid->n[0], n1 = grid->n[1], n2 = grid->n[2];
+  const int ax = cid % n0, ay = (cid / n0) % n1, az = cid / (n0 * n1);
+  const int dy = (row == 0) ? 0 : (row == 1 ? 1 : row - 3), dz = (row >= 2) ? 1 : 0;
+  int by = ay + dy, bz = az + dz;
+  if (periodic) {
+    if ((n1 == 1 && dy) || (n2 == 1 && dz)) return r;
+    by = by < 0 ? by + n1 : (by >= n1 ? by - n1 : by);
+    bz = bz < 0 ? bz + n2 : (bz >= n2 ? bz - n2 : bz);
+  } else if (by < 0 || bz < 0 || by >= n1 || bz >= n2) {
+    return r;
+  }
+  const int rowbase = n0 * (by + n1 * bz);
+  int xlo = (row == 0) ? ax : ax - 1, xhi = ax + 1;  // inclusive cell range along x
+  if (periodic && n0 > 1) {
+    if (xlo < 0) {  // wraps on the low side: [n0-1] and [0 .. xhi]
+      r.s1 = sCstart[rowbase + n0 - 1];
+      r.len1 = sCstart[rowbase + n0] - r.s1;
+      xlo = 0;
+    } else if (xhi >= n0) {  // wraps on the high side: [xlo .. n0-1] and [0]
+      r.s1 = sCstart[rowbase];
+      r.len1 = sCstart[rowbase + 1] - r.s1;
+      xhi = n0 - 1;
+    }
+  } else {
+    xlo = xlo < 0 ? 0 : xlo;
+    xhi = xhi >= n0 ? n0 - 1 : xhi;
+    if (periodic) xlo = xhi = ax;  // a single cell spans a periodic x: only dx = 0
+  }
+  r.s0 = sCstart[rowbase + xlo];
+  r.len0 = sCstart[rowbase + xhi + 1] - r.s0;
+  if (row == 0) r.own_len = sCstart[rowbase + ax + 1] - r.s0;
+  return r;
+}
+
+#ifdef MB_FRAME_PROFILE
+#define MB_TICK(slot) { const long long _now = clock64(); prof_t[slot] += _now - prof_last; prof_n[slot] += 1; prof_last = _now; }
+#else
+#define MB_TICK(slot)
+#endif
+
+template <class T, bool WP, bool CACHE_BACK>
+__global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, const FrameSmem L) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const FrameSmem L = frame_smem_layout<T>(a.n, WP);
+  const bool cells = a.all_pairs_cutoff > T(0);
   T* sC = reinterpret_cast<T*>(smem + L.c);
   T* sQ = reinterpret_cast<T*>(smem + L.q);
+  T* sB = reinterpret_cast<T*>(smem + L.back);
   T* sP = reinterpret_cast<T*>(smem + L.p);
   T* sAcc = reinterpret_cast<T*>(smem + L.acc);
   T* sE = reinterpret_cast<T*>(smem + L.e);
   unsigned char* sF = smem + L.flags;  // bits 0-1 seq, bit 2 is_end
+  uint32_t* qNL = reinterpret_cast<uint32_t*>(smem + L.q_nl);
   uint32_t* qSR = reinterpret_cast<uint32_t*>(smem + L.q_sr);
   uint32_t* qBP = reinterpret_cast<uint32_t*>(smem + L.q_bp);
   uint32_t* qCX = reinterpret_cast<uint32_t*>(smem + L.q_cx);
   int* wcnt = reinterpret_cast<int*>(smem + L.wcnt);
-  int* ctr = reinterpret_cast<int*>(smem + L.ctr);  // [0] n_sr [1] n_bp [2] n_cx
+  int* ctr = reinterpret_cast<int*>(smem + L.ctr);  // [0] n_sr [1] n_bp [2] n_cx [3] n_nl [5] too many bonds [6] more tiles
+  // packed cell coordinates (10 bits per axis): needed only while the cell list is built, aliases queues SR/BP/CX
+  uint32_t* sCell = reinterpret_cast<uint32_t*>(smem + L.q_sr);
+  int* sRect = reinterpret_cast<int*>(smem + L.rect);  // exclusive prefix of the padded rectangle sizes
+  int* sCstart = reinterpret_cast<int*>(smem + L.cstart);
+  uint16_t* sCorder = reinterpret_cast<uint16_t*>(smem + L.corder);
+  uint16_t* sExcl = reinterpret_cast<uint16_t*>(smem + L.excl);
+  CellGrid<T>* grid = reinterpret_cast<CellGrid<T>*>(smem + L.grid);
+  int* sCursor = reinterpret_cast<int*>(smem + L.q_nl);  // per-cell fill cursors; aliases queue NL, used only during the cell build
 
+#ifdef MB_FRAME_PROFILE
+  long long prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_last = clock64();
+  int prof_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
   const int frame = blockIdx.x;
   const int n = a.n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long fbase = (long long)frame * n;
   for (int k = threadIdx.x; k < 3 * n; k += kFB) sC[k] = a.center[3 * fbase + k];
   for (int k = threadIdx.x; k < 4 * n; k += kFB) sQ[k] = a.quat[4 * fbase + k];
@@ -127,13 +254,22 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a) {
   }
   for (int k = threadIdx.x; k < n; k += kFB)
     sF[k] = (unsigned char)((a.seq[k] & 3) | ((a.is_end && a.is_end[k]) ? 4 : 0));
-  if (threadIdx.x < 4) ctr[threadIdx.x] = 0;
+  if (threadIdx.x < 8) ctr[threadIdx.x] = 0;
   __syncthreads();
 
   const ModelT<T>& M = a.M;
   const Geom<T>& g = M.geom[0];
   const mb_bank_forms F = M.forms[0];
   const unsigned mask = a.mask;
+  if (CACHE_BACK) {
+    for (int i = threadIdx.x; i < n; i += kFB) {
+      const Nuc<T> ni = smem_nuc(sC, sQ, i);
+      const V3<T> b = site(ni, g.back[0], g.back[1], g.back[2]);
+      sB[3 * i] = b.x;
+      sB[3 * i + 1] = b.y;
+      sB[3 * i + 2] = b.z;
+    }
+  }
   T cot[MB_N_TERMS];
 #pragma unroll
   for (int t = 0; t < MB_N_TERMS; ++t) cot[t] = a.cot ? a.cot[(long long)frame * MB_N_TERMS + t] : T(1);
@@ -162,6 +298,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a) {
     }
   }
 
+  MB_TICK(0)  // staging + bonded
   // ---------------------------------------------------------------- unbonded pairs
   RegAcc<T, MB_P_DEBYE_KAPPA, 5> dacc;
   RegAcc<T, MB_P_UEXC_EPS, 17> xacc;
@@ -196,19 +333,219 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a) {
     bp_hi = fmax(bp_hi, sP[MB_P_CROSS_RCHIGH]);
   }
 
-  // ---- one scheduler loop; every phase body appears exactly once so it is inlined and its accumulators stay
-  // in registers.  All conditions are CTA-uniform (queue counters live in shared memory, read after barriers).
-  if ((mask & MB_UNBONDED_TERMS) && a.pair_capacity > 0) {
-    const int32_t* pl = a.pairs + (long long)frame * a.pair_frame_stride;
-    long long count = a.pair_capacity;
-    if (a.pair_count) {
-      const long long c = a.pair_count[frame];
-      count = c < count ? c : count;
+  const bool have_unbonded = (mask & MB_UNBONDED_TERMS) && (cells || a.pair_capacity > 0);
+  const bool periodic = M.box[0] > T(0);
+  const T cut2 = a.all_pairs_cutoff * a.all_pairs_cutoff;
+
+  // ---------------------------------------------------------------- all-pairs mode: shared-memory cell list
+  if (have_unbonded && cells) {
+    // exclusion table from the bonded list (up to kExcl partners per nucleotide; more -> NaN energies)
+    for (int k = threadIdx.x; k < kExcl * n; k += kFB) sExcl[k] = 0xffff;
+    // bounding box (free space) -> grid
+    T lo[3] = {T(1e30), T(1e30), T(1e30)}, hi[3] = {T(-1e30), T(-1e30), T(-1e30)};
+    if (!periodic) {
+      for (int i = threadIdx.x; i < n; i += kFB)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const T x = sC[3 * i + d];
+          lo[d] = fmin(lo[d], x);
+          hi[d] = fmax(hi[d], x);
+        }
     }
-    long long base = 0;
+    T* red = sE;  // scratch: 6 x kFWarps reals fit in the 8 x kFWarps energy buffer
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      T l = lo[d], h = hi[d];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        l = fmin(l, __shfl_xor_sync(kFull, l, o));
+        h = fmax(h, __shfl_xor_sync(kFull, h, o));
+      }
+      if (lane == 0) {
+        red[(2 * d) * kFWarps + warp] = l;
+        red[(2 * d + 1) * kFWarps + warp] = h;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      T cs = a.all_pairs_cutoff * T(1.0001);
+      T ext[3];
+      for (int d = 0; d < 3; ++d) {
+        if (periodic) {
+          grid->origin[d] = T(0);
+          ext[d] = M.box[d];
+        } else {
+          T l = red[(2 * d) * kFWarps], h = red[(2 * d + 1) * kFWarps];
+          for (int w = 1; w < kFWarps; ++w) {
+            l = fmin(l, red[(2 * d) * kFWarps + w]);
+            h = fmax(h, red[(2 * d + 1) * kFWarps + w]);
+          }
+          grid->origin[d] = l;
+          ext[d] = h - l;
+        }
+      }
+      while (true) {
+        long long tot = 1;
+        for (int d = 0; d < 3; ++d) {
+          int nd = periodic ? int(ext[d] / cs) : int(ext[d] / cs) + 1;
+          if (nd < 1) nd = 1;
+          if (periodic && nd < 3) nd = 1;  // fewer than 3 cells along a periodic axis: one cell spanning it
+          grid->n[d] = nd;
+          tot *= nd;
+        }
+        if (tot <= kMaxCells) {
+          grid->ncell = int(tot);
+          break;
+        }
+        cs *= T(1.26);
+      }
+      for (int d = 0; d < 3; ++d) grid->inv[d] = periodic ? T(grid->n[d]) / ext[d] : T(1) / cs;
+    }
+    __syncthreads();
+    const int ncell = grid->ncell;
+    for (int k = threadIdx.x; k <= ncell; k += kFB) {
+      sCstart[k] = 0;
+      sCursor[k] = 0;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < a.n_bonded; k += kFB) {
+      const int p = a.bonded[2 * k], r = a.bonded[2 * k + 1];
+      for (int side = 0; side < 2; ++side) {
+        const int me = side ? r : p, other = side ? p : r;
+        bool placed = false;
+        for (int s = 0; s < kExcl && !placed; ++s) {
+          // 16-bit compare-and-swap through the containing 32-bit word
+          unsigned* word = reinterpret_cast<unsigned*>(sExcl) + ((me * kExcl + s) >> 1);
+          const int sh = ((me * kExcl + s) & 1) * 16;
+          unsigned old = *word;
+          while (((old >> sh) & 0xffffu) == 0xffffu) {
+            const unsigned want = (old & ~(0xffffu << sh)) | (unsigned(other) << sh);
+            const unsigned prev = atomicCAS(word, old, want);
+            if (prev == old) {
+              placed = true;
+              break;
+            }
+            old = prev;
+          }
+        }
+        if (!placed) ctr[5] = 1;  // more than kExcl bonded partners
+      }
+    }
+    for (int i = threadIdx.x; i < n; i += kFB) {
+      int cc[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        T x = sC[3 * i + d] - grid->origin[d];
+        if (periodic) {
+          x = fmod(x, M.box[d]);
+          if (x < T(0)) x += M.box[d];
+        }
+        int ci = int(x * grid->inv[d]);
+        ci = ci < 0 ? 0 : (ci >= grid->n[d] ? grid->n[d] - 1 : ci);
+        cc[d] = ci;
+      }
+      const int cid = cc[0] + grid->n[0] * (cc[1] + grid->n[1] * cc[2]);
+      sCell[i] = uint32_t(cc[0]) | (uint32_t(cc[1]) << 10) | (uint32_t(cc[2]) << 20);
+      atomicAdd(&sCstart[cid + 1], 1);
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the (<= kMaxCells) cell counts by one warp
+      int carry = 0;
+      for (int base = 0; base < ncell; base += 32) {
+        const int k = base + lane;
+        const int v = (k < ncell) ? sCstart[k + 1] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(kFull, x, o);
+          if (lane >= o) x += y;
+        }
+        if (k < ncell) sCstart[k + 1] = carry + x;
+        carry += __shfl_sync(kFull, x, 31);
+      }
+    }
+    __syncthreads();
+    // members of each cell in ascending nucleotide order (deterministic): warp 0 walks the nucleotides in chunks of
+    // 32; lanes that share a cell rank themselves with match_any, the lowest such lane bumps the cell's cursor
+    if (warp == 0) {
+      const int n0 = grid->n[0], n1 = grid->n[1];
+      for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < n;
+        int cid = -1 - lane;  // distinct dummy keys for idle lanes
+        if (valid) {
+          const uint32_t cc = sCell[i];
+          cid = int(cc & 1023) + n0 * (int((cc >> 10) & 1023) + n1 * int(cc >> 20));
+        }
+        const unsigned peers = __match_any_sync(kFull, cid);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int leader = __ffs(peers) - 1;
+        int slot = 0;
+        if (valid && lane == leader) {
+          slot = sCursor[cid];
+          sCursor[cid] = slot + __popc(peers);
+        }
+        slot = __shfl_sync(kFull, slot, leader);
+        if (valid) sCorder[sCstart[cid] + slot + rank] = (uint16_t)i;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // rectangles: (cell A, half-shell row) -> |A| x |row members| candidate pairs, padded to a multiple of kSlice so
+    // that one thread's kSlice consecutive candidates never straddle two rectangles
+    const int nrect = 5 * ncell;
+    for (int R = threadIdx.x; R < nrect; R += kFB) {
+      const int cid = R / 5, row = R - 5 * cid;
+      const int na = sCstart[cid + 1] - sCstart[cid];
+      int len = 0;
+      if (na > 0) {
+        RowRun rr = row_run(grid, sCstart, periodic, cid, row);
+        len = rr.len0 + rr.len1;
+      }
+      sRect[R + 1] = ((na * len + kSlice - 1) / kSlice) * kSlice;
+    }
+    if (threadIdx.x == 0) sRect[0] = 0;
+    __syncthreads();
+    if (warp == 0) {
+      int carry = 0;
+      for (int base = 0; base < nrect; base += 32) {
+        const int k = base + lane;
+        int x = (k < nrect) ? sRect[k + 1] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(kFull, x, o);
+          if (lane >= o) x += y;
+        }
+        if (k < nrect) sRect[k + 1] = carry + x;
+        carry += __shfl_sync(kFull, x, 31);
+      }
+    }
+    __syncthreads();
+  }
+
+  MB_TICK(1)  // cell list build
+  // ---------------------------------------------------------------- scheduler loop
+  // Every phase body appears exactly once so it is inlined and its accumulators stay in registers.  All conditions
+  // are CTA-uniform (queue counters live in shared memory, read after barriers).
+  if (have_unbonded) {
+    const int32_t* pl = cells ? nullptr : a.pairs + (long long)frame * a.pair_frame_stride;
+    long long count = 0;
+    if (!cells) {
+      count = a.pair_capacity;
+      if (a.pair_count) {
+        const long long c = a.pair_count[frame];
+        count = c < count ? c : count;
+      }
+    }
+    long long base = 0;  // list mode: next list entry
+    // all-pairs mode producer state: position in the flattened list of (cell, half-shell row) candidate rectangles;
+    // a step examines kFB * kSlice candidates, so at most that many pairs enter queue NL per step
+    int cand_base = 0;
+    const int nrect = cells ? 5 * grid->ncell : 0;
+    const int ncand = cells ? sRect[nrect] : 0;
     bool flush = false;
     while (true) {
-      const int n_sr = ctr[0], n_bp = ctr[1], n_cx = ctr[2];
+      const int n_sr = ctr[0], n_bp = ctr[1], n_cx = ctr[2], n_nl = ctr[3];
       __syncthreads();  // everyone has read the counters before anyone updates them
       if (n_bp >= kFB || (flush && n_bp > 0)) {
         // ---------------- phase 3a: hydrogen bonding + cross stacking on the BP queue
@@ -241,6 +578,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a) {
         }
         if (threadIdx.x == 0) ctr[1] = n_bp - cnt;
         __syncthreads();
+        MB_TICK(5)
         continue;
       }
       if (n_cx >= kFB || (flush && n_cx > 0)) {
@@ -262,6 +600,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a) {
           e[MB_TERM_COAX] += coax_term<T, false, false>(sP, 0, F.coax_form, in, ds, rs, db, ni.a1, nj.a1, ni.a3, nj.a3, cot[MB_TERM_COAX], CG, nacc);
         if (threadIdx.x == 0) ctr[2] = n_cx - cnt;
         __syncthreads();
+        MB_TICK(6)
         continue;
       }
       if (n_sr >= kFB || (flush && n_sr > 0)) {
@@ -303,15 +642,59 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a) {
         if (threadIdx.x == 0) ctr[0] = n_sr - cnt;
         q_push(qBP, &ctr[1], wcnt, to_bp, pk);
         q_push(qCX, &ctr[2], wcnt, to_cx, pk);
+        MB_TICK(4)
+        continue;
+      }
+      if (n_nl >= kU1 * kFB || (flush && n_nl > 0)) {
+        // ---------------- phase 1: Debye-Hueckel on up to kU1 found pairs per thread (independent chains: the CTA
+        // has only 16 warps, so latency is hidden inside the thread), short-range filter into queue SR
+        const int cnt = n_nl >= kU1 * kFB ? kU1 * kFB : n_nl;
+        const int first = n_nl - cnt;
+        unsigned sr_bits = 0;
+        uint32_t pks[kU1];
+#pragma unroll
+        for (int u = 0; u < kU1; ++u) {
+          const int t = threadIdx.x + u * kFB;
+          const bool valid = t < cnt;
+          const uint32_t pk = valid ? qNL[first + t] : 0u;
+          pks[u] = pk;
+          const int i = pk & 0xffff, j = pk >> 16;
+          const V3<T> ci = v3<T>(sC[3 * i], sC[3 * i + 1], sC[3 * i + 2]), cj = v3<T>(sC[3 * j], sC[3 * j + 1], sC[3 * j + 2]);
+          const V3<T> dc = disp(cj, ci, M.box);
+          const T d2 = dot(dc, dc);
+          if (want_debye) {
+            V3<T> db;
+            if (CACHE_BACK) {
+              db = disp(v3<T>(sB[3 * j], sB[3 * j + 1], sB[3 * j + 2]), v3<T>(sB[3 * i], sB[3 * i + 1], sB[3 * i + 2]), M.box);
+            } else {
+              const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
+              db = disp(site(nj, g.back[0], g.back[1], g.back[2]), site(ni, g.back[0], g.back[1], g.back[2]), M.box);
+            }
+            T m = T(1);
+            if (M.half_charged_ends) m = ((sF[i] & 4) ? T(0.5) : T(1)) * ((sF[j] & 4) ? T(0.5) : T(1));
+            V3<T> gd;
+            if (WP)
+              e[MB_TERM_DEBYE] += debye_term<T, false, true>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, dacc);
+            else
+              e[MB_TERM_DEBYE] += debye_term<T, false, false>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, nacc);
+          }
+          if (valid && d2 < sr_cut2) sr_bits |= 1u << u;
+        }
+        if (threadIdx.x == 0) ctr[3] = first;
+        if (want_sr)
+          q_push_multi<kU1>(qSR, &ctr[0], wcnt, sr_bits, pks);
+        else
+          __syncthreads();
+        MB_TICK(3)
         continue;
       }
       if (flush) break;
-      if (base >= count) {
-        flush = true;
-        continue;
-      }
-      // ---------------- phase 1: one tile of the frame's pair list: Debye-Hueckel, short-range filter
-      {
+      // ---------------- producer
+      if (!cells) {
+        if (base >= count) {
+          flush = true;
+          continue;
+        }
         const long long k = base + threadIdx.x;
         base += kFB;
         int i = 0, j = 0;
@@ -320,27 +703,84 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a) {
           i = pl[k];
           j = pl[a.pair_capacity + k];
           valid = (i >= 0 && j >= 0 && i < n && j < n);
-          if (!valid) i = j = 0;
         }
-        const V3<T> ci = v3<T>(sC[3 * i], sC[3 * i + 1], sC[3 * i + 2]), cj = v3<T>(sC[3 * j], sC[3 * j + 1], sC[3 * j + 2]);
-        const V3<T> dc = disp(cj, ci, M.box);
-        const T d2 = dot(dc, dc);
-        if (want_debye) {
-          const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
-          const V3<T> db = disp(site(nj, g.back[0], g.back[1], g.back[2]), site(ni, g.back[0], g.back[1], g.back[2]), M.box);
-          T m = T(1);
-          if (M.half_charged_ends) m = ((sF[i] & 4) ? T(0.5) : T(1)) * ((sF[j] & 4) ? T(0.5) : T(1));
-          V3<T> gd;
-          if (WP)
-            e[MB_TERM_DEBYE] += debye_term<T, false, true>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, dacc);
-          else
-            e[MB_TERM_DEBYE] += debye_term<T, false, false>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, nacc);
+        q_push(qNL, &ctr[3], wcnt, valid, uint32_t(i) | (uint32_t(j) << 16));
+      } else {
+        if (cand_base >= ncand) {
+          flush = true;
+          continue;
         }
-        if (want_sr) q_push(qSR, &ctr[0], wcnt, valid && d2 < sr_cut2, uint32_t(i) | (uint32_t(j) << 16));
+        // each thread takes kSlice consecutive candidates of the flattened rectangle list (one rectangle, by padding)
+        const int c0 = cand_base + threadIdx.x * kSlice;
+        cand_base += kFB * kSlice;
+        unsigned accept = 0;  // bit u: candidate c0 + u is a pair inside the cutoff
+        uint32_t found[kSlice];
+#pragma unroll
+        for (int u = 0; u < kSlice; ++u) found[u] = 0u;
+        if (c0 < ncand) {
+          int lo = 0, hi = nrect;  // largest R with sRect[R] <= c0
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (sRect[mid] <= c0) lo = mid; else hi = mid;
+          }
+          const int R = lo, cid = R / 5, row = R - 5 * cid;
+          const int a0 = sCstart[cid], na = sCstart[cid + 1] - a0;
+          const RowRun rr = row_run(grid, sCstart, periodic, cid, row);
+          const int len = rr.len0 + rr.len1;
+          const int l0 = c0 - sRect[R];
+          int ia = l0 / len, k = l0 - ia * len;  // len > 0: an empty rectangle has size 0 and is never found
+          // the producer is shared-memory-bandwidth bound (random 8-byte reads): keep p's centre and bonded partners in
+          // registers while ia stays the same, and read a candidate's y,z only if its x already passes
+          int cur = -1, pp = 0, e0 = 0, e1 = 0;
+          T px = 0, py = 0, pz = 0;
+#pragma unroll
+          for (int u = 0; u < kSlice; ++u) {
+            if (ia < na) {
+              if (ia != cur) {
+                cur = ia;
+                pp = sCorder[a0 + ia];
+                px = sC[3 * pp];
+                py = sC[3 * pp + 1];
+                pz = sC[3 * pp + 2];
+                const unsigned ex = *reinterpret_cast<const unsigned*>(sExcl + pp * kExcl);  // both partners in one word
+                e0 = int(ex & 0xffffu);
+                e1 = int(ex >> 16);
+              }
+              const int r = sCorder[k < rr.len0 ? rr.s0 + k : rr.s1 + (k - rr.len0)];
+              if (!(k < rr.own_len && r <= pp) && r != e0 && r != e1) {
+                T dx = sC[3 * r] - px;
+                if (periodic) dx = wrap1(dx, M.box[0]);
+                if (dx * dx < cut2) {
+                  T dy = sC[3 * r + 1] - py, dz = sC[3 * r + 2] - pz;
+                  if (periodic) {
+                    dy = wrap1(dy, M.box[1]);
+                    dz = wrap1(dz, M.box[2]);
+                  }
+                  if (dx * dx + dy * dy + dz * dz < cut2) {
+                    accept |= 1u << u;
+                    found[u] = pp < r ? (uint32_t(pp) | (uint32_t(r) << 16)) : (uint32_t(r) | (uint32_t(pp) << 16));
+                  }
+                }
+              }
+            }
+            if (++k == len) {
+              k = 0;
+              ++ia;
+            }
+          }
+        }
+        q_push_multi<kSlice>(qNL, &ctr[3], wcnt, accept, found);
       }
+      MB_TICK(2)
     }
   }
 
+#ifdef MB_FRAME_PROFILE
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("frame-kernel cycles: stage+bonded %lld | cells %lld | producer %lld (%d steps) | phase1 %lld (%d) | phase2 %lld (%d) | "
+           "hb+cross %lld (%d) | coax %lld (%d)\n", prof_t[0], prof_t[1], prof_t[2], prof_n[2], prof_t[3], prof_n[3], prof_t[4],
+           prof_n[4], prof_t[5], prof_n[5], prof_t[6], prof_n[6]);
+#endif
   // ---------------------------------------------------------------- flush
   if (WP) {
 #pragma unroll
@@ -348,7 +788,6 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a) {
 #pragma unroll
     for (int k = 0; k < 17; ++k) block_sum_to(xacc.r[k], &sAcc[MB_P_UEXC_EPS + k]);
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int t = 0; t < MB_N_TERMS; ++t) {
     T v = e[t];
@@ -357,9 +796,11 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a) {
     if (lane == 0) sE[warp * MB_N_TERMS + t] = v;
   }
   __syncthreads();
+  const bool poisoned = cells && ctr[5] != 0;
   if (threadIdx.x < MB_N_TERMS && a.terms) {
     T v = 0;
     for (int w = 0; w < kFWarps; ++w) v += sE[w * MB_N_TERMS + threadIdx.x];
+    if (poisoned) v = T(NAN);
     if (v != T(0)) atomicAdd(&a.terms[(long long)frame * MB_N_TERMS + threadIdx.x], v);
   }
   if (WP) {
@@ -372,23 +813,43 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a) {
 }
 
 template <class T>
+static bool pick_layout(const EnergyDev<T>& a, bool wp, bool* cache_back, FrameSmem* L) {
+  const bool cells = a.all_pairs_cutoff > T(0);
+  if ((long long)a.n * 11 * (long long)sizeof(T) > 227 * 1024) return false;
+  if (cells && (size_t)a.n * 4 > sizeof(uint32_t) * (kSrCap + 2 * kQCap)) return false;  // sCell aliases the SR/BP/CX queues
+  for (int cb = 1; cb >= 0; --cb) {
+    *L = frame_smem_layout<T>(a.n, wp, cb != 0, cells);
+    if (L->total <= 227u * 1024u) {
+      *cache_back = cb != 0;
+      return true;
+    }
+  }
+  return false;
+}
+
+template <class T>
 bool frame_kernel_eligible(const EnergyDev<T>& a) {
   if (a.M.n_banks != 1 || a.n > 65535) return false;
-  return frame_smem_layout<T>(a.n, true).total <= 227 * 1024;
+  bool cb;
+  FrameSmem L;
+  return pick_layout(a, true, &cb, &L);
+}
+
+template <class T, bool WP, bool CB>
+static int launch_one(cudaStream_t s, const EnergyDev<T>& a, const FrameSmem& L) {
+  MB_CUDA_CHECK(cudaFuncSetAttribute(k_frame_energy<T, WP, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  k_frame_energy<T, WP, CB><<<a.n_frames, kFB, L.total, s>>>(a, L);
+  MB_CUDA_CHECK(cudaGetLastError());
+  return MB_OK;
 }
 
 template <class T>
 int launch_frame_kernel(cudaStream_t s, const EnergyDev<T>& a, bool wp) {
-  const size_t smem = frame_smem_layout<T>(a.n, wp).total;
-  if (wp) {
-    MB_CUDA_CHECK(cudaFuncSetAttribute(k_frame_energy<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_frame_energy<T, true><<<a.n_frames, kFB, smem, s>>>(a);
-  } else {
-    MB_CUDA_CHECK(cudaFuncSetAttribute(k_frame_energy<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_frame_energy<T, false><<<a.n_frames, kFB, smem, s>>>(a);
-  }
-  MB_CUDA_CHECK(cudaGetLastError());
-  return MB_OK;
+  bool cb;
+  FrameSmem L;
+  MB_REQUIRE(pick_layout(a, wp, &cb, &L), MB_ECAPACITY, "frame kernel: frame does not fit in shared memory");
+  if (wp) return cb ? launch_one<T, true, true>(s, a, L) : launch_one<T, true, false>(s, a, L);
+  return cb ? launch_one<T, false, true>(s, a, L) : launch_one<T, false, false>(s, a, L);
 }
 
 template bool frame_kernel_eligible<float>(const EnergyDev<float>&);

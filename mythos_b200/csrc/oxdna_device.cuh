@@ -168,6 +168,8 @@ MB_HD T wrap1(T d, T L) {
 }
 template <class T>
 MB_HD V3<T> disp(const V3<T>& a, const V3<T>& b, const T box[3]) {
+  // the box is either all zero (free space) or all positive (ABI contract): one test for the common free case
+  if (!(box[0] > T(0))) return v3<T>(a.x - b.x, a.y - b.y, a.z - b.z);
   return v3<T>(wrap1(a.x - b.x, box[0]), wrap1(a.y - b.y, box[1]), wrap1(a.z - b.z, box[2]));
 }
 

@@ -67,6 +67,7 @@ def _launch(
     per_frame_param_grad: bool = False,
     pair_count: torch.Tensor | None = None,
     flags: int = 0,
+    all_pairs_cutoff: float = 0.0,
 ):
     _lib.require_cuda(center, "center")
     F, N = center.shape[0], center.shape[1]
@@ -114,6 +115,7 @@ def _launch(
     a.term_mask = term_mask
     a.flags = flags
     a.pair_count = _lib.ptr(pair_count) if cap else None
+    a.all_pairs_cutoff = float(all_pairs_cutoff)
     a.terms = _lib.ptr(terms)
     a.d_center = _lib.ptr(d_center)
     a.d_quat = _lib.ptr(d_quat)
@@ -154,6 +156,7 @@ class CellListPairs:
     capacity: int = 0  # 0 = size from the first frame
     workspace: torch.Tensor | None = None
     max_count: int = 0
+    use_lists: bool = False  # True once the frame-resident all-pairs mode was found not to apply
     _pending: list = dc.field(default_factory=list)
 
     def chunk(self, sl: slice, center: torch.Tensor):
@@ -196,6 +199,19 @@ def _chunks(n_frames: int, source) -> list[slice]:
 
 def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, want_pos, want_par, per_frame_par, flags=0):
     """Chunked launch over frames; concatenates / sums the per-chunk outputs."""
+    if isinstance(source, CellListPairs) and not want_pos and model.n_banks == 1 and not source.use_lists and not (flags & _lib.FLAG_GENERIC_KERNEL):
+        # all-pairs mode inside the frame-resident kernel: the CTA finds its own pairs, no list in HBM
+        try:
+            outs = [
+                _launch(model, topo, center[sl], quat[sl], params, None, 0, term_mask, None if cot is None else cot[sl],
+                        want_terms, False, want_par, per_frame_par, None, flags, source.r_cutoff)
+                for sl in _chunks(center.shape[0], None)
+            ]
+            return _merge(outs, want_terms, False, want_par, per_frame_par)
+        except _lib.MythosB200Error as err:
+            if getattr(err, "status", None) != 3:  # MB_ECAPACITY: frame too large for shared memory -> device lists
+                raise
+            source.use_lists = True
     while True:
         outs = []
         for sl in _chunks(center.shape[0], source):
@@ -206,6 +222,10 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
             )
         if not isinstance(source, CellListPairs) or source.verify():
             break
+    return _merge(outs, want_terms, want_pos, want_par, per_frame_par)
+
+
+def _merge(outs, want_terms, want_pos, want_par, per_frame_par):
     if len(outs) == 1:
         return outs[0]
     terms = torch.cat([o[0] for o in outs]) if want_terms else None

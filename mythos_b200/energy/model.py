@@ -153,7 +153,11 @@ class Plan:
 
         if isinstance(ub, AllPairs):
             box = tuple(self.model.box)
-            return functional.CellListPairs(bonded=topo.bonded, box=box, r_cutoff=interaction_range(self))
+            src = functional.CellListPairs(bonded=topo.bonded, box=box, r_cutoff=interaction_range(self))
+            # the in-kernel cell list keeps 2 bonded partners per nucleotide (like the reference's (N,2) mask)
+            if topo.bonded.numel() and int(torch.bincount(topo.bonded.reshape(-1).long()).max()) > 2:
+                src.use_lists = True
+            return src
         return functional.StaticPairs(device_pairs(ub, device))
 
     def evaluate(self, center: torch.Tensor, quat: torch.Tensor) -> torch.Tensor:
