@@ -421,6 +421,9 @@ typedef struct mb_langevin_args {
   void* traj_center;      /* optional out (traj_rows,N,3): positions after this call's drift at row *step_ptr      */
   void* traj_quat;        /* optional out (traj_rows,N,4)                                                          */
   int64_t traj_rows;
+  int32_t zero_forces;    /* after the kick, zero d_center / d_quat (they are then written, not only read): the next
+                           * mythos_b200_energy_* call can run with MB_FLAG_ACCUMULATE and no memset nodes           */
+  int32_t _pad2;
 } mb_langevin_args;
 int mythos_b200_langevin_f64(void* cuda_stream, const mb_langevin_args* a);
 int mythos_b200_langevin_f32(void* cuda_stream, const mb_langevin_args* a);

@@ -142,6 +142,8 @@ class LangevinArgs(C.Structure):
         ("traj_center", C.c_void_p),
         ("traj_quat", C.c_void_p),
         ("traj_rows", C.c_int64),
+        ("zero_forces", C.c_int32),
+        ("_pad2", C.c_int32),
     ]
 
 

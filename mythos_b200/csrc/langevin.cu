@@ -69,9 +69,10 @@ struct LangevinDev {
   T* quat;
   T* p_center;
   T* p_quat;
-  const T* d_center;
-  const T* d_quat;
+  T* d_center;
+  T* d_quat;
   const T* noise;
+  int zero_forces;
   T dt, kT, gamma_c, gamma_q, mass, inertia[3], box[3];
   uint64_t seed, step;
   const unsigned long long* step_ptr;  // device-side step counter (CUDA-graph replays), overrides `step`
@@ -132,6 +133,10 @@ __global__ void k_langevin(LangevinDev<T> a) {
   const T kick = (a.phase == 2) ? a.dt : h;
   for (int d = 0; d < 3; ++d) pc[d] -= kick * a.d_center[3 * i + d];
   for (int d = 0; d < 4; ++d) pq[d] -= kick * a.d_quat[4 * i + d];
+  if (a.zero_forces) {  // hand the gradient buffers back zeroed: the next force evaluation accumulates into them
+    for (int d = 0; d < 3; ++d) a.d_center[3 * i + d] = T(0);
+    for (int d = 0; d < 4; ++d) a.d_quat[4 * i + d] = T(0);
+  }
   if (a.phase != 1) {
     for (int half = 0; half < 2; ++half) {
       // A(dt/2)
@@ -200,8 +205,9 @@ static int langevin_impl(cudaStream_t s, const mb_langevin_args* x) {
   a.quat = static_cast<T*>(x->quat);
   a.p_center = static_cast<T*>(x->p_center);
   a.p_quat = static_cast<T*>(x->p_quat);
-  a.d_center = static_cast<const T*>(x->d_center);
-  a.d_quat = static_cast<const T*>(x->d_quat);
+  a.d_center = static_cast<T*>(const_cast<void*>(x->d_center));
+  a.d_quat = static_cast<T*>(const_cast<void*>(x->d_quat));
+  a.zero_forces = x->zero_forces;
   a.noise = static_cast<const T*>(x->noise);
   a.dt = T(x->dt);
   a.kT = T(x->kT);

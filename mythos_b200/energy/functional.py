@@ -68,6 +68,7 @@ def _launch(
     pair_count: torch.Tensor | None = None,
     flags: int = 0,
     all_pairs_cutoff: float = 0.0,
+    out: tuple | None = None,
 ):
     _lib.require_cuda(center, "center")
     F, N = center.shape[0], center.shape[1]
@@ -82,8 +83,11 @@ def _launch(
     if params.numel() != np_:
         raise _lib.MythosB200Error(f"params has {params.numel()} entries, expected {np_}")
     terms = torch.empty((F, _lib.N_TERMS), dtype=dtype, device=dev) if want_terms else None
-    d_center = torch.empty_like(center) if want_pos_grad else None
-    d_quat = torch.empty_like(quat) if want_pos_grad else None
+    if out is not None:  # caller-owned gradient buffers (MD loop): (d_center, d_quat), accumulated into
+        d_center, d_quat = out
+    else:
+        d_center = torch.empty_like(center) if want_pos_grad else None
+        d_quat = torch.empty_like(quat) if want_pos_grad else None
     d_params = None
     stride = 0
     if want_param_grad:

@@ -78,6 +78,15 @@ class _Forces:
             want_pos_grad=True)
         return terms[0], dcen[0], dq[0]
 
+    def accumulate_into(self, center: torch.Tensor, quat: torch.Tensor, d_center: torch.Tensor, d_quat: torch.Tensor) -> None:
+        """Forces only, ADDED into caller-owned (already zeroed) buffers: two pair-kernel launches, no memsets, no energies."""
+        if not isinstance(self.source, functional.StaticPairs):
+            raise _lib.MythosB200Error("accumulate_into needs an explicit pair list")
+        pairs, stride, _ = self.source.chunk(slice(0, 1), center)
+        functional._launch(self.plan.model, self.topo, center.unsqueeze(0), quat.unsqueeze(0), self.params, pairs, stride,
+                           self.plan.term_mask, self.cot, False, True, False, False, None, _lib.FLAG_ACCUMULATE, 0.0,
+                           (d_center.unsqueeze(0), d_quat.unsqueeze(0)))
+
 
 def nvt_langevin(energy_fn, shift_fn, dt: float, kT: float, gamma: RigidBody | Any = 0.1, seed: int = 0):
     """Fused rigid-body BAOAB Langevin integrator with the ``simulator_init`` calling convention."""
@@ -95,7 +104,7 @@ def nvt_langevin(energy_fn, shift_fn, dt: float, kT: float, gamma: RigidBody | A
             cache["f"] = _Forces(energy_fn, R.center.shape[0], R.center.device, R.center.dtype, unbonded_neighbors)
         return cache["f"]
 
-    def launch(state: NVTLangevinState, phase: int, noise=None, traj=None, advance=False):
+    def launch(state: NVTLangevinState, phase: int, noise=None, traj=None, advance=False, zero_forces=False):
         c, q = state.position.center, state.position.orientation.vec
         a = _lib.LangevinArgs()
         a.n = c.shape[0]
@@ -112,6 +121,7 @@ def nvt_langevin(energy_fn, shift_fn, dt: float, kT: float, gamma: RigidBody | A
         a.noise = _lib.ptr(noise)
         a.phase = phase
         a.advance_step = 1 if advance else 0
+        a.zero_forces = 1 if zero_forces else 0
         a.step_ptr = state.step.data_ptr()
         if traj is not None:
             a.traj_center, a.traj_quat, a.traj_rows = traj[0].data_ptr(), traj[1].data_ptr(), traj[0].shape[0]
@@ -246,11 +256,11 @@ class MDSimulator:
         c, q = state.position.center, state.position.orientation.vec
 
         def one_step():
-            step_fn.launch(state, 2 if one_step.started else 0, traj=traj, advance=True)
+            # 4 launches per step: B-A-O-A (zeroes the gradient buffers after the kick), counter++, bonded pairs, unbonded
+            # pairs (both accumulate (dE/dcenter, dE/dquat) straight into the state's buffers)
+            step_fn.launch(state, 2 if one_step.started else 0, traj=traj, advance=True, zero_forces=True)
             one_step.started = True
-            _, dcen, dq = f(c, q)
-            state.force.center.copy_(dcen)
-            state.force.orientation.vec.copy_(dq)
+            f.accumulate_into(c, q, state.force.center, state.force.orientation.vec)
 
         one_step.started = False
         stream = torch.cuda.Stream(device=c.device)
