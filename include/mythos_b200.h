@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MB_ABI_VERSION 1
+#define MB_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------------------- */
 enum mb_status {
@@ -369,10 +369,15 @@ typedef struct mb_energy_args {
                               * shared-memory cell list inside the kernel.  The caller passes the interaction range of its
                               * parameters (all terms have compact support).  MB_ECAPACITY if the frame-resident kernel
                               * does not apply (3 banks, position gradients requested, frame too large for shared memory) */
+  void* workspace;           /* optional scratch of mythos_b200_energy_workspace_bytes(): lets explicit pair lists run through
+                              * the phase-queued list kernels (per-nucleotide records, backbone-site gradient buffer, short-range list);
+                              * NULL or too small = the one-thread-per-pair kernels                                        */
+  size_t workspace_bytes;
 } mb_energy_args;
 #define MB_FLAG_ACCUMULATE 0x1u /* add into the outputs instead of zeroing them first */
 #define MB_FLAG_GENERIC_KERNEL 0x2u /* force the one-thread-per-pair kernels even where the frame-resident kernel applies */
 
+size_t mythos_b200_energy_workspace_bytes(int32_t n, int32_t n_frames, int64_t pair_capacity, int32_t real_bytes /* 4 or 8 */);
 int mythos_b200_energy_f64(void* cuda_stream, const mb_energy_args* a);
 int mythos_b200_energy_f32(void* cuda_stream, const mb_energy_args* a);
 

@@ -95,6 +95,8 @@ class EnergyArgs(C.Structure):
         ("d_params_frame_stride", C.c_int64),
         ("pair_count", C.c_void_p),
         ("all_pairs_cutoff", C.c_double),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -161,6 +163,7 @@ class WeightsArgs(C.Structure):
 _SIGNATURES = {
     "mythos_b200_energy_f64": (C.c_int, [C.c_void_p, C.POINTER(EnergyArgs)]),
     "mythos_b200_energy_f32": (C.c_int, [C.c_void_p, C.POINTER(EnergyArgs)]),
+    "mythos_b200_energy_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
     "mythos_b200_nl_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "mythos_b200_nl_build_f64": (C.c_int, [C.c_void_p, C.POINTER(NlArgs)]),
     "mythos_b200_nl_build_f32": (C.c_int, [C.c_void_p, C.POINTER(NlArgs)]),

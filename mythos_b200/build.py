@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libmythos_b200.so"
-SOURCES = ["abi_common.cu", "energy_kernels.cu", "frame_kernels.cu", "neighbors.cu", "langevin.cu", "difftre.cu", "peaks.cu"]
+SOURCES = ["abi_common.cu", "energy_kernels.cu", "frame_kernels.cu", "list_kernels.cu", "neighbors.cu", "langevin.cu", "difftre.cu", "peaks.cu"]
 NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",
@@ -42,11 +42,14 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: Path | None = None, defines: tuple[str, ...] = ()) -> Path:
+    """Build the library.  ``out`` / ``defines`` build a kernel-variant copy (experiments: load it through the
+    MYTHOS_B200_LIB environment variable); the default build is the product."""
+    lib = Path(out) if out else LIB
+    if out is None and not force and not needs_build():
         return LIB
     objs = []
-    obj_dir = PKG / "csrc" / "_obj"
+    obj_dir = PKG / "csrc" / ("_obj" if out is None else "_obj_" + lib.stem)
     obj_dir.mkdir(exist_ok=True)
     procs = []
     for src in SOURCES:
@@ -54,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if not path.exists():
             continue
         obj = obj_dir / (path.stem + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(path), "-o", str(obj)]
+        cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", str(path), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -65,11 +68,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             print(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [_nvcc(), "-shared", "-o", str(LIB), *objs, "-lcudart"]
+    cmd = [_nvcc(), "-shared", "-o", str(lib), *objs, "-lcudart"]
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(LIB)
+    _out = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")), None)
+    _defs = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=_out, defines=_defs))

@@ -13,35 +13,6 @@ namespace mb {
 
 constexpr int kBlock = 128;
 
-template <class T>
-__device__ __forceinline__ Nuc<T> load_nuc(const T* __restrict__ center, const T* __restrict__ quat, long long idx,
-                                           T q[4]) {
-  Nuc<T> n;
-  n.c = v3<T>(center[3 * idx], center[3 * idx + 1], center[3 * idx + 2]);
-  q[0] = quat[4 * idx];
-  q[1] = quat[4 * idx + 1];
-  q[2] = quat[4 * idx + 2];
-  q[3] = quat[4 * idx + 3];
-  axes_from_quat(q[0], q[1], q[2], q[3], n.a1, n.a2, n.a3);
-  return n;
-}
-
-template <class T>
-__device__ __forceinline__ void scatter_nuc_grad(const EnergyDev<T>& a, long long idx, const NucGrad<T>& g,
-                                                 const T q[4]) {
-  if (a.d_center) {
-    atomicAdd(&a.d_center[3 * idx], g.c.x);
-    atomicAdd(&a.d_center[3 * idx + 1], g.c.y);
-    atomicAdd(&a.d_center[3 * idx + 2], g.c.z);
-  }
-  if (a.d_quat) {
-    T dq[4];
-    quat_grad(g, q[0], q[1], q[2], q[3], dq);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) atomicAdd(&a.d_quat[4 * idx + c], dq[c]);
-  }
-}
-
 // block-reduce the 8 per-term energies and add them to terms[frame]
 template <class T>
 __device__ __forceinline__ void reduce_terms(T e[MB_N_TERMS], T* sE, T* out) {
@@ -135,7 +106,7 @@ __global__ void __launch_bounds__(kBlock) k_pairs(const EnergyDev<T> a) {
 }
 
 template <class T, bool WF, bool WP>
-static int launch_pairs(cudaStream_t s, const EnergyDev<T>& a) {
+static int launch_pairs(cudaStream_t s, const EnergyDev<T>& a, void* list_ws) {
   const size_t smem = sizeof(T) * (size_t)(a.M.n_banks * MB_P_COUNT * (WP ? 2 : 1) + (kBlock / 32) * MB_N_TERMS);
   if ((a.mask & MB_BONDED_TERMS) && a.n_bonded > 0) {
     dim3 grid(ceil_div(a.n_bonded, kBlock), a.n_frames);
@@ -143,6 +114,7 @@ static int launch_pairs(cudaStream_t s, const EnergyDev<T>& a) {
     MB_CUDA_CHECK(cudaGetLastError());
   }
   if ((a.mask & MB_UNBONDED_TERMS) && a.pair_capacity > 0) {
+    if (list_ws) return launch_list_kernel<T>(s, a, list_ws, WF, WP);  // phase-queued (list_kernels.cu)
     dim3 grid(ceil_div(a.pair_capacity, kBlock), a.n_frames);
     k_pairs<T, WF, WP, false><<<grid, kBlock, smem, s>>>(a);
     MB_CUDA_CHECK(cudaGetLastError());
@@ -197,6 +169,11 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
   a.d_quat = static_cast<T*>(x->d_quat);
   a.d_params = static_cast<T*>(x->d_params);
   a.d_params_frame_stride = x->d_params_frame_stride;
+  a.rec = nullptr;
+  a.gback = nullptr;
+  a.sr_list = nullptr;
+  a.sr_count = nullptr;
+  a.sr_capacity = 0;
 
   const size_t np = (size_t)m.n_banks * MB_P_COUNT;
   if (!(x->flags & MB_FLAG_ACCUMULATE)) {
@@ -216,14 +193,24 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
   MB_REQUIRE(!(x->all_pairs_cutoff > 0), MB_ECAPACITY,
              "energy: all_pairs_cutoff needs the frame-resident kernel (single bank, no position gradients, frame fits in "
              "shared memory); build a neighbour list with mythos_b200_nl_build_* instead");
-  if (wf && wp) return launch_pairs<T, true, true>(s, a);
-  if (wf) return launch_pairs<T, true, false>(s, a);
-  if (wp) return launch_pairs<T, false, true>(s, a);
-  return launch_pairs<T, false, false>(s, a);
+  // phase-queued list kernel when the caller lends the workspace it needs; otherwise one thread per pair
+  void* lk = nullptr;
+  if (!(x->flags & MB_FLAG_GENERIC_KERNEL) && x->workspace &&
+      x->workspace_bytes >= list_workspace_bytes<T>(x->n, x->n_frames, x->pair_capacity))
+    lk = x->workspace;
+  if (wf && wp) return launch_pairs<T, true, true>(s, a, lk);
+  if (wf) return launch_pairs<T, true, false>(s, a, lk);
+  if (wp) return launch_pairs<T, false, true>(s, a, lk);
+  return launch_pairs<T, false, false>(s, a, lk);
 }
 
 }  // namespace mb
 
+extern "C" size_t mythos_b200_energy_workspace_bytes(int32_t n, int32_t n_frames, int64_t pair_capacity, int32_t real_bytes) {
+  if (n <= 0 || n_frames <= 0 || pair_capacity <= 0) return 0;
+  return real_bytes == 4 ? mb::list_workspace_bytes<float>(n, n_frames, pair_capacity)
+                         : mb::list_workspace_bytes<double>(n, n_frames, pair_capacity);
+}
 extern "C" int mythos_b200_energy_f64(void* stream, const mb_energy_args* a) {
   return mb::energy_impl<double>(static_cast<cudaStream_t>(stream), a);
 }

@@ -41,17 +41,6 @@ constexpr int kMaxCells = 512;
 constexpr int kMaxRect = 5 * kMaxCells;  // (cell, half-shell row) rectangles of the all-pairs producer
 constexpr int kExcl = 2;                // bonded partners per nucleotide (as the reference's (N,2) dense mask)
 
-template <class T, int BASE, int COUNT>
-struct RegAcc {
-  T r[COUNT];
-  __device__ __forceinline__ void zero() {
-#pragma unroll
-    for (int k = 0; k < COUNT; ++k) r[k] = T(0);
-  }
-  __device__ __forceinline__ void add(int, int idx, T v) { r[idx - BASE] += v; }
-  __device__ __forceinline__ void add_scatter(int, int, T, bool) {}
-};
-
 struct FrameSmem {
   // byte offsets into dynamic shared memory; computed on the host and passed as a kernel parameter so that the
   // kernel re-reads them from the constant bank instead of rematerialising the whole chain under register pressure

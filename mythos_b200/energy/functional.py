@@ -125,6 +125,13 @@ def _launch(
     a.d_quat = _lib.ptr(d_quat)
     a.d_params = _lib.ptr(d_params)
     a.d_params_frame_stride = stride
+    ws = None
+    if cap and not (flags & _lib.FLAG_GENERIC_KERNEL):
+        # scratch of the phase-queued list kernel (caller-owned, as everywhere in the C-ABI); the caching allocator
+        # makes this a pointer bump, and it is graph-capture safe
+        need = int(_lib.lib().mythos_b200_energy_workspace_bytes(N, F, cap, 8 if dtype == torch.float64 else 4))
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), need
     fn = getattr(_lib.lib(), f"mythos_b200_energy_{sfx}")
     with torch.cuda.device(dev):
         _lib.check(fn(_lib.current_stream(dev), C.byref(a)), "mythos_b200_energy")
