@@ -400,7 +400,14 @@ typedef struct mb_nl_args {
   int32_t* overflow;      /* out (1), OR-ed */
   void* workspace;
   size_t workspace_bytes;
+  uint32_t flags;         /* MB_NL_* */
+  uint32_t _pad;
+  int32_t* max_row;       /* rows mode: out (F) longest row found (to size the rows), or NULL */
 } mb_nl_args;
+#define MB_NL_ROWS 0x1u /* one-pass build: instead of a compact list, row k-major slots of width capacity / n per nucleotide
+                         * (entry k * n + p = k-th partner of the p-th nucleotide in cell order), unused slots = n (the
+                         * padding value); *overflow bit 0 is set if a row is too narrow; count = pairs found.  Consumers
+                         * must scan the whole capacity (pair_count = NULL).                                            */
 size_t mythos_b200_nl_workspace_bytes(int32_t n, int32_t n_frames);
 int mythos_b200_nl_build_f64(void* cuda_stream, const mb_nl_args* a);
 int mythos_b200_nl_build_f32(void* cuda_stream, const mb_nl_args* a);

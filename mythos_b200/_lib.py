@@ -31,6 +31,7 @@ TERM_NAMES = (
 BONDED_TERMS, UNBONDED_TERMS, ALL_TERMS = 0x07, 0xF8, 0xFF
 FLAG_ACCUMULATE = 0x1
 FLAG_GENERIC_KERNEL = 0x2
+NL_ROWS = 0x1
 MAX_BANKS = 3
 STATUS = {0: "MB_OK", 1: "MB_EINVAL_SHAPE", 2: "MB_EINVAL_MODEL", 3: "MB_ECAPACITY", 4: "MB_ECUDA"}
 
@@ -116,6 +117,9 @@ class NlArgs(C.Structure):
         ("overflow", C.c_void_p),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
+        ("flags", C.c_uint32),
+        ("_pad", C.c_uint32),
+        ("max_row", C.c_void_p),
     ]
 
 

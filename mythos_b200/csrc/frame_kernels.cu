@@ -4,25 +4,28 @@
 // -- are staged once in shared memory (56 + 24 B per nucleotide in float64: 163 KB at N = 2040, inside the 227 KB a
 // CTA may use on sm_100a), and every pair of the frame is found AND evaluated from there: in all-pairs mode
 // (the reference's `topology.unbonded_neighbors` semantics) the CTA bins its nucleotides into a shared-memory cell
-// list and walks cell pairs itself, so no pair list ever exists in HBM; with an explicit list the list is streamed.
+// list and walks it itself, so no pair list ever exists in HBM; with an explicit list the list is streamed.
 //
 // Work is regrouped so that each code region runs with (nearly) full warps -- the generic one-thread-per-pair
 // kernel spent 93 % of its issue slots waiting on instruction fetch because every lane wandered through a 229 KB
 // instruction stream (profiles/r01_v1_*):
 //
 //   phase B   bonded pairs (FENE, bonded excluded volume, stacking), one thread per bond
-//   producer  all-pairs mode: each warp walks one (cell, half-shell neighbour cell) tile of the shared-memory cell list,
-//             lanes over the flattened member pairs; accepted pairs are staged per warp and merged in warp order
-//             (deterministic) into queue NL.   list mode: one tile of the frame's pair list goes into queue NL.
-//   phase 1   a CTA-full of queue NL: Debye-Hueckel on the (cached) backbone sites, parameter gradients in REGISTERS;
-//             pairs inside the short-range centre cutoff are compacted into queue SR
+//   producer  all-pairs mode: cells of HALF the cutoff (5x5x5 stencil: 58 % of the candidates a 3x3x3 stencil of
+//             full-size cells has to test).  Thread t walks the forward half shell of the nucleotides at cell-order
+//             positions t, t+512, ...: 13 (dy,dz) rows, each one contiguous run of the cell-ordered list.  A step tests
+//             kSlice candidates per thread.  list mode: kSlice list entries per thread.
+//             Either way a candidate inside the caller's centre cutoff is split by the exact supports of the terms:
+//             backbone-site distance inside the Debye-Hueckel cutoff -> queue DB (about 1 listed pair in 3), centre
+//             distance inside the short-range cutoff -> queue SR (1 in 6); the rest is dropped right there.
+//   phase 1   a CTA-full of DB: Debye-Hueckel on the cached backbone sites, parameter gradients in REGISTERS
 //   phase 2   a CTA-full of SR: excluded volume (4 site pairs), gradients in registers; pairs inside the hydrogen-bond /
 //             cross-stacking radial window go to queue BP, inside the coaxial window to queue CX
 //   phase 3   a CTA-full of BP / CX: the six-angle products with dense lanes; their parameter gradients are
 //             warp-reduced into the shared-memory bank image
 //   flush     partial queues, register accumulators -> bank image -> one J row, per-term energies -> one terms row
 //
-// Every queue append is ordered (block prefix over warp ballots), so results are bitwise repeatable run to run.
+// Every queue append is ordered (block prefix over warp counts), so results are bitwise repeatable run to run.
 #include "energy_dev.cuh"
 
 namespace mb {
@@ -33,18 +36,23 @@ namespace mb {
 constexpr int kFB = MB_FRAME_THREADS;  // threads per CTA (one CTA per SM: the frame fills most of shared memory)
 constexpr int kFWarps = kFB / 32;
 constexpr int kQCap = 2 * kFB;          // SR / BP / CX queues
-constexpr int kSlice = 8;               // candidates one thread examines per producer step (independent, unrolled)
+#ifndef MB_FRAME_STENCIL
+#define MB_FRAME_STENCIL 2  // cells of cutoff / 2 (falls back to 1 when the grid would not fit)
+#endif
+#ifndef MB_FRAME_SLICE
+#define MB_FRAME_SLICE 6
+#endif
+constexpr int kSlice = MB_FRAME_SLICE;  // candidates one thread examines per producer step (independent, unrolled)
 constexpr int kU1 = 2;                  // pairs per thread in one phase-1 batch (instruction-level parallelism)
-constexpr int kNlCap = kU1 * kFB + kFB * kSlice;
-constexpr int kSrCap = kFB + kU1 * kFB;
-constexpr int kMaxCells = 512;
-constexpr int kMaxRect = 5 * kMaxCells;  // (cell, half-shell row) rectangles of the all-pairs producer
+constexpr int kNlCap = kU1 * kFB + kFB * kSlice;  // queue DB: a phase-1 backlog + one producer step
+constexpr int kSrCap = kFB + kFB * kSlice;        // queue SR: a phase-2 backlog + one producer step
+constexpr int kMaxCells = 2048;
 constexpr int kExcl = 2;                // bonded partners per nucleotide (as the reference's (N,2) dense mask)
 
 struct FrameSmem {
   // byte offsets into dynamic shared memory; computed on the host and passed as a kernel parameter so that the
   // kernel re-reads them from the constant bank instead of rematerialising the whole chain under register pressure
-  unsigned c, q, back, p, acc, e, flags, q_nl, q_sr, q_bp, q_cx, wcnt, ctr, rect, cstart, corder, excl, grid, total;
+  unsigned c, q, back, p, acc, e, flags, q_nl, q_sr, q_bp, q_cx, wcnt, ctr, cstart, corder, excl, grid, total;
 };
 template <class T>
 inline FrameSmem frame_smem_layout(int n, bool wp, bool cache_back, bool cells) {
@@ -66,9 +74,8 @@ inline FrameSmem frame_smem_layout(int n, bool wp, bool cache_back, bool cells) 
   L.q_sr = take(sizeof(uint32_t) * kSrCap);
   L.q_bp = take(sizeof(uint32_t) * kQCap);
   L.q_cx = take(sizeof(uint32_t) * kQCap);
-  L.wcnt = take(sizeof(int) * (kFWarps + 1));
+  L.wcnt = take(sizeof(int) * 2 * (kFWarps + 1));
   L.ctr = take(sizeof(int) * 8);
-  L.rect = take(cells ? sizeof(int) * (kMaxRect + 1) : 0);
   L.cstart = take(cells ? sizeof(int) * (kMaxCells + 1) : 0);
   L.corder = take(cells ? sizeof(uint16_t) * n : 0);
   L.excl = take(cells ? sizeof(uint16_t) * kExcl * n : 0);
@@ -128,6 +135,38 @@ __device__ __forceinline__ void q_push_multi(uint32_t* q, int* n, int* wcnt, uns
   __syncthreads();
 }
 
+// ordered block-wide append of up to U entries per thread into TWO queues at once (bit u of bits_a / bits_b selects
+// vals[u] for queue a / b); one scan serves both (counts packed 16 + 16 bits); order = (thread, u)
+template <int U>
+__device__ __forceinline__ void q_push2_multi(uint32_t* qa, int* na, unsigned bits_a, uint32_t* qb, int* nb, unsigned bits_b,
+                                              int* wcnt, const uint32_t vals[U]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mine = __popc(bits_a) | (__popc(bits_b) << 16);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) wcnt[warp] = incl;
+  __syncthreads();
+  const int old_a = *na, old_b = *nb;
+  const int before = warp_prefix(wcnt, warp, lane);
+  const int excl = before + incl - mine;
+  int off_a = old_a + (excl & 0xffff), off_b = old_b + (excl >> 16);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (bits_a & (1u << u)) qa[off_a++] = vals[u];
+    if (bits_b & (1u << u)) qb[off_b++] = vals[u];
+  }
+  __syncthreads();
+  if (threadIdx.x == kFB - 1) {
+    *na = old_a + ((before + incl) & 0xffff);
+    *nb = old_b + ((before + incl) >> 16);
+  }
+  __syncthreads();
+}
+
 template <class T>
 __device__ __forceinline__ Nuc<T> smem_nuc(const T* sC, const T* sQ, int i) {
   Nuc<T> n;
@@ -148,22 +187,31 @@ __device__ __forceinline__ void block_sum_to(T v, T* dst) {
 template <class T>
 struct CellGrid {
   T origin[3], inv[3];  // cell = (x - origin) * inv
-  int n[3], ncell;
+  int n[3], ncell, S;   // S = stencil half-width in cells
 };
 
-// members of one forward-half-shell row of cell `cid`: cells that are neighbours along x have consecutive ids, so
-// the row is one contiguous run of the cell-ordered list (two runs when a periodic x wraps).  row 0 = own cell
-// (partners after p only: the first own_len entries) + the +x cell; rows 1..4 = (dy,dz) in
-// {(+1,0), (-1,+1), (0,+1), (+1,+1)} with x offsets -1..+1.
+// Cell grid with stencil half-width S (cell edge >= cutoff / S).  The forward half shell of a cell is 1 + S + S(2S+1)
+// (dy,dz) rows; cells that are neighbours along x have consecutive ids, so a row is one contiguous run of the
+// cell-ordered list (two runs when a periodic x wraps).  Row 0 = own cell (partners after p only) and the +x cells.
 struct RowRun {
-  int s0, len0, s1, len1, own_len;
+  int s0, len0, s1, len1;
 };
+__device__ __forceinline__ int half_shell_rows(int S) { return 1 + S + S * (2 * S + 1); }
+
 template <class T>
-__device__ __forceinline__ RowRun row_run(const CellGrid<T>* grid, const int* sCstart, bool periodic, int cid, int row) {
-  RowRun r{0, 0, 0, 0, 0};
+__device__ __forceinline__ RowRun row_run(const CellGrid<T>* grid, const int* sCstart, bool periodic, int ax, int ay, int az,
+                                          int row, int own_skip) {
+  RowRun r{0, 0, 0, 0};
+  const int S = grid->S;
   const int n0 = grid->n[0], n1 = grid->n[1], n2 = grid->n[2];
-  const int ax = cid % n0, ay = (cid / n0) % n1, az = cid / (n0 * n1);
-  const int dy = (row == 0) ? 0 : (row == 1 ? 1 : row - 3), dz = (row >= 2) ? 1 : 0;
+  int dy = 0, dz = 0;
+  if (row > S) {
+    const int k = row - S - 1;
+    dz = 1 + k / (2 * S + 1);
+    dy = k % (2 * S + 1) - S;
+  } else {
+    dy = row;
+  }
   int by = ay + dy, bz = az + dz;
   if (periodic) {
     if ((n1 == 1 && dy) || (n2 == 1 && dz)) return r;
@@ -173,15 +221,15 @@ __device__ __forceinline__ RowRun row_run(const CellGrid<T>* grid, const int* sC
     return r;
   }
   const int rowbase = n0 * (by + n1 * bz);
-  int xlo = (row == 0) ? ax : ax - 1, xhi = ax + 1;  // inclusive cell range along x
+  int xlo = (row == 0) ? ax : ax - S, xhi = ax + S;  // inclusive cell range along x
   if (periodic && n0 > 1) {
-    if (xlo < 0) {  // wraps on the low side: [n0-1] and [0 .. xhi]
-      r.s1 = sCstart[rowbase + n0 - 1];
+    if (xlo < 0) {  // wraps on the low side: [n0+xlo .. n0-1] and [0 .. xhi]
+      r.s1 = sCstart[rowbase + n0 + xlo];
       r.len1 = sCstart[rowbase + n0] - r.s1;
       xlo = 0;
-    } else if (xhi >= n0) {  // wraps on the high side: [xlo .. n0-1] and [0]
+    } else if (xhi >= n0) {  // wraps on the high side: [xlo .. n0-1] and [0 .. xhi-n0]
       r.s1 = sCstart[rowbase];
-      r.len1 = sCstart[rowbase + 1] - r.s1;
+      r.len1 = sCstart[rowbase + xhi - n0 + 1] - r.s1;
       xhi = n0 - 1;
     }
   } else {
@@ -191,8 +239,28 @@ __device__ __forceinline__ RowRun row_run(const CellGrid<T>* grid, const int* sC
   }
   r.s0 = sCstart[rowbase + xlo];
   r.len0 = sCstart[rowbase + xhi + 1] - r.s0;
-  if (row == 0) r.own_len = sCstart[rowbase + ax + 1] - r.s0;
+  if (row == 0) {  // own cell: members are in ascending id order, partners of p are the ones after it
+    r.s0 += own_skip;
+    r.len0 -= own_skip;
+  }
   return r;
+}
+
+// integer cell coordinates of a position (the same arithmetic wherever it is needed, so results agree bit for bit)
+template <class T>
+__device__ __forceinline__ void cell_of(const CellGrid<T>* grid, const T* box, bool periodic, T px, T py, T pz, int cc[3]) {
+  const T pos[3] = {px, py, pz};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    T x = pos[d] - grid->origin[d];
+    if (periodic) {
+      x = fmod(x, box[d]);
+      if (x < T(0)) x += box[d];
+    }
+    int ci = int(x * grid->inv[d]);
+    ci = ci < 0 ? 0 : (ci >= grid->n[d] ? grid->n[d] - 1 : ci);
+    cc[d] = ci;
+  }
 }
 
 #ifdef MB_FRAME_PROFILE
@@ -220,7 +288,6 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   int* ctr = reinterpret_cast<int*>(smem + L.ctr);  // [0] n_sr [1] n_bp [2] n_cx [3] n_nl [5] too many bonds [6] more tiles
   // packed cell coordinates (10 bits per axis): needed only while the cell list is built, aliases queues SR/BP/CX
   uint32_t* sCell = reinterpret_cast<uint32_t*>(smem + L.q_sr);
-  int* sRect = reinterpret_cast<int*>(smem + L.rect);  // exclusive prefix of the padded rectangle sizes
   int* sCstart = reinterpret_cast<int*>(smem + L.cstart);
   uint16_t* sCorder = reinterpret_cast<uint16_t*>(smem + L.corder);
   uint16_t* sExcl = reinterpret_cast<uint16_t*>(smem + L.excl);
@@ -357,7 +424,6 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      T cs = a.all_pairs_cutoff * T(1.0001);
       T ext[3];
       for (int d = 0; d < 3; ++d) {
         if (periodic) {
@@ -373,12 +439,15 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
           ext[d] = h - l;
         }
       }
+      // cells of half the cutoff (stencil +-2) when the grid fits, else of the full cutoff (stencil +-1), else coarser
+      int S = MB_FRAME_STENCIL;
+      T cs = a.all_pairs_cutoff * T(1.0001) / T(S);
       while (true) {
         long long tot = 1;
         for (int d = 0; d < 3; ++d) {
           int nd = periodic ? int(ext[d] / cs) : int(ext[d] / cs) + 1;
           if (nd < 1) nd = 1;
-          if (periodic && nd < 3) nd = 1;  // fewer than 3 cells along a periodic axis: one cell spanning it
+          if (periodic && nd < 2 * S + 1) nd = 1;  // too few cells along a periodic axis for the stencil: one cell spanning it
           grid->n[d] = nd;
           tot *= nd;
         }
@@ -386,8 +455,14 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
           grid->ncell = int(tot);
           break;
         }
-        cs *= T(1.26);
+        if (S > 1) {
+          S = 1;
+          cs = a.all_pairs_cutoff * T(1.0001);
+        } else {
+          cs *= T(1.26);
+        }
       }
+      grid->S = S;
       for (int d = 0; d < 3; ++d) grid->inv[d] = periodic ? T(grid->n[d]) / ext[d] : T(1) / cs;
     }
     __syncthreads();
@@ -422,17 +497,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
     }
     for (int i = threadIdx.x; i < n; i += kFB) {
       int cc[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        T x = sC[3 * i + d] - grid->origin[d];
-        if (periodic) {
-          x = fmod(x, M.box[d]);
-          if (x < T(0)) x += M.box[d];
-        }
-        int ci = int(x * grid->inv[d]);
-        ci = ci < 0 ? 0 : (ci >= grid->n[d] ? grid->n[d] - 1 : ci);
-        cc[d] = ci;
-      }
+      cell_of(grid, M.box, periodic, sC[3 * i], sC[3 * i + 1], sC[3 * i + 2], cc);
       const int cid = cc[0] + grid->n[0] * (cc[1] + grid->n[1] * cc[2]);
       sCell[i] = uint32_t(cc[0]) | (uint32_t(cc[1]) << 10) | (uint32_t(cc[2]) << 20);
       atomicAdd(&sCstart[cid + 1], 1);
@@ -480,36 +545,6 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
       }
     }
     __syncthreads();
-    // rectangles: (cell A, half-shell row) -> |A| x |row members| candidate pairs, padded to a multiple of kSlice so
-    // that one thread's kSlice consecutive candidates never straddle two rectangles
-    const int nrect = 5 * ncell;
-    for (int R = threadIdx.x; R < nrect; R += kFB) {
-      const int cid = R / 5, row = R - 5 * cid;
-      const int na = sCstart[cid + 1] - sCstart[cid];
-      int len = 0;
-      if (na > 0) {
-        RowRun rr = row_run(grid, sCstart, periodic, cid, row);
-        len = rr.len0 + rr.len1;
-      }
-      sRect[R + 1] = ((na * len + kSlice - 1) / kSlice) * kSlice;
-    }
-    if (threadIdx.x == 0) sRect[0] = 0;
-    __syncthreads();
-    if (warp == 0) {
-      int carry = 0;
-      for (int base = 0; base < nrect; base += 32) {
-        const int k = base + lane;
-        int x = (k < nrect) ? sRect[k + 1] : 0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int y = __shfl_up_sync(kFull, x, o);
-          if (lane >= o) x += y;
-        }
-        if (k < nrect) sRect[k + 1] = carry + x;
-        carry += __shfl_sync(kFull, x, 31);
-      }
-    }
-    __syncthreads();
   }
 
   MB_TICK(1)  // cell list build
@@ -527,11 +562,13 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
       }
     }
     long long base = 0;  // list mode: next list entry
-    // all-pairs mode producer state: position in the flattened list of (cell, half-shell row) candidate rectangles;
-    // a step examines kFB * kSlice candidates, so at most that many pairs enter queue NL per step
-    int cand_base = 0;
-    const int nrect = cells ? 5 * grid->ncell : 0;
-    const int ncand = cells ? sRect[nrect] : 0;
+    // all-pairs mode producer state of this thread: it walks the forward half shells of the nucleotides at cell-order
+    // positions threadIdx.x, +kFB, ... as one candidate stream, kSlice candidates per step
+    // (packed into five registers so that the consumer phases keep theirs: position | row << 16 | fresh << 24, k | len << 16,
+    // the row's two runs as start | length << 16, cell coordinates 10 bits each)
+    unsigned st_a = unsigned(threadIdx.x) | (1u << 24), st_kl = 0u, st_r0 = 0u, st_r1 = 0u, st_c = 0u;
+    const int n_rows = cells ? half_shell_rows(grid->S) : 0;
+    const T rc_debye2 = want_debye ? sP[MB_P_DEBYE_RCUT] * sP[MB_P_DEBYE_RCUT] : T(-1);
     bool flush = false;
     while (true) {
       const int n_sr = ctr[0], n_bp = ctr[1], n_cx = ctr[2], n_nl = ctr[3];
@@ -635,131 +672,173 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         continue;
       }
       if (n_nl >= kU1 * kFB || (flush && n_nl > 0)) {
-        // ---------------- phase 1: Debye-Hueckel on up to kU1 found pairs per thread (independent chains: the CTA
-        // has only 16 warps, so latency is hidden inside the thread), short-range filter into queue SR
+        // ---------------- phase 1: Debye-Hueckel on up to kU1 in-range pairs per thread (independent chains: the CTA
+        // has only 16 warps, so latency is hidden inside the thread)
         const int cnt = n_nl >= kU1 * kFB ? kU1 * kFB : n_nl;
         const int first = n_nl - cnt;
-        unsigned sr_bits = 0;
-        uint32_t pks[kU1];
 #pragma unroll
         for (int u = 0; u < kU1; ++u) {
           const int t = threadIdx.x + u * kFB;
           const bool valid = t < cnt;
           const uint32_t pk = valid ? qNL[first + t] : 0u;
-          pks[u] = pk;
           const int i = pk & 0xffff, j = pk >> 16;
-          const V3<T> ci = v3<T>(sC[3 * i], sC[3 * i + 1], sC[3 * i + 2]), cj = v3<T>(sC[3 * j], sC[3 * j + 1], sC[3 * j + 2]);
-          const V3<T> dc = disp(cj, ci, M.box);
-          const T d2 = dot(dc, dc);
-          if (want_debye) {
-            V3<T> db;
-            if (CACHE_BACK) {
-              db = disp(v3<T>(sB[3 * j], sB[3 * j + 1], sB[3 * j + 2]), v3<T>(sB[3 * i], sB[3 * i + 1], sB[3 * i + 2]), M.box);
-            } else {
-              const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
-              db = disp(site(nj, g.back[0], g.back[1], g.back[2]), site(ni, g.back[0], g.back[1], g.back[2]), M.box);
-            }
-            T m = T(1);
-            if (M.half_charged_ends) m = ((sF[i] & 4) ? T(0.5) : T(1)) * ((sF[j] & 4) ? T(0.5) : T(1));
-            V3<T> gd;
-            if (WP)
-              e[MB_TERM_DEBYE] += debye_term<T, false, true>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, dacc);
-            else
-              e[MB_TERM_DEBYE] += debye_term<T, false, false>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, nacc);
+          V3<T> db;
+          if (CACHE_BACK) {
+            db = disp(v3<T>(sB[3 * j], sB[3 * j + 1], sB[3 * j + 2]), v3<T>(sB[3 * i], sB[3 * i + 1], sB[3 * i + 2]), M.box);
+          } else {
+            const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
+            db = disp(site(nj, g.back[0], g.back[1], g.back[2]), site(ni, g.back[0], g.back[1], g.back[2]), M.box);
           }
-          if (valid && d2 < sr_cut2) sr_bits |= 1u << u;
+          T m = T(1);
+          if (M.half_charged_ends) m = ((sF[i] & 4) ? T(0.5) : T(1)) * ((sF[j] & 4) ? T(0.5) : T(1));
+          V3<T> gd;
+          if (WP)
+            e[MB_TERM_DEBYE] += debye_term<T, false, true>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, dacc);
+          else
+            e[MB_TERM_DEBYE] += debye_term<T, false, false>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, nacc);
         }
+        __syncthreads();  // the batch has been read before the counter moves
         if (threadIdx.x == 0) ctr[3] = first;
-        if (want_sr)
-          q_push_multi<kU1>(qSR, &ctr[0], wcnt, sr_bits, pks);
-        else
-          __syncthreads();
+        __syncthreads();
         MB_TICK(3)
         continue;
       }
       if (flush) break;
-      // ---------------- producer
+      // ---------------- producer: kSlice candidates per thread; a candidate inside the caller's centre cutoff goes to
+      // queue DB if its backbone sites are inside the Debye-Hueckel cutoff and to queue SR if its centres are inside the
+      // short-range cutoff (the exact supports of the terms: everything else contributes exactly zero)
+      unsigned acc_db = 0, acc_sr = 0;
+      uint32_t found[kSlice];
+#pragma unroll
+      for (int u = 0; u < kSlice; ++u) found[u] = 0u;
       if (!cells) {
         if (base >= count) {
           flush = true;
           continue;
         }
-        const long long k = base + threadIdx.x;
-        base += kFB;
-        int i = 0, j = 0;
-        bool valid = k < count;
-        if (valid) {
-          i = pl[k];
-          j = pl[a.pair_capacity + k];
-          valid = (i >= 0 && j >= 0 && i < n && j < n);
+#pragma unroll
+        for (int u = 0; u < kSlice; ++u) {
+          const long long k = base + threadIdx.x + (long long)u * kFB;
+          if (k < count) {
+            const int i = pl[k], j = pl[a.pair_capacity + k];
+            if (i >= 0 && j >= 0 && i < n && j < n) {
+              found[u] = uint32_t(i) | (uint32_t(j) << 16);
+              const V3<T> dc = disp(v3<T>(sC[3 * j], sC[3 * j + 1], sC[3 * j + 2]), v3<T>(sC[3 * i], sC[3 * i + 1], sC[3 * i + 2]), M.box);
+              if (want_sr && dot(dc, dc) < sr_cut2) acc_sr |= 1u << u;
+              if (want_debye) {
+                V3<T> db;
+                if (CACHE_BACK) {
+                  db = disp(v3<T>(sB[3 * j], sB[3 * j + 1], sB[3 * j + 2]), v3<T>(sB[3 * i], sB[3 * i + 1], sB[3 * i + 2]), M.box);
+                } else {
+                  const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
+                  db = disp(site(nj, g.back[0], g.back[1], g.back[2]), site(ni, g.back[0], g.back[1], g.back[2]), M.box);
+                }
+                if (dot(db, db) < rc_debye2) acc_db |= 1u << u;
+              }
+            }
+          }
         }
-        q_push(qNL, &ctr[3], wcnt, valid, uint32_t(i) | (uint32_t(j) << 16));
+        base += (long long)kFB * kSlice;
       } else {
-        if (cand_base >= ncand) {
+        // CTA-uniform exit test: every thread has exhausted its stream
+        const int busy = __syncthreads_or(int(st_a & 0xffffu) < n);
+        if (!busy) {
           flush = true;
           continue;
         }
-        // each thread takes kSlice consecutive candidates of the flattened rectangle list (one rectangle, by padding)
-        const int c0 = cand_base + threadIdx.x * kSlice;
-        cand_base += kFB * kSlice;
-        unsigned accept = 0;  // bit u: candidate c0 + u is a pair inside the cutoff
-        uint32_t found[kSlice];
-#pragma unroll
-        for (int u = 0; u < kSlice; ++u) found[u] = 0u;
-        if (c0 < ncand) {
-          int lo = 0, hi = nrect;  // largest R with sRect[R] <= c0
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (sRect[mid] <= c0) lo = mid; else hi = mid;
+        int st_pos = int(st_a & 0xffffu), st_row = int((st_a >> 16) & 0xffu), st_k = int(st_kl & 0xffffu), st_len = int(st_kl >> 16);
+        bool st_fresh = (st_a >> 24) != 0u;
+        RowRun st_run{int(st_r0 & 0xffffu), int(st_r0 >> 16), int(st_r1 & 0xffffu), int(st_r1 >> 16)};
+        int st_ax = int(st_c & 1023u), st_ay = int((st_c >> 10) & 1023u), st_az = int(st_c >> 20);
+        int st_p = 0, st_e0 = 0xffff, st_e1 = 0xffff;
+        T st_x = 0, st_y = 0, st_z = 0;
+        if (st_pos < n && !st_fresh) {  // reload the current nucleotide
+          st_p = sCorder[st_pos];
+          st_x = sC[3 * st_p];
+          st_y = sC[3 * st_p + 1];
+          st_z = sC[3 * st_p + 2];
+          const unsigned ex = *reinterpret_cast<const unsigned*>(sExcl + st_p * kExcl);
+          st_e0 = int(ex & 0xffffu);
+          st_e1 = int(ex >> 16);
+        }
+        {
+          // advance to a row that still has candidates, once per step with the warp converged (a row transition inside
+          // the slice would make every lane wait for every other lane's row decode); the slice ends with the row
+          while (st_pos < n && st_k >= st_len) {
+            int skip = 0;
+            if (st_fresh) {
+              st_fresh = false;
+              st_p = sCorder[st_pos];
+              st_x = sC[3 * st_p];
+              st_y = sC[3 * st_p + 1];
+              st_z = sC[3 * st_p + 2];
+              const unsigned ex = *reinterpret_cast<const unsigned*>(sExcl + st_p * kExcl);  // both partners in one word
+              st_e0 = int(ex & 0xffffu);
+              st_e1 = int(ex >> 16);
+              int cc[3];  // the build-time cell table aliases the queues, so the coordinates are recomputed
+              cell_of(grid, M.box, periodic, st_x, st_y, st_z, cc);
+              st_ax = cc[0];
+              st_ay = cc[1];
+              st_az = cc[2];
+              skip = st_pos - sCstart[st_ax + grid->n[0] * (st_ay + grid->n[1] * st_az)] + 1;
+              st_row = 0;
+            } else {
+              ++st_row;
+            }
+            if (st_row >= n_rows) {  // next nucleotide of this thread
+              st_pos += kFB;
+              st_fresh = true;
+              st_k = st_len = 0;
+              continue;
+            }
+            st_run = row_run(grid, sCstart, periodic, st_ax, st_ay, st_az, st_row, skip);
+            st_k = 0;
+            st_len = st_run.len0 + st_run.len1;
           }
-          const int R = lo, cid = R / 5, row = R - 5 * cid;
-          const int a0 = sCstart[cid], na = sCstart[cid + 1] - a0;
-          const RowRun rr = row_run(grid, sCstart, periodic, cid, row);
-          const int len = rr.len0 + rr.len1;
-          const int l0 = c0 - sRect[R];
-          int ia = l0 / len, k = l0 - ia * len;  // len > 0: an empty rectangle has size 0 and is never found
-          // the producer is shared-memory-bandwidth bound (random 8-byte reads): keep p's centre and bonded partners in
-          // registers while ia stays the same, and read a candidate's y,z only if its x already passes
-          int cur = -1, pp = 0, e0 = 0, e1 = 0;
-          T px = 0, py = 0, pz = 0;
+        }
+        const int st_cnt = (st_pos < n) ? ((st_len - st_k) < kSlice ? (st_len - st_k) : kSlice) : 0;
 #pragma unroll
-          for (int u = 0; u < kSlice; ++u) {
-            if (ia < na) {
-              if (ia != cur) {
-                cur = ia;
-                pp = sCorder[a0 + ia];
-                px = sC[3 * pp];
-                py = sC[3 * pp + 1];
-                pz = sC[3 * pp + 2];
-                const unsigned ex = *reinterpret_cast<const unsigned*>(sExcl + pp * kExcl);  // both partners in one word
-                e0 = int(ex & 0xffffu);
-                e1 = int(ex >> 16);
-              }
-              const int r = sCorder[k < rr.len0 ? rr.s0 + k : rr.s1 + (k - rr.len0)];
-              if (!(k < rr.own_len && r <= pp) && r != e0 && r != e1) {
-                T dx = sC[3 * r] - px;
-                if (periodic) dx = wrap1(dx, M.box[0]);
-                if (dx * dx < cut2) {
-                  T dy = sC[3 * r + 1] - py, dz = sC[3 * r + 2] - pz;
-                  if (periodic) {
-                    dy = wrap1(dy, M.box[1]);
-                    dz = wrap1(dz, M.box[2]);
-                  }
-                  if (dx * dx + dy * dy + dz * dz < cut2) {
-                    accept |= 1u << u;
-                    found[u] = pp < r ? (uint32_t(pp) | (uint32_t(r) << 16)) : (uint32_t(r) | (uint32_t(pp) << 16));
+        for (int u = 0; u < kSlice; ++u) {
+          if (u < st_cnt) {
+            const int kk = st_k + u;
+            const int r = sCorder[kk < st_run.len0 ? st_run.s0 + kk : st_run.s1 + (kk - st_run.len0)];
+            if (r != st_e0 && r != st_e1) {
+              T dx = sC[3 * r] - st_x;
+              if (periodic) dx = wrap1(dx, M.box[0]);
+              if (dx * dx < cut2) {
+                T dy = sC[3 * r + 1] - st_y, dz = sC[3 * r + 2] - st_z;
+                if (periodic) {
+                  dy = wrap1(dy, M.box[1]);
+                  dz = wrap1(dz, M.box[2]);
+                }
+                const T d2 = dx * dx + dy * dy + dz * dz;
+                if (d2 < cut2) {
+                  const int i = st_p < r ? st_p : r, j = st_p < r ? r : st_p;
+                  found[u] = uint32_t(i) | (uint32_t(j) << 16);
+                  if (want_sr && d2 < sr_cut2) acc_sr |= 1u << u;
+                  if (want_debye) {
+                    V3<T> db;
+                    if (CACHE_BACK) {
+                      db = disp(v3<T>(sB[3 * j], sB[3 * j + 1], sB[3 * j + 2]), v3<T>(sB[3 * i], sB[3 * i + 1], sB[3 * i + 2]), M.box);
+                    } else {
+                      const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
+                      db = disp(site(nj, g.back[0], g.back[1], g.back[2]), site(ni, g.back[0], g.back[1], g.back[2]), M.box);
+                    }
+                    if (dot(db, db) < rc_debye2) acc_db |= 1u << u;
                   }
                 }
               }
             }
-            if (++k == len) {
-              k = 0;
-              ++ia;
-            }
           }
         }
-        q_push_multi<kSlice>(qNL, &ctr[3], wcnt, accept, found);
+        st_k += st_cnt;
+        st_a = unsigned(st_pos) | (unsigned(st_row) << 16) | (st_fresh ? (1u << 24) : 0u);
+        st_kl = unsigned(st_k) | (unsigned(st_len) << 16);
+        st_r0 = unsigned(st_run.s0) | (unsigned(st_run.len0) << 16);
+        st_r1 = unsigned(st_run.s1) | (unsigned(st_run.len1) << 16);
+        st_c = unsigned(st_ax) | (unsigned(st_ay) << 10) | (unsigned(st_az) << 20);
       }
+      q_push2_multi<kSlice>(qNL, &ctr[3], acc_db, qSR, &ctr[0], acc_sr, wcnt, found);
       MB_TICK(2)
     }
   }
@@ -818,7 +897,7 @@ static bool pick_layout(const EnergyDev<T>& a, bool wp, bool* cache_back, FrameS
 
 template <class T>
 bool frame_kernel_eligible(const EnergyDev<T>& a) {
-  if (a.M.n_banks != 1 || a.n > 65535) return false;
+  if (a.M.n_banks != 1 || a.n > 60000) return false;  // 16-bit indices, with headroom for the producer stream position
   bool cb;
   FrameSmem L;
   return pick_layout(a, true, &cb, &L);

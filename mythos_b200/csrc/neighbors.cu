@@ -1,4 +1,4 @@
-// neighbors.cu -- batched cell-list neighbour build: integer binning, counting sort, count / scan / fill.
+// neighbors.cu -- batched cell-list neighbour build: integer binning, counting sort into cell order, count / scan / fill.
 //
 // Replaces mythos/utils/neighbors.py:12-59, i.e. jax_md.partition.neighbor_list(format=OrderedSparse,
 // disable_cell_list=True, custom_mask_function=bonded mask), whose per-rebuild cost is an O(N^2) distance
@@ -8,47 +8,79 @@
 // evaluated in the positions' dtype with explicit round-to-nearest mul/add (no FMA contraction), so the pair
 // SET is bit-exact against an all-pairs evaluation of the same expression.
 //
-// Per frame (frames are independent; grid.y = frame):
-//   1. bounds    min corner of the frame (free space) -> cell origin
-//   2. bin       integer cell coordinates (10 bits per axis) -> key; hashed bucket; bucket histogram
-//   3. scan      exclusive scan of the histogram
-//   4. scatter   particle ids into bucket order, then each bucket segment sorted by id (deterministic)
-//   5. count     per particle: half-shell walk (own cell with j>i + 13 forward cells), accept test
-//   6. scan      exclusive scan of the per-particle counts -> offsets, total -> count[frame]
-//   7. fill      same walk, writing (min(i,j), max(i,j)) at the particle's offset; tail padded with N
+// All frames of a call are processed together (every kernel is one launch over F x N nucleotides or F x C cells):
+//   1. bounds    per-frame bounding box (free space) by block reduction + ordered-integer atomics
+//   2. grid      per frame: cell edge = cutoff / S (stencil half-width S = 2 when the cell table allows, else 1,
+//                else coarser), grid dimensions, origin
+//   3. bin       integer cell id per nucleotide, cell histogram
+//   4. scan      one exclusive scan over all F x C cell counts: a cell's start in the frame-major sorted order
+//   5. scatter   nucleotide ids into their cell (atomic cursor), then rank inside the cell by id (deterministic) and
+//                write the cell-ordered records (coordinates + id, one 128/256-bit row each)
+//   6. count     one thread per cell-ordered nucleotide walks its forward half shell: (1 + S + S(2S+1)) rows, each one
+//                contiguous run of the sorted arrays (x-neighbouring cells have consecutive ids); neighbouring lanes sit
+//                in the same or adjacent cells, so candidate loads are broadcasts out of L1
+//   7. scan      exclusive scan of the per-nucleotide counts -> offsets; per-frame totals -> count[frame]
+//   8. fill      same walk, writing (min(i,j), max(i,j)) at the nucleotide's offset; tail padded with N
+// Rows mode (MB_NL_ROWS) replaces 6-8 by ONE walk that writes a fixed-width row per nucleotide with the unused slots set
+// to the padding value N: still a valid OrderedSparse list (consumers mask entries >= N wherever they are), at half the
+// cost -- the shape the energy kernels of this library are fed with.
 #include "common.cuh"
 
 namespace mb {
 
 constexpr int kNlBlock = 128;
 constexpr int kMaxExcl = 4;
+constexpr int kNlUnroll = 4;      // candidates in flight per thread in the walk
+constexpr int kScanChunk = 2048;  // elements per block of the multi-block scan (256 threads x 8)
+
+template <class T>
+struct NlGrid {
+  T origin[3], inv[3], width[3];
+  int n[3], S, ncell, _pad;
+};
+
+// cell-ordered record of one nucleotide: coordinates + id in one 16-byte-aligned row (128-bit loads)
+template <class T>
+struct NlRec;
+template <>
+struct alignas(16) NlRec<double> {
+  double x, y, z;
+  int32_t id, pad;
+};
+template <>
+struct alignas(16) NlRec<float> {
+  float x, y, z;
+  int32_t id;
+};
 
 template <class T>
 struct NlDev {
-  int n, n_frames, n_bonded, hbits;  // buckets per frame = 1 << hbits
+  int n, n_frames, n_bonded, cmax;  // cmax = cell-table entries per frame
   const T* center;
   const int32_t* bonded;
   T box[3];
   int periodic;
-  T cell;   // cell edge >= cutoff
-  T cut2;   // (r_cutoff + dr_threshold)^2 in T
+  T cut;    // r_cutoff + dr_threshold
+  T cut2;   // its square, in T
   int32_t* pairs;
   long long capacity;
   int32_t* count;
   int32_t* overflow;
+  int32_t* max_row;  // rows mode: (F) longest row found, or nullptr
   // workspace
-  int32_t* excl;     // (N, kMaxExcl)
-  T* origin;         // (F, 3)
-  int32_t* dims;     // (F, 3)
-  uint32_t* key;     // (F, N)
-  int32_t* bstart;   // (F, H + 1)  histogram, then exclusive scan
-  int32_t* cursor;   // (F, H)
-  int32_t* order;    // (F, N) particle ids in bucket order
-  int32_t* nbcount;  // (F, N + 1) per-particle pair counts, then exclusive scan
+  int32_t* excl;       // (N, kMaxExcl)
+  unsigned long long* bounds;  // (F, 6) ordered-integer min / max corners
+  NlGrid<T>* grid;     // (F)
+  int32_t* cell;       // (F*N) cell id of each nucleotide
+  int32_t* cstart;     // (F*cmax + 1) histogram, then exclusive scan (global offsets into the sorted arrays)
+  int32_t* cursor;     // (F*cmax)
+  int32_t* tmp_order;  // (F*N) ids in cell order, unsorted inside a cell
+  NlRec<T>* srec;      // (F*N) cell-ordered (coordinates, id), ids ascending inside a cell
+  int32_t* nbcount;    // (F*N + 1) per-nucleotide pair counts (cell order), then exclusive scan
+  int32_t* scan_tmp;   // block sums of the multi-block scan
 };
 
-__device__ __forceinline__ uint32_t bucket_of(uint32_t key, int hbits) { return (key * 2654435761u) >> (32 - hbits); }
-
+// ------------------------------------------------------------------------------------------------ exclusions
 __global__ void k_nl_excl_init(int32_t* excl, int n) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n * kMaxExcl) excl[k] = -1;
@@ -66,87 +98,171 @@ __global__ void k_nl_excl_fill(int32_t* excl, const int32_t* bonded, int nb, int
   }
 }
 
+// ------------------------------------------------------------------------------------------------ bounds
+// order-preserving map of a real onto an unsigned integer, so that min / max can be taken with integer atomics
+__device__ __forceinline__ unsigned long long ord_encode(double v) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ord_decode(unsigned long long e) {
+  const unsigned long long u = (e >> 63) ? (e & 0x7fffffffffffffffull) : ~e;
+  return __longlong_as_double((long long)u);
+}
+
+__global__ void k_nl_bounds_init(unsigned long long* bounds, int n_frames) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_frames * 6) bounds[k] = (k % 6 < 3) ? ~0ull : 0ull;
+}
+
 template <class T>
 __global__ void k_nl_bounds(NlDev<T> a) {
-  const int f = blockIdx.x;
-  __shared__ T smin[3][kNlBlock];
-  T m[3] = {T(1e30), T(1e30), T(1e30)};
-  if (!a.periodic) {
-    for (int i = threadIdx.x; i < a.n; i += kNlBlock) {
-      const T* c = a.center + 3ll * ((long long)f * a.n + i);
-      for (int d = 0; d < 3; ++d) m[d] = c[d] < m[d] ? c[d] : m[d];
+  const int f = blockIdx.y;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+    const T* c = a.center + 3ll * ((long long)f * a.n + i);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double x = double(c[d]);
+      lo[d] = x < lo[d] ? x : lo[d];
+      hi[d] = x > hi[d] ? x : hi[d];
     }
   }
-  for (int d = 0; d < 3; ++d) smin[d][threadIdx.x] = m[d];
-  __syncthreads();
-  for (int s = kNlBlock / 2; s > 0; s >>= 1) {
-    if (threadIdx.x < s)
-      for (int d = 0; d < 3; ++d)
-        smin[d][threadIdx.x] = smin[d][threadIdx.x + s] < smin[d][threadIdx.x] ? smin[d][threadIdx.x + s] : smin[d][threadIdx.x];
-    __syncthreads();
-  }
-  if (threadIdx.x < 3) {
-    const int d = threadIdx.x;
-    if (a.periodic) {
-      a.origin[3 * f + d] = T(0);
-      int nd = int(a.box[d] / a.cell);
-      if (nd < 3) nd = 1;  // fewer than 3 cells along a periodic axis: a single cell spanning it
-      if (nd > 1024) nd = 1024;
-      a.dims[3 * f + d] = nd;
-    } else {
-      a.origin[3 * f + d] = smin[d][0];
-      a.dims[3 * f + d] = 1024;  // open grid; coordinates beyond are clipped into the last cell
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double l = __shfl_xor_sync(0xffffffffu, lo[d], o), h = __shfl_xor_sync(0xffffffffu, hi[d], o);
+      lo[d] = l < lo[d] ? l : lo[d];
+      hi[d] = h > hi[d] ? h : hi[d];
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (lo[d] < 1e299) atomicMin(&a.bounds[6 * f + d], ord_encode(lo[d]));
+      if (hi[d] > -1e299) atomicMax(&a.bounds[6 * f + 3 + d], ord_encode(hi[d]));
     }
   }
 }
 
+// one thread per frame: grid dimensions
 template <class T>
-__device__ __forceinline__ void cell_coords(const NlDev<T>& a, int f, const T* c, int cc[3]) {
+__global__ void k_nl_grid(NlDev<T> a) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= a.n_frames) return;
+  NlGrid<T> g;
+  T ext[3];
   for (int d = 0; d < 3; ++d) {
-    const int nd = a.dims[3 * f + d];
-    T x = c[d] - a.origin[3 * f + d];
-    int ci;
     if (a.periodic) {
-      // positions may lie outside the primary image; cell width along this axis is box/nd >= cell
-      T s = fmod(x, a.box[d]);
-      if (s < T(0)) s += a.box[d];
-      ci = int(s / (a.box[d] / T(nd)));
-      if (ci >= nd) ci = nd - 1;
-      if (ci < 0) ci = 0;
+      g.origin[d] = T(0);
+      ext[d] = a.box[d];
     } else {
-      ci = int(x / a.cell);
-      if (ci < 0) ci = 0;
-      if (ci >= nd) ci = nd - 1;
+      const double l = ord_decode(a.bounds[6 * f + d]), h = ord_decode(a.bounds[6 * f + 3 + d]);
+      g.origin[d] = T(l);
+      ext[d] = T(h - l);
+      if (!(ext[d] >= T(0))) ext[d] = T(0);
     }
+  }
+  int S = 2;
+  T cs = a.cut * T(1.0001) / T(S);  // a hair wider than needed so rounding in the binning can never hide a pair
+  while (true) {
+    long long tot = 1;
+    for (int d = 0; d < 3; ++d) {
+      long long nd = a.periodic ? (long long)(ext[d] / cs) : (long long)(ext[d] / cs) + 1;
+      if (nd < 1) nd = 1;
+      if (a.periodic && nd < 2 * S + 1) nd = 1;  // too few cells along a periodic axis for the stencil: one cell spans it
+      if (nd > 1 << 20) nd = 1 << 20;
+      g.n[d] = int(nd);
+      tot *= nd;
+      if (tot > (1ll << 40)) tot = 1ll << 40;
+    }
+    if (tot <= a.cmax) {
+      g.ncell = int(tot);
+      break;
+    }
+    if (S > 1) {
+      S = 1;
+      cs = a.cut * T(1.0001);
+    } else {
+      cs *= T(1.26);
+    }
+  }
+  g.S = S;
+  for (int d = 0; d < 3; ++d) {
+    g.width[d] = a.periodic ? ext[d] / T(g.n[d]) : cs;
+    g.inv[d] = T(1) / g.width[d];
+  }
+  g._pad = 0;
+  a.grid[f] = g;
+}
+
+template <class T>
+__device__ __forceinline__ int cell_id(const NlDev<T>& a, const NlGrid<T>& g, const T* c, int cc[3]) {
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    T x = c[d] - g.origin[d];
+    if (a.periodic) {  // positions may lie outside the primary image
+      x = fmod(x, a.box[d]);
+      if (x < T(0)) x += a.box[d];
+    }
+    int ci = int(x * g.inv[d]);
+    ci = ci < 0 ? 0 : (ci >= g.n[d] ? g.n[d] - 1 : ci);
     cc[d] = ci;
   }
+  return cc[0] + g.n[0] * (cc[1] + g.n[1] * cc[2]);
 }
 
 template <class T>
 __global__ void k_nl_bin(NlDev<T> a) {
-  const int f = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.n * a.n_frames) return;
+  const int f = int(idx / a.n);
   int cc[3];
-  cell_coords(a, f, a.center + 3ll * ((long long)f * a.n + i), cc);
-  const uint32_t key = uint32_t(cc[0]) | (uint32_t(cc[1]) << 10) | (uint32_t(cc[2]) << 20);
-  a.key[(long long)f * a.n + i] = key;
-  const long long H = 1ll << a.hbits;
-  atomicAdd(&a.bstart[(long long)f * (H + 1) + bucket_of(key, a.hbits)], 1);
+  const int cid = cell_id(a, a.grid[f], a.center + 3 * idx, cc);
+  a.cell[idx] = cid;
+  atomicAdd(&a.cstart[(long long)f * a.cmax + cid], 1);
 }
 
-// exclusive scan of `len` int32 per segment, one block per segment; writes the total at [len]
-__global__ void k_seg_scan(int32_t* data, long long seg_stride, int len) {
+// ------------------------------------------------------------------------------------------------ multi-block scan
+// exclusive scan of data[0..n) in place; data[n] receives the total.  Three launches: local scans + block sums,
+// scan of the block sums (one block), add.
+__global__ void k_scan_local(int32_t* data, long long n, int32_t* sums) {
+  __shared__ int32_t swarp[8];
+  const long long base = (long long)blockIdx.x * kScanChunk + threadIdx.x * 8;
+  int32_t v[8];
+  int32_t t = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    v[k] = (base + k < n) ? data[base + k] : 0;
+    t += v[k];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int32_t x = t;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) swarp[warp] = x;
+  __syncthreads();
+  int32_t before = 0;
+  for (int w = 0; w < warp; ++w) before += swarp[w];
+  int32_t run = before + x - t;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (base + k < n) data[base + k] = run;
+    run += v[k];
+  }
+  if (threadIdx.x == 255) sums[blockIdx.x] = run;
+}
+__global__ void k_scan_sums(int32_t* sums, int nblocks) {
   __shared__ int32_t swarp[32];
   __shared__ int32_t carry;
-  int32_t* seg = data + (long long)blockIdx.x * seg_stride;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int base = 0; base < len; base += blockDim.x) {
+  for (int base = 0; base < nblocks; base += blockDim.x) {
     const int k = base + threadIdx.x;
-    const int32_t v = (k < len) ? seg[k] : 0;
+    const int32_t v = (k < nblocks) ? sums[k] : 0;
     int32_t x = v;
+#pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
       if (lane >= o) x += y;
@@ -155,6 +271,7 @@ __global__ void k_seg_scan(int32_t* data, long long seg_stride, int len) {
     __syncthreads();
     if (warp == 0) {
       int32_t w = (lane < nw) ? swarp[lane] : 0;
+#pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int32_t y = __shfl_up_sync(0xffffffffu, w, o);
         if (lane >= o) w += y;
@@ -163,45 +280,57 @@ __global__ void k_seg_scan(int32_t* data, long long seg_stride, int len) {
     }
     __syncthreads();
     const int32_t before = carry + (warp ? swarp[warp - 1] : 0);
-    if (k < len) seg[k] = before + x - v;
+    if (k < nblocks) sums[k] = before + x - v;
     __syncthreads();
     if (threadIdx.x == 0) carry += swarp[nw - 1];
     __syncthreads();
   }
-  if (threadIdx.x == 0) seg[len] = carry;
+  if (threadIdx.x == 0) sums[nblocks] = carry;
+}
+__global__ void k_scan_add(int32_t* data, long long n, const int32_t* sums, int nblocks) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) data[k] += sums[k / kScanChunk];
+  if (k == 0) data[n] = sums[nblocks];
+}
+static void scan_exclusive(cudaStream_t s, int32_t* data, long long n, int32_t* tmp) {
+  const int nblocks = int((n + kScanChunk - 1) / kScanChunk);
+  k_scan_local<<<nblocks, 256, 0, s>>>(data, n, tmp);
+  k_scan_sums<<<1, 1024, 0, s>>>(tmp, nblocks);
+  k_scan_add<<<ceil_div(n, 256), 256, 0, s>>>(data, n, tmp, nblocks);
 }
 
+// ------------------------------------------------------------------------------------------------ cell order
 template <class T>
 __global__ void k_nl_scatter(NlDev<T> a) {
-  const int f = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
-  const long long H = 1ll << a.hbits;
-  const uint32_t b = bucket_of(a.key[(long long)f * a.n + i], a.hbits);
-  const int pos = atomicAdd(&a.cursor[(long long)f * H + b], 1);
-  a.order[(long long)f * a.n + a.bstart[(long long)f * (H + 1) + b] + pos] = i;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.n * a.n_frames) return;
+  const int f = int(idx / a.n);
+  const long long c = (long long)f * a.cmax + a.cell[idx];
+  const int pos = a.cstart[c] + atomicAdd(&a.cursor[c], 1);
+  a.tmp_order[pos] = int(idx - (long long)f * a.n);
 }
 
+// rank inside the cell by id (members of a cell: a few to a few dozen), write the sorted copies
 template <class T>
-__global__ void k_nl_sort_buckets(NlDev<T> a) {
-  const int f = blockIdx.y;
-  const long long H = 1ll << a.hbits;
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= H) return;
-  const int32_t* bs = a.bstart + (long long)f * (H + 1);
-  int32_t* o = a.order + (long long)f * a.n;
-  const int lo = bs[b], hi = bs[b + 1];
-  for (int p = lo + 1; p < hi; ++p) {
-    const int v = o[p];
-    int q = p - 1;
-    while (q >= lo && o[q] > v) {
-      o[q + 1] = o[q];
-      --q;
-    }
-    o[q + 1] = v;
-  }
+__global__ void k_nl_rank(NlDev<T> a) {
+  const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= (long long)a.n * a.n_frames) return;
+  const int f = int(pos / a.n);
+  const int id = a.tmp_order[pos];
+  const long long c = (long long)f * a.cmax + a.cell[(long long)f * a.n + id];
+  const int lo = a.cstart[c], hi = a.cstart[c + 1];
+  int rank = 0;
+  for (int q = lo; q < hi; ++q) rank += a.tmp_order[q] < id;
+  const T* ctr = a.center + 3 * ((long long)f * a.n + id);
+  NlRec<T> r{};
+  r.x = ctr[0];
+  r.y = ctr[1];
+  r.z = ctr[2];
+  r.id = id;
+  a.srec[lo + rank] = r;
 }
 
+// ------------------------------------------------------------------------------------------------ walk
 template <class T>
 __device__ __forceinline__ T wrap_nl(T d, T L) {
   T s = fmod(d + T(0.5) * L, L);
@@ -213,71 +342,120 @@ __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
 
-template <class T, bool FILL>
-__global__ void k_nl_walk(NlDev<T> a) {
-  const int f = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
-  const long long fb = (long long)f * a.n;
-  const long long H = 1ll << a.hbits;
-  const T* ci = a.center + 3 * (fb + i);
-  const T xi = ci[0], yi = ci[1], zi = ci[2];
-  const uint32_t mykey = a.key[fb + i];
-  const int cx = mykey & 1023, cy = (mykey >> 10) & 1023, cz = (mykey >> 20) & 1023;
-  const int nx = a.dims[3 * f], ny = a.dims[3 * f + 1], nz = a.dims[3 * f + 2];
+// MODE 0: count, 1: fill (compact list), 2: rows (one pass: fixed-width row per nucleotide, slot-major)
+template <class T, int MODE, bool PERIODIC>
+__global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
+  constexpr bool FILL = MODE == 1, ROWS = MODE == 2;
+  const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= (long long)a.n * a.n_frames) return;
+  const int f = int(pos / a.n);
+  const NlGrid<T> g = a.grid[f];
+  const NlRec<T> me = a.srec[pos];
+  const int i = me.id;
+  const T xi = me.x, yi = me.y, zi = me.z;
+  int cc[3];
+  {
+    const T c[3] = {xi, yi, zi};
+    cell_id(a, g, c, cc);
+  }
+  const int32_t* cs = a.cstart + (long long)f * a.cmax;
   int ex[kMaxExcl];
+#pragma unroll
   for (int s = 0; s < kMaxExcl; ++s) ex[s] = a.excl[i * kMaxExcl + s];
-  const int32_t* bs = a.bstart + f * (H + 1);
-  const int32_t* ord = a.order + fb;
   int found = 0;
   long long wpos = 0;
   int32_t* out0 = nullptr;
   int32_t* out1 = nullptr;
   if (FILL) {
-    wpos = a.nbcount[(long long)f * (a.n + 1) + i];
+    wpos = a.nbcount[pos] - a.nbcount[(long long)f * a.n];
     out0 = a.pairs + (long long)f * 2 * a.capacity;
     out1 = out0 + a.capacity;
   }
-  // half shell: offsets (dx,dy,dz) that are lexicographically >= 0 in (dz,dy,dx) order
-  for (int dz = 0; dz <= 1; ++dz) {
-    for (int dy = (dz ? -1 : 0); dy <= 1; ++dy) {
-      for (int dx = ((dz || dy) ? -1 : 0); dx <= 1; ++dx) {
-        int ox = cx + dx, oy = cy + dy, oz = cz + dz;
-        if (a.periodic) {
-          if ((nx == 1 && dx) || (ny == 1 && dy) || (nz == 1 && dz)) continue;
-          ox = (ox + nx) % nx;
-          oy = (oy + ny) % ny;
-          oz = (oz + nz) % nz;
-        } else if (ox < 0 || oy < 0 || oz < 0 || ox >= nx || oy >= ny || oz >= nz) {
-          continue;
+  // rows mode: slot k of the nucleotide at cell-order position p (within its frame) is entry k * N + p, so that the
+  // lanes of a warp, which advance through their slots at about the same pace, write neighbouring addresses
+  const int row_width = ROWS ? int(a.capacity / a.n) : 0;
+  if (ROWS) {
+    out0 = a.pairs + (long long)f * 2 * a.capacity + (pos - (long long)f * a.n);
+    out1 = out0 + a.capacity;
+  }
+  const int S = g.S, n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+  const int n_rows = 1 + S + S * (2 * S + 1);
+  for (int row = 0; row < n_rows; ++row) {
+    int dy = row, dz = 0;
+    if (row > S) {
+      const int k = row - S - 1;
+      dz = 1 + k / (2 * S + 1);
+      dy = k % (2 * S + 1) - S;
+    }
+    int by = cc[1] + dy, bz = cc[2] + dz;
+    if (PERIODIC) {
+      if ((n1 == 1 && dy) || (n2 == 1 && dz)) continue;
+      by = by < 0 ? by + n1 : (by >= n1 ? by - n1 : by);
+      bz = bz < 0 ? bz + n2 : (bz >= n2 ? bz - n2 : bz);
+    } else if (by < 0 || bz < 0 || by >= n1 || bz >= n2) {
+      continue;
+    }
+    const int rowbase = n0 * (by + n1 * bz);
+    int xlo = (row == 0) ? cc[0] : cc[0] - S, xhi = cc[0] + S;
+    // up to two runs of the sorted arrays (a periodic x wraps)
+    int rs[2] = {0, 0}, re[2] = {0, 0};
+    if (PERIODIC && n0 > 1) {
+      if (xlo < 0) {
+        rs[1] = cs[rowbase + n0 + xlo];
+        re[1] = cs[rowbase + n0];
+        xlo = 0;
+      } else if (xhi >= n0) {
+        rs[1] = cs[rowbase];
+        re[1] = cs[rowbase + xhi - n0 + 1];
+        xhi = n0 - 1;
+      }
+    } else {
+      xlo = xlo < 0 ? 0 : xlo;
+      xhi = xhi >= n0 ? n0 - 1 : xhi;
+      if (PERIODIC) xlo = xhi = cc[0];
+    }
+    rs[0] = cs[rowbase + xlo];
+    re[0] = cs[rowbase + xhi + 1];
+    if (row == 0) rs[0] = int(pos) + 1 > rs[0] ? int(pos) + 1 : rs[0];  // own cell: ids ascend, partners come after
+#pragma unroll
+    for (int run = 0; run < 2; ++run) {
+      for (int q0 = rs[run]; q0 < re[run]; q0 += kNlUnroll) {
+        NlRec<T> c[kNlUnroll];
+#pragma unroll
+        for (int u = 0; u < kNlUnroll; ++u) {  // independent 128-bit loads first, tests after
+          const int q = q0 + u < re[run] ? q0 + u : re[run] - 1;
+          c[u] = a.srec[q];
         }
-        const bool own = !(dx || dy || dz);
-        const uint32_t nkey = uint32_t(ox) | (uint32_t(oy) << 10) | (uint32_t(oz) << 20);
-        const uint32_t b = bucket_of(nkey, a.hbits);
-        const int lo = bs[b], hi = bs[b + 1];
-        for (int p = lo; p < hi; ++p) {
-          const int j = ord[p];
-          if (a.key[fb + j] != nkey) continue;
-          if (own && j <= i) continue;
-          if (j == ex[0] || j == ex[1] || j == ex[2] || j == ex[3]) continue;
-          const int lo_i = i < j ? i : j, hi_j = i < j ? j : i;
-          // receiver = lower index, as the OrderedSparse format keeps i < j
-          const T* cl = (lo_i == i) ? ci : a.center + 3 * (fb + j);
-          const T* ch = (lo_i == i) ? a.center + 3 * (fb + j) : ci;
-          T ddx = cl[0] - ch[0], ddy = cl[1] - ch[1], ddz = cl[2] - ch[2];
-          if (a.periodic) {
+#pragma unroll
+        for (int u = 0; u < kNlUnroll; ++u) {
+          const int j = c[u].id;
+          // receiver = lower index (OrderedSparse keeps i < j): dR = R_low - R_high, as the reference evaluates it
+          const bool me_low = i < j;
+          // (in free space the two orders give exact negatives, whose squares are identical: no selects needed)
+          T ddx = xi - c[u].x, ddy = yi - c[u].y, ddz = zi - c[u].z;
+          if (PERIODIC) {
+            if (!me_low) {
+              ddx = c[u].x - xi;
+              ddy = c[u].y - yi;
+              ddz = c[u].z - zi;
+            }
             ddx = wrap_nl(ddx, a.box[0]);
             ddy = wrap_nl(ddy, a.box[1]);
             ddz = wrap_nl(ddz, a.box[2]);
           }
           const T d2 = add_rn(add_rn(mul_rn(ddx, ddx), mul_rn(ddy, ddy)), mul_rn(ddz, ddz));
-          if (d2 < a.cut2) {
+          const bool ok = q0 + u < re[run] && d2 < a.cut2 && j != ex[0] && j != ex[1] && j != ex[2] && j != ex[3];
+          if (ok) {
             if (FILL) {
               if (wpos < a.capacity) {
-                out0[wpos] = lo_i;
-                out1[wpos] = hi_j;
+                out0[wpos] = me_low ? i : j;
+                out1[wpos] = me_low ? j : i;
               }
               ++wpos;
+            }
+            if (ROWS && found < row_width) {
+              out0[(long long)found * a.n] = me_low ? i : j;
+              out1[(long long)found * a.n] = me_low ? j : i;
             }
             ++found;
           }
@@ -285,17 +463,60 @@ __global__ void k_nl_walk(NlDev<T> a) {
       }
     }
   }
-  (void)xi;
-  (void)yi;
-  (void)zi;
-  if (!FILL) a.nbcount[(long long)f * (a.n + 1) + i] = found;
+  if (MODE == 0) a.nbcount[pos] = found;
+  if (ROWS) {
+    for (int k = found; k < row_width; ++k) {  // unused slots carry the padding value N, as the tail of a compact list
+      out0[(long long)k * a.n] = a.n;
+      out1[(long long)k * a.n] = a.n;
+    }
+    if (found > row_width) atomicOr(a.overflow, 1);
+    // per-frame totals and the longest row (so that the caller can size the rows), one atomic per warp where possible
+    int tot = found, mx = found;
+    const unsigned am = __activemask();
+    const int f0 = __shfl_sync(am, f, __ffs(am) - 1);
+    const bool uniform = am == 0xffffffffu && __all_sync(am, f == f0);
+    if (uniform) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        const int m = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = m > mx ? m : mx;
+      }
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&a.count[f], tot);
+        if (a.max_row) atomicMax(&a.max_row[f], mx);
+      }
+    } else {
+      atomicAdd(&a.count[f], found);
+      if (a.max_row) atomicMax(&a.max_row[f], found);
+    }
+  }
+}
+
+// rows mode: entries beyond N * row_width (capacity not a multiple of N) are padding
+template <class T>
+__global__ void k_nl_rows_tail(NlDev<T> a) {
+  const int f = blockIdx.y;
+  const long long first = (long long)(a.capacity / a.n) * a.n;
+  int32_t* out0 = a.pairs + (long long)f * 2 * a.capacity;
+  for (long long k = first + blockIdx.x * blockDim.x + threadIdx.x; k < a.capacity; k += (long long)gridDim.x * blockDim.x) {
+    out0[k] = a.n;
+    out0[a.capacity + k] = a.n;
+  }
+}
+__global__ void k_nl_zero_counts(int32_t* count, int32_t* max_row, int n_frames) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_frames) {
+    count[k] = 0;
+    if (max_row) max_row[k] = 0;
+  }
 }
 
 template <class T>
 __global__ void k_nl_finish(NlDev<T> a) {
   // pad the tail with N and publish count / overflow
   const int f = blockIdx.y;
-  const int total = a.nbcount[(long long)f * (a.n + 1) + a.n];
+  const int total = a.nbcount[(long long)(f + 1) * a.n] - a.nbcount[(long long)f * a.n];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.count[f] = total;
     if (total > a.capacity) atomicOr(a.overflow, 1);
@@ -309,16 +530,17 @@ __global__ void k_nl_finish(NlDev<T> a) {
   }
 }
 
-static int hash_bits(int n) {
-  int b = 5;
-  while ((1ll << b) < 2ll * n && b < 24) ++b;
-  return b;
+static int cells_per_frame(int n) {
+  long long c = 2ll * n;
+  if (c < 4096) c = 4096;
+  if (c > (1 << 22)) c = 1 << 22;
+  return int(c);
 }
 static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 
 template <class T>
 static size_t carve(NlDev<T>* a, void* ws, int n, int F) {
-  const size_t H = size_t(1) << hash_bits(n);
+  const size_t C = (size_t)cells_per_frame(n), R = (size_t)F * n;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     void* p = ws ? static_cast<char*>(ws) + off : nullptr;
@@ -328,20 +550,25 @@ static size_t carve(NlDev<T>* a, void* ws, int n, int F) {
   void* p;
   p = take(sizeof(int32_t) * n * kMaxExcl);
   if (a) a->excl = static_cast<int32_t*>(p);
-  p = take(sizeof(double) * 3 * F);
-  if (a) a->origin = static_cast<T*>(p);
-  p = take(sizeof(int32_t) * 3 * F);
-  if (a) a->dims = static_cast<int32_t*>(p);
-  p = take(sizeof(uint32_t) * (size_t)F * n);
-  if (a) a->key = static_cast<uint32_t*>(p);
-  p = take(sizeof(int32_t) * (size_t)F * (H + 1));
-  if (a) a->bstart = static_cast<int32_t*>(p);
-  p = take(sizeof(int32_t) * (size_t)F * H);
+  p = take(sizeof(unsigned long long) * 6 * F);
+  if (a) a->bounds = static_cast<unsigned long long*>(p);
+  p = take(sizeof(NlGrid<double>) * F);
+  if (a) a->grid = static_cast<NlGrid<T>*>(p);
+  p = take(sizeof(int32_t) * R);
+  if (a) a->cell = static_cast<int32_t*>(p);
+  p = take(sizeof(int32_t) * (F * C + 1));
+  if (a) a->cstart = static_cast<int32_t*>(p);
+  p = take(sizeof(int32_t) * F * C);
   if (a) a->cursor = static_cast<int32_t*>(p);
-  p = take(sizeof(int32_t) * (size_t)F * n);
-  if (a) a->order = static_cast<int32_t*>(p);
-  p = take(sizeof(int32_t) * (size_t)F * (n + 1));
+  p = take(sizeof(int32_t) * R);
+  if (a) a->tmp_order = static_cast<int32_t*>(p);
+  p = take(sizeof(NlRec<double>) * R);
+  if (a) a->srec = static_cast<NlRec<T>*>(p);
+  p = take(sizeof(int32_t) * (R + 1));
   if (a) a->nbcount = static_cast<int32_t*>(p);
+  const size_t longest = (F * C + 1 > R + 1) ? F * C + 1 : R + 1;
+  p = take(sizeof(int32_t) * (longest / kScanChunk + 2));
+  if (a) a->scan_tmp = static_cast<int32_t*>(p);
   return off;
 }
 
@@ -349,6 +576,7 @@ template <class T>
 static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
   MB_REQUIRE(x, MB_EINVAL_SHAPE, "nl_build: null args");
   MB_REQUIRE(x->n > 0 && x->n_frames > 0 && x->n_frames <= 65535, MB_EINVAL_SHAPE, "nl_build: bad n / n_frames");
+  MB_REQUIRE((long long)x->n * x->n_frames < (1ll << 31) - 4096, MB_EINVAL_SHAPE, "nl_build: n * n_frames must fit in 31 bits");
   MB_REQUIRE(x->center && x->pairs && x->count && x->overflow, MB_EINVAL_SHAPE, "nl_build: missing buffers");
   MB_REQUIRE(x->n_bonded == 0 || x->bonded, MB_EINVAL_SHAPE, "nl_build: bonded list missing");
   MB_REQUIRE(x->capacity > 0, MB_EINVAL_SHAPE, "nl_build: capacity must be positive");
@@ -362,39 +590,54 @@ static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
   a.n = x->n;
   a.n_frames = x->n_frames;
   a.n_bonded = x->n_bonded;
-  a.hbits = hash_bits(x->n);
+  a.cmax = cells_per_frame(x->n);
   a.center = static_cast<const T*>(x->center);
   a.bonded = x->bonded;
   for (int d = 0; d < 3; ++d) a.box[d] = T(x->box[d]);
   a.periodic = periodic;
-  const T cut = T(x->r_cutoff) + T(x->dr_threshold);
-  a.cut2 = cut * cut;
-  a.cell = cut * T(1.0001);  // a hair wider than the cutoff so rounding in the binning can never hide a pair
+  a.cut = T(x->r_cutoff) + T(x->dr_threshold);
+  a.cut2 = a.cut * a.cut;
   a.pairs = x->pairs;
   a.capacity = x->capacity;
   a.count = x->count;
   a.overflow = x->overflow;
+  a.max_row = (x->flags & MB_NL_ROWS) ? x->max_row : nullptr;
+  MB_REQUIRE(!(x->flags & MB_NL_ROWS) || x->capacity >= x->n, MB_EINVAL_SHAPE, "nl_build: rows mode needs capacity >= n");
   carve<T>(&a, x->workspace, x->n, x->n_frames);
 
-  const long long H = 1ll << a.hbits;
   const int F = x->n_frames, n = x->n;
-  MB_CUDA_CHECK(cudaMemsetAsync(a.bstart, 0, sizeof(int32_t) * (size_t)F * (H + 1), s));
-  MB_CUDA_CHECK(cudaMemsetAsync(a.cursor, 0, sizeof(int32_t) * (size_t)F * H, s));
+  const long long R = (long long)F * n, FC = (long long)F * a.cmax;
+  MB_CUDA_CHECK(cudaMemsetAsync(a.cstart, 0, sizeof(int32_t) * (size_t)(FC + 1), s));
+  MB_CUDA_CHECK(cudaMemsetAsync(a.cursor, 0, sizeof(int32_t) * (size_t)FC, s));
   k_nl_excl_init<<<ceil_div((long long)n * kMaxExcl, 256), 256, 0, s>>>(a.excl, n);
   if (x->n_bonded > 0)
     k_nl_excl_fill<<<ceil_div(x->n_bonded, 256), 256, 0, s>>>(a.excl, a.bonded, x->n_bonded, n, a.overflow);
-  k_nl_bounds<T><<<F, kNlBlock, 0, s>>>(a);
-  dim3 gp(ceil_div(n, kNlBlock), F);
-  k_nl_bin<T><<<gp, kNlBlock, 0, s>>>(a);
-  k_seg_scan<<<F, 1024, 0, s>>>(a.bstart, H + 1, (int)H);
-  k_nl_scatter<T><<<gp, kNlBlock, 0, s>>>(a);
-  dim3 gb(ceil_div(H, kNlBlock), F);
-  k_nl_sort_buckets<T><<<gb, kNlBlock, 0, s>>>(a);
-  k_nl_walk<T, false><<<gp, kNlBlock, 0, s>>>(a);
-  k_seg_scan<<<F, 1024, 0, s>>>(a.nbcount, n + 1, n);
-  k_nl_walk<T, true><<<gp, kNlBlock, 0, s>>>(a);
-  dim3 gf(min(ceil_div(x->capacity, 256), 1024), F);
-  k_nl_finish<T><<<gf, 256, 0, s>>>(a);
+  if (!periodic) {
+    k_nl_bounds_init<<<ceil_div(6ll * F, 256), 256, 0, s>>>(a.bounds, F);
+    int bx = ceil_div(n, 256 * 4);
+    if (bx > 64) bx = 64;
+    k_nl_bounds<T><<<dim3(bx, F), 256, 0, s>>>(a);
+  }
+  k_nl_grid<T><<<ceil_div(F, 128), 128, 0, s>>>(a);
+  const int gr = ceil_div(R, kNlBlock);
+  k_nl_bin<T><<<gr, kNlBlock, 0, s>>>(a);
+  scan_exclusive(s, a.cstart, FC, a.scan_tmp);
+  k_nl_scatter<T><<<gr, kNlBlock, 0, s>>>(a);
+  k_nl_rank<T><<<gr, kNlBlock, 0, s>>>(a);
+  if (x->flags & MB_NL_ROWS) {
+    k_nl_zero_counts<<<ceil_div(F, 256), 256, 0, s>>>(a.count, a.max_row, F);
+    if (periodic) k_nl_walk<T, 2, true><<<gr, kNlBlock, 0, s>>>(a);
+    else k_nl_walk<T, 2, false><<<gr, kNlBlock, 0, s>>>(a);
+    if (x->capacity % n) k_nl_rows_tail<T><<<dim3(1, F), 256, 0, s>>>(a);
+  } else {
+    if (periodic) k_nl_walk<T, 0, true><<<gr, kNlBlock, 0, s>>>(a);
+    else k_nl_walk<T, 0, false><<<gr, kNlBlock, 0, s>>>(a);
+    scan_exclusive(s, a.nbcount, R, a.scan_tmp);
+    if (periodic) k_nl_walk<T, 1, true><<<gr, kNlBlock, 0, s>>>(a);
+    else k_nl_walk<T, 1, false><<<gr, kNlBlock, 0, s>>>(a);
+    dim3 gf(min(ceil_div(x->capacity, 256), 1024), F);
+    k_nl_finish<T><<<gf, 256, 0, s>>>(a);
+  }
   MB_CUDA_CHECK(cudaGetLastError());
   return MB_OK;
 }

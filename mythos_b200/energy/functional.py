@@ -167,7 +167,7 @@ class CellListPairs:
     capacity: int = 0  # 0 = size from the first frame
     workspace: torch.Tensor | None = None
     max_count: int = 0
-    use_lists: bool = False  # True once the frame-resident all-pairs mode was found not to apply
+    in_kernel: bool = False  # True: let the frame-resident kernel find the pairs itself (in-kernel cell list) where it applies
     _pending: list = dc.field(default_factory=list)
 
     def chunk(self, sl: slice, center: torch.Tensor):
@@ -177,7 +177,7 @@ class CellListPairs:
         c = center.detach()
         if self.capacity <= 0:
             _, count, _, self.workspace = neighbors.build_pairs(c[:1], self.bonded, self.box, self.r_cutoff, 0.0, 1, self.workspace)
-            self.capacity = max(int(int(count.max().item()) * 1.15) + 64, 64)
+            self.capacity = max(int(int(count.max().item()) * 1.06) + 64, 64)
         pairs, count, overflow, self.workspace = neighbors.build_pairs(
             c, self.bonded, self.box, self.r_cutoff, 0.0, self.capacity, self.workspace
         )
@@ -196,11 +196,11 @@ class CellListPairs:
         self.max_count = max(self.max_count, worst)
         if worst <= self.capacity:
             return True
-        self.capacity = int(worst * 1.15) + 64  # jax_md would report did_buffer_overflow; here the pass re-runs
+        self.capacity = int(worst * 1.06) + 64  # jax_md would report did_buffer_overflow; here the pass re-runs
         return False
 
 
-FRAME_CHUNK = 512  # frames per launch group: keeps a chunk's pair lists (~90 MB at N=2k) inside the 126 MB L2
+FRAME_CHUNK = 1184  # frames per launch group (8 waves of one CTA per SM); bounds the pair-list buffer (~1.2 GB at N=2k)
 
 
 def _chunks(n_frames: int, source) -> list[slice]:
@@ -210,7 +210,7 @@ def _chunks(n_frames: int, source) -> list[slice]:
 
 def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, want_pos, want_par, per_frame_par, flags=0):
     """Chunked launch over frames; concatenates / sums the per-chunk outputs."""
-    if isinstance(source, CellListPairs) and not want_pos and model.n_banks == 1 and not source.use_lists and not (flags & _lib.FLAG_GENERIC_KERNEL):
+    if isinstance(source, CellListPairs) and not want_pos and model.n_banks == 1 and source.in_kernel and not (flags & _lib.FLAG_GENERIC_KERNEL):
         # all-pairs mode inside the frame-resident kernel: the CTA finds its own pairs, no list in HBM
         try:
             outs = [
@@ -222,7 +222,7 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
         except _lib.MythosB200Error as err:
             if getattr(err, "status", None) != 3:  # MB_ECAPACITY: frame too large for shared memory -> device lists
                 raise
-            source.use_lists = True
+            source.in_kernel = False
     while True:
         outs = []
         for sl in _chunks(center.shape[0], source):

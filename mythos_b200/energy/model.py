@@ -153,11 +153,13 @@ class Plan:
 
         if isinstance(ub, AllPairs):
             box = tuple(self.model.box)
-            src = functional.CellListPairs(bonded=topo.bonded, box=box, r_cutoff=interaction_range(self))
+            # per-frame device lists (one-pass rows layout) streamed through the energy kernels; the frame-resident
+            # kernel can also find its pairs itself (src.in_kernel = True), which measured slower on B200
+            in_kernel = getattr(ub, "in_kernel", False)
             # the in-kernel cell list keeps 2 bonded partners per nucleotide (like the reference's (N,2) mask)
-            if topo.bonded.numel() and int(torch.bincount(topo.bonded.reshape(-1).long()).max()) > 2:
-                src.use_lists = True
-            return src
+            if in_kernel and topo.bonded.numel() and int(torch.bincount(topo.bonded.reshape(-1).long()).max()) > 2:
+                in_kernel = False
+            return functional.CellListPairs(bonded=topo.bonded, box=box, r_cutoff=interaction_range(self), in_kernel=in_kernel)
         return functional.StaticPairs(device_pairs(ub, device))
 
     def evaluate(self, center: torch.Tensor, quat: torch.Tensor) -> torch.Tensor:

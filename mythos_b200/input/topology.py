@@ -34,8 +34,11 @@ class AllPairs:
     unbonded terms over per-frame device cell lists at the interaction range of their parameters -- the same
     energies, since every unbonded term has compact support."""
 
-    def __init__(self, n: int):
+    def __init__(self, n: int, in_kernel: bool = False):
         self.n = int(n)
+        # True: where the frame-resident kernel applies, let it find the pairs itself (shared-memory cell list) instead
+        # of streaming device lists through it
+        self.in_kernel = bool(in_kernel)
 
     @property
     def T(self) -> "AllPairs":  # noqa: N802 - BaseEnergyFunction stores topology.unbonded_neighbors.T

@@ -29,8 +29,13 @@ def build_pairs(
     dr_threshold: float,
     capacity: int,
     workspace: torch.Tensor | None = None,
+    rows: bool = False,
+    max_row: torch.Tensor | None = None,
 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Raw batched build.  center (F,N,3) on the device -> (pairs (F,2,capacity) int32, count (F,), overflow (1,), workspace)."""
+    """Raw batched build.  center (F,N,3) on the device -> (pairs (F,2,capacity) int32, count (F,), overflow (1,), workspace).
+
+    ``rows=True`` is the one-pass layout (``MB_NL_ROWS``): fixed-width rows per nucleotide, unused slots = N; pass a
+    ``max_row`` (F,) int32 tensor to receive the longest row of each frame."""
     _lib.require_cuda(center, "center")
     if center.dim() != 3:
         raise _lib.MythosB200Error("center must be (F,N,3)")
@@ -55,6 +60,8 @@ def build_pairs(
     a.pairs, a.capacity = pairs.data_ptr(), capacity
     a.count, a.overflow = count.data_ptr(), overflow.data_ptr()
     a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
+    a.flags = _lib.NL_ROWS if rows else 0
+    a.max_row = max_row.data_ptr() if (rows and max_row is not None) else None
     fn = getattr(_lib.lib(), f"mythos_b200_nl_build_{_lib.suffix(center.dtype)}")
     with torch.cuda.device(dev):
         _lib.check(fn(_lib.current_stream(dev), C.byref(a)), "mythos_b200_nl_build")

@@ -158,11 +158,11 @@ def test_frame_resident_kernel_equals_pair_kernel(workload, dtype):
     params = plan.device_params(cd.device, dtype)
     cot = torch.tensor(np.random.default_rng(1).uniform(0.5, 1.5, size=(len(c), 8)), device=DEV, dtype=dtype)
     outs = []
-    for flags, use_lists in ((0, False), (_lib.FLAG_GENERIC_KERNEL, False), (0, True)):
-        # 0/False: frame kernel finds its own pairs (shared-memory cell list); GENERIC: device lists + pair kernels;
-        # 0/True: device lists streamed through the frame kernel
+    for flags, in_kernel in ((0, True), (_lib.FLAG_GENERIC_KERNEL, False), (0, False)):
+        # 0/True: frame kernel finds its own pairs (shared-memory cell list); GENERIC: device lists + pair kernels;
+        # 0/False: device lists (rows layout) streamed through the frame kernel (the default)
         src = plan.pairs(cd.device, topo)
-        src.use_lists = use_lists
+        src.in_kernel = in_kernel
         terms, _, _, J = functional.energy_and_gradients(plan.model, topo, cd, qd, params, src, cot=cot, want_pos_grad=False,
                                                          want_param_grad=True, per_frame_param_grad=True, flags=flags)
         outs.append((terms.cpu().numpy(), J.cpu().numpy()))
@@ -173,10 +173,12 @@ def test_frame_resident_kernel_equals_pair_kernel(workload, dtype):
     np.testing.assert_allclose(outs[2][1], outs[1][1], rtol=tol, atol=tol * np.abs(outs[1][1]).max())
 
 
+@pytest.mark.parametrize("in_kernel", [False, True])
 @pytest.mark.parametrize("box", [None, 9.0, 30.0])
-def test_all_pairs_sentinel_equals_explicit_all_pairs_list(box):
-    """AllPairs (in-kernel cell list at the interaction range) == the reference's explicit N(N-1)/2 list, in free space
-    and in periodic boxes (a 9.0 box is smaller than 3 cells along each axis: single-cell axes)."""
+def test_all_pairs_sentinel_equals_explicit_all_pairs_list(box, in_kernel):
+    """AllPairs (device cell lists, or the in-kernel cell list, at the interaction range) == the reference's explicit
+    N(N-1)/2 list, in free space and in periodic boxes (a 9.0 box is smaller than the stencil along each axis:
+    single-cell axes)."""
     from mythos_b200 import space
     from mythos_b200.input.topology import AllPairs
 
@@ -187,5 +189,5 @@ def test_all_pairs_sentinel_equals_explicit_all_pairs_list(box):
     c, q = synthetic.rejittered_frames(s, 5, seed0=77)
     states = RigidBody(torch.tensor(c, device=DEV), Quaternion(torch.tensor(q, device=DEV)))
     want = efn.compute_terms_frames(states)
-    got = efn.with_props(unbonded_neighbors=AllPairs(top.n_nucleotides)).compute_terms_frames(states)
+    got = efn.with_props(unbonded_neighbors=AllPairs(top.n_nucleotides, in_kernel=in_kernel)).compute_terms_frames(states)
     np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-10, atol=1e-10)

@@ -69,6 +69,27 @@ def test_pair_set_bit_exact(dtype, periodic, cutoff):
         assert int(count[f]) == len(want)
 
 
+@pytest.mark.parametrize("periodic", [False, True])
+def test_rows_layout_same_pair_set(periodic):
+    """MB_NL_ROWS (one pass, fixed-width rows, unused slots = N) holds the same pair set as the compact list, reports the
+    longest row, and flags rows that are too narrow."""
+    s = synthetic.assembly(6, seed=3)
+    box = (9.5, 8.0, 26.0) if periodic else (0.0, 0.0, 0.0)
+    c = torch.tensor(np.stack([s.center, s.center + 0.3]), device=DEV)
+    bonded = torch.tensor(s.topology.bonded_neighbors)
+    n = s.center.shape[0]
+    pairs, count, overflow, ws = neighbors.build_pairs(c, bonded, box, 3.0, 0.2, 60000)
+    mr = torch.zeros((2,), dtype=torch.int32, device=DEV)
+    rows, rcount, rov, ws = neighbors.build_pairs(c, bonded, box, 3.0, 0.2, 128 * n + 17, rows=True, max_row=mr)
+    assert int(rov.item()) == 0 and torch.equal(rcount, count)
+    for f in range(2):
+        assert to_set(rows[f], n) == to_set(pairs[f], n)
+    width = int(mr.max().item())
+    assert 0 < width <= 128
+    _, _, rov2, _ = neighbors.build_pairs(c, bonded, box, 3.0, 0.2, (width - 1) * n, rows=True, max_row=mr)
+    assert int(rov2.item()) & 1
+
+
 def test_capacity_overflow_is_reported_and_list_truncated():
     s = synthetic.assembly(2, seed=1)
     c = torch.tensor(s.center[None], device=DEV)

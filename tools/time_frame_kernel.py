@@ -33,4 +33,10 @@ for wp in (True, False):
     pairs, count, ov, ws = neighbors.build_pairs(cd, topo.bonded, (0, 0, 0), cut, 0.0, 100000)
     t_nl, _ = timeit(lambda: neighbors.build_pairs(cd, topo.bonded, (0, 0, 0), cut, 0.0, 100000, ws))
     t_list, o2 = timeit(lambda: functional._launch(plan.model, topo, cd, qd, params, pairs, 2 * 100000, 0xFF, ones, True, False, wp, True, count))
+    K = 80
+    mr = torch.zeros((F,), dtype=torch.int32, device=dev)
+    rp, rcount, rov, ws = neighbors.build_pairs(cd, topo.bonded, (0, 0, 0), cut, 0.0, K * cd.shape[1], ws, rows=True, max_row=mr)
+    t_rows, _ = timeit(lambda: neighbors.build_pairs(cd, topo.bonded, (0, 0, 0), cut, 0.0, K * cd.shape[1], ws, rows=True, max_row=mr))
+    t_rlist, o3 = timeit(lambda: functional._launch(plan.model, topo, cd, qd, params, rp, 2 * K * cd.shape[1], 0xFF, ones, True, False, wp, True, None))
+    print(f"   rows mode (K={K}, longest row {int(mr.max())}, overflow {int(rov)}): nl {t_rows:.3f} ms + frame kernel {t_rlist:.3f} ms; max|dE| {float((o3[0]-o2[0]).abs().max()):.2e}")
     print(f"WP={wp} F={F}: in-kernel all-pairs {t_cell:.3f} ms | nl build {t_nl:.3f} ms + list mode {t_list:.3f} ms; max|dE| {float((o1[0]-o2[0]).abs().max()):.2e}")
