@@ -11,8 +11,10 @@ all-reduced over NCCL.
   value   frames/s with frames resident in HBM and the packed parameter bank on the device (CUDA events, max over ranks)
   e2e     frames/s through the public API ``compute_loss_and_grad`` with HOST (pinned) frame buffers: H2D of the frames,
           theta -> bank chain on the host, kernels, D2H of loss and gradients inside the timed region
-  roofline  dominant kernel (unbonded pairs, E + dE/dparams): algorithmic flop-equivalents / CUDA-event time vs the
-          FP64 FMA issue peak measured in this run by the library's micro-benchmark (and HBM bytes vs measured copy BW)
+  roofline  dominant kernel (k_frame_energy: all terms of a frame, E + dE/dparams, pair lists streamed from the per-frame
+          device neighbour build): algorithmic flop-equivalents / CUDA-event time vs the FP64 FMA issue peak measured in
+          this run by the library's micro-benchmark (and HBM bytes vs measured copy BW)
+  md / forces_8k / forces_100k   the other BASELINE configs that fit one GPU (configs[1], [2], [4]), N = 1 only
   cpu_baseline  the CPU oracle (port of the reference algorithm; the reference itself needs JAX, absent here) on a
           bounded sample of the same frames
 
@@ -156,6 +158,130 @@ def md_benchmark(dev, n_steps: int = 10000):
     return {"metric": "MD nucleotide-steps/s", "value": 120 * n_steps / (ms * 1e-3), "unit": "nucleotide-steps/s",
             "workload": "configs[1]: oxDNA1 Langevin MD, 60-bp duplex (N=120), 10^4 steps, all-pairs list (U=7021), float64",
             "ms_total": ms, "us_per_step": 1e3 * ms / n_steps, "final_energy_per_nt": e_last / 120}
+
+
+# Work model: SURVEY 8d's per-pair counts, split per term so that a term counts for a pair only
+# inside its radial support (flops / 2 + weighted specials = FMA-issue slots, float64):
+#   distance screen of a listed pair                         30 flop
+#   Debye-Hueckel (backbone sites inside r_cut)              65 flop + exp + div + sqrt
+#   excluded volume (centres inside the short-range cutoff)  200 flop + 4 div + 2 sqrt
+#   hydrogen bonding + cross stacking (base-site window)     330 flop + 6 acos + exp + sqrt + div
+#   coaxial stacking (stacking-site window)                  225 flop + 2 acos + sqrt + div
+# (sum over a pair inside every support = SURVEY's 820 flop + 8 acos + 2 exp + 5 sqrt + 7 div)
+SLOT_SCREEN = 30 / 2
+SLOT_DEBYE = 65 / 2 + 40 + 16 + 16
+SLOT_EXC = 200 / 2 + 4 * 16 + 2 * 16
+SLOT_HBCR = 330 / 2 + 6 * 70 + 40 + 16 + 16
+SLOT_COAX = 225 / 2 + 2 * 70 + 16 + 16
+
+
+def pair_support_counts(plan, center, quat, pairs, count):
+    """Per-frame means of: listed pairs, pairs inside the Debye support, the short-range centre cutoff, the
+    hydrogen-bond / cross-stacking window and the coaxial window -- measured on the device from (F,2,cap) lists."""
+    from mythos_b200 import _lib
+
+    names = {nm: k for k, nm in enumerate(_lib.param_names())}
+    v = plan.params_vector().detach().double()
+    P = lambda nm: float(v[names[nm]])  # noqa: E731  (bank 0)
+    g = plan.model.geom[0]
+    F, n = center.shape[0], center.shape[1]
+    i, j = pairs[:, 0].long(), pairs[:, 1].long()
+    valid = (i < n) & (torch.arange(pairs.shape[-1], device=pairs.device)[None, :] < count[:, None])
+    i, j = i.clamp(max=n - 1), j.clamp(max=n - 1)
+    q0, q1, q2, q3 = quat.unbind(-1)
+    a1 = torch.stack([q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3, 2 * (q1 * q2 + q0 * q3), 2 * (q1 * q3 - q0 * q2)], -1)
+    a2 = torch.stack([2 * (q1 * q2 - q0 * q3), q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3, 2 * (q2 * q3 + q0 * q1)], -1)
+    a3 = torch.stack([2 * (q1 * q3 + q0 * q2), 2 * (q2 * q3 - q0 * q1), q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3], -1)
+    back = center + g.back[0] * a1 + g.back[1] * a2 + g.back[2] * a3
+    base, stack = center + g.base * a1, center + g.stack * a1
+
+    def d2(x):
+        gi = torch.gather(x, 1, i.unsqueeze(-1).expand(-1, -1, 3))
+        gj = torch.gather(x, 1, j.unsqueeze(-1).expand(-1, -1, 3))
+        return (gi - gj).square().sum(-1)
+
+    ob = sum(x * x for x in g.back) ** 0.5
+    sr = max(P("unbonded_excluded_volume.dr_c_backbone") + 2 * ob, P("unbonded_excluded_volume.dr_c_base") + 2 * abs(g.base),
+             max(P("unbonded_excluded_volume.dr_c_back_base"), P("unbonded_excluded_volume.dr_c_base_back")) + ob + abs(g.base),
+             P("hydrogen_bonding.dr_c_high_hb") + 2 * abs(g.base), P("cross_stacking.dr_c_high_cross") + 2 * abs(g.base),
+             P("coaxial_stacking.dr_c_high_coax") + 2 * abs(g.stack))
+    in_sr = valid & (d2(center) < sr * sr)
+    db = d2(back)
+    in_db = valid & (db < P("debye.r_cut") ** 2) if plan.model.forms[0].has_debye else valid & False
+    bb = d2(base)
+    lo = min(P("hydrogen_bonding.dr_c_low_hb"), P("cross_stacking.dr_c_low_cross"))
+    hi = max(P("hydrogen_bonding.dr_c_high_hb"), P("cross_stacking.dr_c_high_cross"))
+    in_bp = in_sr & (bb > lo * lo) & (bb < hi * hi)
+    ss = d2(stack)
+    in_cx = in_sr & (ss > P("coaxial_stacking.dr_c_low_coax") ** 2) & (ss < P("coaxial_stacking.dr_c_high_coax") ** 2)
+    mean = lambda m: float(m.sum()) / F  # noqa: E731
+    return {"listed": mean(valid), "debye_support": mean(in_db), "short_range": mean(in_sr), "hb_cross_window": mean(in_bp),
+            "coax_window": mean(in_cx)}
+
+
+def slots_forward(n, n_b, u):
+    """Forward work of one configuration in FMA-issue slots (float64) from the measured support counts `u`."""
+    return (60 / 2 * n + (290 / 2 + S_BONDED) * n_b + SLOT_SCREEN * u["listed"] + SLOT_DEBYE * u["debye_support"] +
+            SLOT_EXC * u["short_range"] + SLOT_HBCR * u["hb_cross_window"] + SLOT_COAX * u["coax_window"])
+
+
+def force_benchmark(dev, n_dup: int, model: str, seed: int, peak_tflops: float, label: str, reps: int = 7):
+    """BASELINE.json configs[2] / configs[4]: neighbour rebuild + energy + forces + dE/dparams of one large configuration
+    (float64, free space, neighbour list at the interaction range) -> evaluations/s, device time (CUDA events)."""
+    from mythos_b200.energy import dna2, functional, na1
+    from mythos_b200.energy import model as kmodel
+    from mythos_b200.utils import neighbors, synthetic
+
+    pattern = ((1, 1), (2, 2), (1, 2)) if model == "na1" else None
+    s = synthetic.assembly(n_dup, seed=seed, nt_pattern=pattern)
+    cd = torch.tensor(s.center, device=dev).unsqueeze(0)
+    qd = torch.tensor(s.quat, device=dev).unsqueeze(0)
+    n = cd.shape[1]
+    efn = (na1 if model == "na1" else dna2).create_default_energy_fn(s.topology)
+    plan = kmodel.plan_for(efn.energy_fns)
+    topo = plan.topology(n, dev)
+    params = plan.device_params(dev, torch.float64)
+    cut = kmodel.interaction_range(plan)
+    ones = torch.ones((1, 8), device=dev, dtype=torch.float64)
+    _, count, _, ws = neighbors.build_pairs(cd, topo.bonded, (0, 0, 0), cut, 0.0, 1)
+    cap = int(int(count.item()) * 1.05) + 1024
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts)), out
+
+    t_nl, (pairs, count, ov, ws) = timed(lambda: neighbors.build_pairs(cd, topo.bonded, (0, 0, 0), cut, 0.0, cap, ws))
+    assert int(ov.item()) == 0
+    t_en, _ = timed(lambda: functional._launch(plan.model, topo, cd, qd, params, pairs[0], 0, 0xFF, ones, True, True, True, False, count))
+    t_ef, _ = timed(lambda: functional._launch(plan.model, topo, cd, qd, params, pairs[0], 0, 0xFF, ones, True, True, False, False, count))
+
+    def both():
+        p, cnt, _, _ = neighbors.build_pairs(cd, topo.bonded, (0, 0, 0), cut, 0.0, cap, ws)
+        return functional._launch(plan.model, topo, cd, qd, params, p[0], 0, 0xFF, ones, True, True, True, False, cnt)
+
+    t_all, _ = timed(both)
+    u = pair_support_counts(plan, cd, qd, pairs, count)
+    n_b = int(topo.bonded.shape[0])
+    flop_eq = 2 * 3.0 * slots_forward(n, n_b, u)  # E + forces + theta-VJP = 3 x forward (SURVEY 8d); 1 FMA slot = 2 flop
+    achieved = flop_eq / (t_en * 1e-3) / 1e12
+    return {
+        "workload": label, "n_nucleotides": n, "pairs": u,
+        "metric": "evaluations/s (neighbour rebuild + energy + forces + dE/dparams)", "value": 1e3 / t_all,
+        "nucleotide_evaluations_per_s": n * 1e3 / t_all,
+        "ms": {"neighbour_rebuild": t_nl, "energy_forces_dparams": t_en, "energy_forces": t_ef, "rebuild_plus_evaluation": t_all},
+        "roofline": {"bound": "fp64", "kernels": "k_list_debye + k_list_sr + k_pairs<bonded> (E + forces + dE/dparams)",
+                     "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops if peak_tflops else None,
+                     "work_model": "SURVEY 8d per-pair counts split per term, each counted inside its radial support (measured), x3 for E+F+theta-VJP; NA1: supports measured with the DNA bank's windows"},
+    }
 
 
 class ClockSampler:
@@ -316,26 +442,26 @@ def main():
     _, probe, _, _ = neighbors.build_pairs(cc[:8], topo.bonded, tuple(plan.model.box), rng_cut, 0.0, 1)
     cap = int(int(probe.max()) * 1.1) + 64
     pairs, count, _, _ = neighbors.build_pairs(cc, topo.bonded, tuple(plan.model.box), rng_cut, 0.0, cap)
-    u_nl = float(count.double().mean())
-    i, j = pairs[:8, 0].long(), pairs[:8, 1].long()
-    valid = i < n
-    d = torch.gather(cc[:8], 1, i.clamp(max=n - 1).unsqueeze(-1).expand(-1, -1, 3)) - torch.gather(cc[:8], 1, j.clamp(max=n - 1).unsqueeze(-1).expand(-1, -1, 3))
-    u_sr = float(((d.square().sum(-1) < 1.675**2) & valid).sum()) / 8
-    u_lr = u_nl - u_sr
-    launches = []
+    u = pair_support_counts(plan, cc[:16], qq[:16], pairs[:16], count[:16])
+    launches, nl_launches = [], []
+    stride = 2 * pairs.shape[-1]
     for _ in range(5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         torch.cuda.synchronize(dev)
         e0.record()
-        # the hot kernel exactly as the timed step runs it: all terms, all-pairs mode (in-kernel cell list), E + J rows
-        functional._launch(plan.model, topo, cc, qq, params_dev, None, 0, _lib.ALL_TERMS, ones[:chunk], True, False, True, True,
-                           None, 0, rng_cut)
+        neighbors.build_pairs(cc, topo.bonded, tuple(plan.model.box), rng_cut, 0.0, cap)
         e1.record()
+        # the hot kernel exactly as the timed step runs it: all terms, E + J rows, the chunk's device pair lists streamed
+        functional._launch(plan.model, topo, cc, qq, params_dev, pairs, stride, _lib.ALL_TERMS, ones[:chunk], True, False, True, True,
+                           count)
+        e2.record()
         torch.cuda.synchronize(dev)
-        launches.append(e0.elapsed_time(e1))
+        nl_launches.append(e0.elapsed_time(e1))
+        launches.append(e1.elapsed_time(e2))
     k_ms = float(np.median(launches[1:]))
     n_b = int(topo.bonded.shape[0])
-    slots_fwd = chunk * ((60 * n + 290 * n_b + 30 * u_nl + 65 * u_lr + 820 * u_sr) / 2 + S_BONDED * n_b + S_LR * u_lr + S_SR * u_sr)
+    slots_fwd = chunk * slots_forward(n, n_b, u)
+    nl_ms = float(np.median(nl_launches[1:]))
     flop_eq = 2 * 2.5 * slots_fwd  # E + params-only backward = 2.5 x forward; 1 FMA slot = 2 flop
     achieved = flop_eq / (k_ms * 1e-3) / 1e12
 
@@ -352,16 +478,17 @@ def main():
         best = max(best, 148 * 32 * 256 * 4096 * 16 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    alg_bytes = chunk * (n * 7 * 8 + 232 * 8 + 64)  # frame in, J row + terms row out; pair lists never exist in HBM
+    alg_bytes = chunk * (n * 7 * 8 + 8 * u["listed"] + 232 * 8 + 64)  # frame + pair list in, J row + terms row out
     roofline = {
-        "bound": "fp64", "kernel": "k_frame_energy<double,WP=1> (all terms, in-kernel cell list)", "achieved": achieved, "peak": best, "unit": "TFLOP/s",
+        "bound": "fp64", "kernel": "k_frame_energy<double,WP=1> (all terms of a frame, pair lists from the device neighbour build)", "achieved": achieved, "peak": best, "unit": "TFLOP/s",
         "frac": achieved / best if best else None, "traffic": None,
         "peak_source": "measured in this run (library FMA micro-benchmark, 148x32 blocks x 256 threads)",
-        "kernel_ms_per_launch": k_ms, "frames_per_launch": chunk,
-        "pairs_per_frame": {"listed": u_nl, "long_range_only": u_lr, "short_range": u_sr},
+        "kernel_ms_per_launch": k_ms, "frames_per_launch": chunk, "neighbour_build_ms_per_chunk": nl_ms,
+        "share_of_step": k_ms / (k_ms + nl_ms),
+        "pairs_per_frame": u,
         "hbm": {"algorithmic_gb_per_launch": alg_bytes / 1e9, "achieved_gbs": alg_bytes / 1e9 / (k_ms * 1e-3), "peak_gbs": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-        "work_model": "SURVEY 8d provisional per-pair counts x measured pair numbers; fp64 special weights div16 sqrt16 exp40 log50 acos70",
+        "work_model": "SURVEY 8d per-pair counts split per term, each term counted only inside its radial support (supports measured on 16 frames); x2.5 for E + dE/dparams; fp64 special weights div16 sqrt16 exp40 log50 acos70",
     }
 
     cpu_baseline = None
@@ -372,21 +499,26 @@ def main():
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                         "sample": f"{args.cpu_frames} frames of the same workload (oracle: torch-f64 restatement of the reference algorithm, autograd for dE/dparams)"}
 
-    md_line = None
+    md_line = forces_8k = forces_100k = None
     if world == 1:
         md_line = md_benchmark(dev)
+        forces_8k = force_benchmark(dev, 68, "dna2", 0, best,
+                                    "configs[2]: oxDNA2 + Debye, synthetic 68-duplex assembly (N=8160), neighbour list, float64")
+        forces_100k = force_benchmark(dev, 834, "na1", 2, best,
+                                      "configs[4]: NA1 hybrid DNA/RNA, synthetic 834-duplex assembly (N=100080), neighbour rebuild + forces, float64")
 
-    n_chunks = 1  # all-pairs mode: one frame-kernel launch covers the rank's whole block of frames
+    n_chunks = -(-(hi - lo) // functional.FRAME_CHUNK)  # per chunk: 18 neighbour-build kernels + 1 frame kernel
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": workload_name(F), "frames_per_gpu": hi - lo, "n_nucleotides": n,
-                   "l2": "inputs larger than L2 (frames 936 MB + per-chunk pair lists)", "n_theta": len(theta),
+                   "l2": "inputs larger than L2 (frames 936 MB + 0.8 GB of pair lists per 1184-frame chunk)", "n_theta": len(theta),
                    "loss": float(loss.detach()), "n_eff": float(neff.detach()), "grad_norm": float(dp.norm())},
         "e2e": {"value": F / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": args.steps * (n_chunks * 1 + 1),  # k_frame_energy + k_weights per step (torch glue not counted)
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "md": md_line,
+        "gpu_launches": args.steps * (n_chunks * 19 + 1),  # k_nl_* + k_frame_energy per chunk, k_weights per step (torch glue not counted)
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "md": md_line, "forces_8k": forces_8k,
+        "forces_100k": forces_100k,
     }
     print(json.dumps(line))
     if world > 1:

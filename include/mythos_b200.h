@@ -376,6 +376,7 @@ typedef struct mb_energy_args {
 } mb_energy_args;
 #define MB_FLAG_ACCUMULATE 0x1u /* add into the outputs instead of zeroing them first */
 #define MB_FLAG_GENERIC_KERNEL 0x2u /* force the one-thread-per-pair kernels even where the frame-resident kernel applies */
+#define MB_FLAG_LIST_KERNEL 0x4u /* explicit lists with forces / several banks: use the phase-queued list kernels even for short lists (needs workspace) */
 
 size_t mythos_b200_energy_workspace_bytes(int32_t n, int32_t n_frames, int64_t pair_capacity, int32_t real_bytes /* 4 or 8 */);
 int mythos_b200_energy_f64(void* cuda_stream, const mb_energy_args* a);
@@ -428,8 +429,9 @@ typedef struct mb_langevin_args {
   uint64_t seed, step;    /* counter-based RNG: noise = philox(seed, step, nucleotide) */
   const void* noise;      /* optional (N,6) standard normals (3 linear + 3 angular) overriding the RNG */
   int32_t phase;          /* 0 = B A O A (first part), 1 = closing B, 2 = closing B of the previous step fused with 0 */
-  int32_t advance_step;   /* after the step, add 1 to *step_ptr on the stream (one-node-per-step CUDA graphs)      */
-  const void* step_ptr;   /* optional device uint64 step counter: RNG counter and trajectory row; overrides `step` */
+  int32_t advance_step;   /* after the step, add 1 to *step_ptr (done inside the kernel by the last block to finish)   */
+  const void* step_ptr;   /* optional device uint64[2]: [0] step counter (RNG counter and trajectory row; overrides
+                           * `step`), [1] scratch that must be zero before the first call                            */
   void* traj_center;      /* optional out (traj_rows,N,3): positions after this call's drift at row *step_ptr      */
   void* traj_quat;        /* optional out (traj_rows,N,4)                                                          */
   int64_t traj_rows;

@@ -31,6 +31,7 @@ TERM_NAMES = (
 BONDED_TERMS, UNBONDED_TERMS, ALL_TERMS = 0x07, 0xF8, 0xFF
 FLAG_ACCUMULATE = 0x1
 FLAG_GENERIC_KERNEL = 0x2
+FLAG_LIST_KERNEL = 0x4
 NL_ROWS = 0x1
 MAX_BANKS = 3
 STATUS = {0: "MB_OK", 1: "MB_EINVAL_SHAPE", 2: "MB_EINVAL_MODEL", 3: "MB_ECAPACITY", 4: "MB_ECUDA"}

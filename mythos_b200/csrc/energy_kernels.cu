@@ -12,6 +12,7 @@
 namespace mb {
 
 constexpr int kBlock = 128;
+constexpr long long kListKernelMinPairs = 65536;  // below this the list kernels' extra launches cost more than they save
 
 // block-reduce the 8 per-term energies and add them to terms[frame]
 template <class T>
@@ -32,21 +33,11 @@ __device__ __forceinline__ void reduce_terms(T e[MB_N_TERMS], T* sE, T* out) {
   }
 }
 
+// one block of pairs: BONDED -> (FENE | bonded excluded volume | stacking, selected by `mask`) of kBlock bonds,
+// else every enabled unbonded term of kBlock listed pairs
 template <class T, bool WF, bool WP, bool BONDED>
-__global__ void __launch_bounds__(kBlock) k_pairs(const EnergyDev<T> a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int np = a.M.n_banks * MB_P_COUNT;
-  T* sP = reinterpret_cast<T*>(smem_raw);
-  T* sE = sP + np;
-  T* sAcc = sE + (kBlock / 32) * MB_N_TERMS;
-  for (int k = threadIdx.x; k < np; k += kBlock) {
-    sP[k] = a.params[k];
-    if (WP) sAcc[k] = T(0);
-  }
-  __syncthreads();
-
+__device__ __forceinline__ void pairs_body(const EnergyDev<T>& a, long long k, unsigned mask, T* sP, T* sE, T* sAcc, int np) {
   const int frame = blockIdx.y;
-  const long long k = (long long)blockIdx.x * kBlock + threadIdx.x;
   const long long fbase = (long long)frame * a.n;
   int i = 0, j = 0;
   bool valid;
@@ -84,11 +75,11 @@ __global__ void __launch_bounds__(kBlock) k_pairs(const EnergyDev<T> a) {
   if (BONDED) {
     const int32_t* snt = a.nt_type_stack ? a.nt_type_stack : a.nt_type;
     const int si = snt ? snt[i] : 1, sj = snt ? snt[j] : 1;
-    bonded_pair<T, WF, WP>(a.M, sP, valid, ni, nj, a.seq[i], a.seq[j], nti, ntj, si, sj, a.mask, cot, e, Gi, Gj, acc);
+    bonded_pair<T, WF, WP>(a.M, sP, valid, ni, nj, a.seq[i], a.seq[j], nti, ntj, si, sj, mask, cot, e, Gi, Gj, acc);
   } else {
     T m = T(1);
     if (a.M.half_charged_ends && a.is_end) m = (a.is_end[i] ? T(0.5) : T(1)) * (a.is_end[j] ? T(0.5) : T(1));
-    unbonded_pair<T, WF, WP>(a.M, sP, valid, ni, nj, a.seq[i], a.seq[j], nti, ntj, m, a.mask, cot, e, Gi, Gj, acc);
+    unbonded_pair<T, WF, WP>(a.M, sP, valid, ni, nj, a.seq[i], a.seq[j], nti, ntj, m, mask, cot, e, Gi, Gj, acc);
   }
   if (WF && valid) {
     scatter_nuc_grad(a, fbase + i, Gi, qi);
@@ -105,20 +96,46 @@ __global__ void __launch_bounds__(kBlock) k_pairs(const EnergyDev<T> a) {
   }
 }
 
+// ONE launch for bonded and unbonded pairs: blocks [0, 3 * bonded_chunks) evaluate one bonded term each for one chunk of
+// bonds (the three terms of a bond run in different blocks: the per-thread dependency chain -- what bounds small
+// systems such as the 60-bp MD duplex -- is a single term long), the remaining blocks one chunk of listed pairs each.
+template <class T, bool WF, bool WP>
+__global__ void __launch_bounds__(kBlock) k_pairs(const EnergyDev<T> a, int bonded_chunks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int np = a.M.n_banks * MB_P_COUNT;
+  T* sP = reinterpret_cast<T*>(smem_raw);
+  T* sE = sP + np;
+  T* sAcc = sE + (kBlock / 32) * MB_N_TERMS;
+  unsigned mask = a.mask;
+  const bool bonded = blockIdx.x < 3 * bonded_chunks;
+  if (bonded) {
+    mask &= 1u << (blockIdx.x % 3);  // MB_TERM_FENE, MB_TERM_BEXC, MB_TERM_STACK = 0, 1, 2
+    if (!mask) return;
+  }
+  for (int k = threadIdx.x; k < np; k += kBlock) {
+    sP[k] = a.params[k];
+    if (WP) sAcc[k] = T(0);
+  }
+  __syncthreads();
+  if (bonded)
+    pairs_body<T, WF, WP, true>(a, (long long)(blockIdx.x / 3) * kBlock + threadIdx.x, mask, sP, sE, sAcc, np);
+  else
+    pairs_body<T, WF, WP, false>(a, (long long)(blockIdx.x - 3 * bonded_chunks) * kBlock + threadIdx.x, mask, sP, sE, sAcc, np);
+}
+
 template <class T, bool WF, bool WP>
 static int launch_pairs(cudaStream_t s, const EnergyDev<T>& a, void* list_ws) {
   const size_t smem = sizeof(T) * (size_t)(a.M.n_banks * MB_P_COUNT * (WP ? 2 : 1) + (kBlock / 32) * MB_N_TERMS);
-  if ((a.mask & MB_BONDED_TERMS) && a.n_bonded > 0) {
-    dim3 grid(ceil_div(a.n_bonded, kBlock), a.n_frames);
-    k_pairs<T, WF, WP, true><<<grid, kBlock, smem, s>>>(a);
+  const int bonded_chunks = ((a.mask & MB_BONDED_TERMS) && a.n_bonded > 0) ? ceil_div(a.n_bonded, kBlock) : 0;
+  const bool unbonded = (a.mask & MB_UNBONDED_TERMS) && a.pair_capacity > 0;
+  const bool lists = unbonded && list_ws != nullptr;  // phase-queued list kernels (list_kernels.cu) take the unbonded part
+  const long long pair_chunks = (unbonded && !lists) ? ceil_div(a.pair_capacity, kBlock) : 0;
+  if (3 * bonded_chunks + pair_chunks > 0) {
+    dim3 grid((unsigned)(3 * bonded_chunks + pair_chunks), a.n_frames);
+    k_pairs<T, WF, WP><<<grid, kBlock, smem, s>>>(a, bonded_chunks);
     MB_CUDA_CHECK(cudaGetLastError());
   }
-  if ((a.mask & MB_UNBONDED_TERMS) && a.pair_capacity > 0) {
-    if (list_ws) return launch_list_kernel<T>(s, a, list_ws, WF, WP);  // phase-queued (list_kernels.cu)
-    dim3 grid(ceil_div(a.pair_capacity, kBlock), a.n_frames);
-    k_pairs<T, WF, WP, false><<<grid, kBlock, smem, s>>>(a);
-    MB_CUDA_CHECK(cudaGetLastError());
-  }
+  if (lists) return launch_list_kernel<T>(s, a, list_ws, WF, WP);
   return MB_OK;
 }
 
@@ -194,8 +211,9 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
              "energy: all_pairs_cutoff needs the frame-resident kernel (single bank, no position gradients, frame fits in "
              "shared memory); build a neighbour list with mythos_b200_nl_build_* instead");
   // phase-queued list kernel when the caller lends the workspace it needs; otherwise one thread per pair
+  // (short lists -- the 60-bp MD duplex has 7 021 pairs -- are launch-latency bound: one generic launch beats four)
   void* lk = nullptr;
-  if (!(x->flags & MB_FLAG_GENERIC_KERNEL) && x->workspace &&
+  if (!(x->flags & MB_FLAG_GENERIC_KERNEL) && x->workspace && ((x->flags & MB_FLAG_LIST_KERNEL) || (long long)x->pair_capacity * x->n_frames >= kListKernelMinPairs) &&
       x->workspace_bytes >= list_workspace_bytes<T>(x->n, x->n_frames, x->pair_capacity))
     lk = x->workspace;
   if (wf && wp) return launch_pairs<T, true, true>(s, a, lk);

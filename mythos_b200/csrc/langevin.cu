@@ -75,7 +75,8 @@ struct LangevinDev {
   int zero_forces;
   T dt, kT, gamma_c, gamma_q, mass, inertia[3], box[3];
   uint64_t seed, step;
-  const unsigned long long* step_ptr;  // device-side step counter (CUDA-graph replays), overrides `step`
+  unsigned long long* step_ptr;        // device-side step counter (CUDA-graph replays), overrides `step`; [1] = block counter
+  int advance;                         // add 1 to *step_ptr once every block has read it
   T* traj_center;                      // optional (S,N,3): position after this step is stored at row *step_ptr
   T* traj_quat;
   long long traj_rows;
@@ -116,9 +117,29 @@ __device__ __forceinline__ T shift1(T x, T L) {
 }
 
 template <class T>
+__device__ __forceinline__ void langevin_body(const LangevinDev<T>& a, int i, unsigned long long step_now);
+
+template <class T>
 __global__ void k_langevin(LangevinDev<T> a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
+  const unsigned long long step_now = a.step_ptr ? *a.step_ptr : a.step;
+  if (i < a.n) langevin_body(a, i, step_now);
+  if (a.step_ptr && a.advance) {
+    // the last block to finish bumps the step counter (every block has read it by then) and re-arms the block counter
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned* done = reinterpret_cast<unsigned*>(a.step_ptr + 1);
+      if (atomicAdd(done, 1u) == gridDim.x - 1) {
+        *done = 0u;
+        *a.step_ptr = step_now + 1ull;
+      }
+    }
+  }
+}
+
+template <class T>
+__device__ __forceinline__ void langevin_body(const LangevinDev<T>& a, int i, unsigned long long step_now) {
   T c[3], q[4], pc[3], pq[4];
   for (int d = 0; d < 3; ++d) {
     c[d] = a.center[3 * i + d];
@@ -152,7 +173,7 @@ __global__ void k_langevin(LangevinDev<T> a) {
         if (a.noise) {
           for (int k = 0; k < 6; ++k) z[k] = double(a.noise[6 * i + k]);
         } else {
-          normals6(a.seed, a.step_ptr ? (uint64_t)(*a.step_ptr) : a.step, uint32_t(i), z);
+          normals6(a.seed, (uint64_t)step_now, uint32_t(i), z);
         }
         const T c1 = exp(-a.gamma_c * a.dt);
         const T c2 = sqrt(a.kT * (T(1) - c1 * c1) * a.mass);
@@ -177,7 +198,7 @@ __global__ void k_langevin(LangevinDev<T> a) {
     for (int d = 0; d < 3; ++d) a.center[3 * i + d] = c[d];
     for (int d = 0; d < 4; ++d) a.quat[4 * i + d] = q[d];
     if (a.traj_center && a.step_ptr) {
-      const long long row = (long long)(*a.step_ptr);
+      const long long row = (long long)step_now;
       if (row < a.traj_rows) {
         for (int d = 0; d < 3; ++d) a.traj_center[(row * a.n + i) * 3 + d] = c[d];
         for (int d = 0; d < 4; ++d) a.traj_quat[(row * a.n + i) * 4 + d] = q[d];
@@ -187,8 +208,6 @@ __global__ void k_langevin(LangevinDev<T> a) {
   for (int d = 0; d < 3; ++d) a.p_center[3 * i + d] = pc[d];
   for (int d = 0; d < 4; ++d) a.p_quat[4 * i + d] = pq[d];
 }
-
-__global__ void k_advance(unsigned long long* p) { *p += 1ull; }
 
 template <class T>
 static int langevin_impl(cudaStream_t s, const mb_langevin_args* x) {
@@ -220,13 +239,13 @@ static int langevin_impl(cudaStream_t s, const mb_langevin_args* x) {
   }
   a.seed = x->seed;
   a.step = x->step;
-  a.step_ptr = static_cast<const unsigned long long*>(x->step_ptr);
+  a.step_ptr = static_cast<unsigned long long*>(const_cast<void*>(x->step_ptr));
+  a.advance = x->advance_step;
   a.traj_center = static_cast<T*>(x->traj_center);
   a.traj_quat = static_cast<T*>(x->traj_quat);
   a.traj_rows = x->traj_rows;
   MB_REQUIRE(!x->traj_center || (x->traj_quat && x->step_ptr), MB_EINVAL_SHAPE, "langevin: trajectory output needs traj_quat and step_ptr");
   k_langevin<T><<<ceil_div(x->n, 128), 128, 0, s>>>(a);
-  if (x->step_ptr && x->advance_step) k_advance<<<1, 1, 0, s>>>(static_cast<unsigned long long*>(const_cast<void*>(x->step_ptr)));
   MB_CUDA_CHECK(cudaGetLastError());
   return MB_OK;
 }

@@ -215,15 +215,27 @@ __global__ void __launch_bounds__(kDB) k_list_debye(const EnergyDev<T> a) {
   pk_t* sr_list = a.sr_list + (long long)frame * a.sr_capacity;
   int* sr_count = a.sr_count + frame;
   constexpr int kTile = kDB * kDU;
-  for (long long base = (long long)blockIdx.x * kTile; base < count; base += (long long)gridDim.x * kTile) {
+  // the index loads of the NEXT tile are issued before the current tile is evaluated: the list streams from HBM
+  // (~40 MB at 100k nucleotides), and index -> record -> arithmetic would otherwise be one dependent chain per step
+  const long long stride = (long long)gridDim.x * kTile;
+  int ni[kDU], nj[kDU];
+#pragma unroll
+  for (int u = 0; u < kDU; ++u) {
+    const long long k = (long long)blockIdx.x * kTile + threadIdx.x + u * kDB;
+    ni[u] = k < count ? pl[k] : -1;
+    nj[u] = k < count ? pl[a.pair_capacity + k] : -1;
+  }
+  for (long long base = (long long)blockIdx.x * kTile; base < count; base += stride) {
     int pi[kDU], pj[kDU];
     bool pv[kDU];
 #pragma unroll
-    for (int u = 0; u < kDU; ++u) {  // all index loads of the step in flight together
-      const long long k = base + threadIdx.x + u * kDB;
-      pv[u] = k < count;
-      pi[u] = pv[u] ? pl[k] : 0;
-      pj[u] = pv[u] ? pl[a.pair_capacity + k] : 0;
+    for (int u = 0; u < kDU; ++u) {
+      pi[u] = ni[u];
+      pj[u] = nj[u];
+      pv[u] = base + threadIdx.x + u * kDB < count;
+      const long long k = base + stride + threadIdx.x + u * kDB;
+      ni[u] = k < count ? pl[k] : -1;
+      nj[u] = k < count ? pl[a.pair_capacity + k] : -1;
     }
     bool sr[kDU];
 #pragma unroll

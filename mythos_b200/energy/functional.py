@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses as dc
+import os
 
 import torch
 
@@ -126,7 +127,7 @@ def _launch(
     a.d_params = _lib.ptr(d_params)
     a.d_params_frame_stride = stride
     ws = None
-    if cap and not (flags & _lib.FLAG_GENERIC_KERNEL):
+    if cap and (cap * F >= 65536 or (flags & _lib.FLAG_LIST_KERNEL)) and not (flags & _lib.FLAG_GENERIC_KERNEL):
         # scratch of the phase-queued list kernel (caller-owned, as everywhere in the C-ABI); the caching allocator
         # makes this a pointer bump, and it is graph-capture safe
         need = int(_lib.lib().mythos_b200_energy_workspace_bytes(N, F, cap, 8 if dtype == torch.float64 else 4))
@@ -200,7 +201,7 @@ class CellListPairs:
         return False
 
 
-FRAME_CHUNK = 1184  # frames per launch group (8 waves of one CTA per SM); bounds the pair-list buffer (~1.2 GB at N=2k)
+FRAME_CHUNK = int(os.environ.get("MYTHOS_B200_FRAME_CHUNK", "1184"))  # frames per launch group (8 waves of one CTA per SM); bounds the pair-list buffer (~1.2 GB at N=2k)
 
 
 def _chunks(n_frames: int, source) -> list[slice]:

@@ -35,7 +35,7 @@ class NVTLangevinState:
     momentum: RigidBody  # center: linear momentum (N,3); orientation.vec: quaternion-conjugate momentum (N,4)
     force: RigidBody  # holds dE/dcenter, dE/dquat (the force is its negative)
     mass: RigidBody  # center: scalar mass; orientation: (3,) principal moments
-    step: torch.Tensor  # (1,) uint64-as-int64 device counter
+    step: torch.Tensor  # (2,) uint64-as-int64: [0] device step counter, [1] kernel scratch
     seed: int = 0
 
 
@@ -152,7 +152,7 @@ def nvt_langevin(energy_fn, shift_fn, dt: float, kT: float, gamma: RigidBody | A
             momentum=RigidBody(pc.contiguous(), Quaternion(pq.contiguous())),
             force=RigidBody(dcen, Quaternion(dq)),
             mass=mass,
-            step=torch.zeros(1, dtype=torch.int64, device=dev),
+            step=torch.zeros(2, dtype=torch.int64, device=dev),  # [0] step counter, [1] scratch of the kernel
             seed=int(key) + seed,
         )
 
@@ -256,8 +256,8 @@ class MDSimulator:
         c, q = state.position.center, state.position.orientation.vec
 
         def one_step():
-            # 4 launches per step: B-A-O-A (zeroes the gradient buffers after the kick), counter++, bonded pairs, unbonded
-            # pairs (both accumulate (dE/dcenter, dE/dquat) straight into the state's buffers)
+            # 2 launches per step: B-A-O-A (zeroes the gradient buffers after the kick, bumps the step counter) and the pair
+            # kernel (bonded + unbonded blocks in one grid, accumulating (dE/dcenter, dE/dquat) into the state's buffers)
             step_fn.launch(state, 2 if one_step.started else 0, traj=traj, advance=True, zero_forces=True)
             one_step.started = True
             f.accumulate_into(c, q, state.force.center, state.force.orientation.vec)
