@@ -244,7 +244,7 @@ def force_benchmark(dev, n_dup: int, model: str, seed: int, peak_tflops: float, 
     cut = kmodel.interaction_range(plan)
     ones = torch.ones((1, 8), device=dev, dtype=torch.float64)
     _, count, _, ws = neighbors.build_pairs(cd, topo.bonded, (0, 0, 0), cut, 0.0, 1)
-    cap = int(int(count.item()) * 1.05) + 1024
+    cap = (int(int(count.item()) * 1.05) + 1024) // 4 * 4
 
     def timed(fn):
         fn()
@@ -440,7 +440,7 @@ def main():
     cc, qq = c_dev[:chunk].contiguous(), q_dev[:chunk].contiguous()
     rng_cut = kmodel.interaction_range(plan)
     _, probe, _, _ = neighbors.build_pairs(cc[:8], topo.bonded, tuple(plan.model.box), rng_cut, 0.0, 1)
-    cap = int(int(probe.max()) * 1.1) + 64
+    cap = (int(int(probe.max()) * 1.1) + 64) // 4 * 4
     pairs, count, _, _ = neighbors.build_pairs(cc, topo.bonded, tuple(plan.model.box), rng_cut, 0.0, cap)
     u = pair_support_counts(plan, cc[:16], qq[:16], pairs[:16], count[:16])
     launches, nl_launches = [], []

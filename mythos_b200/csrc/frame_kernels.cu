@@ -269,10 +269,10 @@ __device__ __forceinline__ void cell_of(const CellGrid<T>* grid, const T* box, b
 #define MB_TICK(slot)
 #endif
 
-template <class T, bool WP, bool CACHE_BACK>
+template <class T, bool WP, bool CACHE_BACK, bool CELLS>
 __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, const FrameSmem L) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const bool cells = a.all_pairs_cutoff > T(0);
+  constexpr bool cells = CELLS;  // all-pairs mode (in-kernel cell list) vs an explicit pair list
   T* sC = reinterpret_cast<T*>(smem + L.c);
   T* sQ = reinterpret_cast<T*>(smem + L.q);
   T* sB = reinterpret_cast<T*>(smem + L.back);
@@ -567,6 +567,20 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
     // (packed into five registers so that the consumer phases keep theirs: position | row << 16 | fresh << 24, k | len << 16,
     // the row's two runs as start | length << 16, cell coordinates 10 bits each)
     unsigned st_a = unsigned(threadIdx.x) | (1u << 24), st_kl = 0u, st_r0 = 0u, st_r1 = 0u, st_c = 0u;
+    // list mode: the NEXT producer step's entries (i | j << 16, all ones = none) are loaded one step ahead, so that the
+    // list, which streams from HBM, is never waited for
+    uint32_t pf[kSlice];
+    if (!cells) {
+#pragma unroll
+      for (int u = 0; u < kSlice; ++u) {
+        const long long k = threadIdx.x + (long long)u * kFB;
+        pf[u] = 0xffffffffu;
+        if (k < count) {
+          const int i = pl[k], j = pl[a.pair_capacity + k];
+          if (i >= 0 && j >= 0 && i < n && j < n) pf[u] = uint32_t(i) | (uint32_t(j) << 16);
+        }
+      }
+    }
     const int n_rows = cells ? half_shell_rows(grid->S) : 0;
     const T rc_debye2 = want_debye ? sP[MB_P_DEBYE_RCUT] * sP[MB_P_DEBYE_RCUT] : T(-1);
     bool flush = false;
@@ -716,13 +730,22 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
           flush = true;
           continue;
         }
+        base += (long long)kFB * kSlice;
 #pragma unroll
         for (int u = 0; u < kSlice; ++u) {
-          const long long k = base + threadIdx.x + (long long)u * kFB;
-          if (k < count) {
-            const int i = pl[k], j = pl[a.pair_capacity + k];
-            if (i >= 0 && j >= 0 && i < n && j < n) {
-              found[u] = uint32_t(i) | (uint32_t(j) << 16);
+          const uint32_t cur = pf[u];
+          {  // issue the next step's loads before touching this step's entries
+            const long long k = base + threadIdx.x + (long long)u * kFB;
+            pf[u] = 0xffffffffu;
+            if (k < count) {
+              const int i2 = pl[k], j2 = pl[a.pair_capacity + k];
+              if (i2 >= 0 && j2 >= 0 && i2 < n && j2 < n) pf[u] = uint32_t(i2) | (uint32_t(j2) << 16);
+            }
+          }
+          if (cur != 0xffffffffu) {
+            const int i = int(cur & 0xffffu), j = int(cur >> 16);
+            {
+              found[u] = cur;
               const V3<T> dc = disp(v3<T>(sC[3 * j], sC[3 * j + 1], sC[3 * j + 2]), v3<T>(sC[3 * i], sC[3 * i + 1], sC[3 * i + 2]), M.box);
               if (want_sr && dot(dc, dc) < sr_cut2) acc_sr |= 1u << u;
               if (want_debye) {
@@ -738,7 +761,6 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
             }
           }
         }
-        base += (long long)kFB * kSlice;
       } else {
         // CTA-uniform exit test: every thread has exhausted its stream
         const int busy = __syncthreads_or(int(st_a & 0xffffu) < n);
@@ -903,12 +925,16 @@ bool frame_kernel_eligible(const EnergyDev<T>& a) {
   return pick_layout(a, true, &cb, &L);
 }
 
-template <class T, bool WP, bool CB>
-static int launch_one(cudaStream_t s, const EnergyDev<T>& a, const FrameSmem& L) {
-  MB_CUDA_CHECK(cudaFuncSetAttribute(k_frame_energy<T, WP, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-  k_frame_energy<T, WP, CB><<<a.n_frames, kFB, L.total, s>>>(a, L);
+template <class T, bool WP, bool CB, bool CELLS>
+static int launch_two(cudaStream_t s, const EnergyDev<T>& a, const FrameSmem& L) {
+  MB_CUDA_CHECK(cudaFuncSetAttribute(k_frame_energy<T, WP, CB, CELLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  k_frame_energy<T, WP, CB, CELLS><<<a.n_frames, kFB, L.total, s>>>(a, L);
   MB_CUDA_CHECK(cudaGetLastError());
   return MB_OK;
+}
+template <class T, bool WP, bool CB>
+static int launch_one(cudaStream_t s, const EnergyDev<T>& a, const FrameSmem& L) {
+  return a.all_pairs_cutoff > T(0) ? launch_two<T, WP, CB, true>(s, a, L) : launch_two<T, WP, CB, false>(s, a, L);
 }
 
 template <class T>

@@ -20,7 +20,8 @@
 //                contiguous run of the sorted arrays (x-neighbouring cells have consecutive ids); neighbouring lanes sit
 //                in the same or adjacent cells, so candidate loads are broadcasts out of L1
 //   7. scan      exclusive scan of the per-nucleotide counts -> offsets; per-frame totals -> count[frame]
-//   8. fill      same walk, writing (min(i,j), max(i,j)) at the nucleotide's offset; tail padded with N
+//   8. fill      same walk replaying the accept bits the count pass recorded (no coordinates, no arithmetic), writing
+//                (min(i,j), max(i,j)) at the nucleotide's offset four pairs per 128-bit store; tail padded with N
 // Rows mode (MB_NL_ROWS) replaces 6-8 by ONE walk that writes a fixed-width row per nucleotide with the unused slots set
 // to the padding value N: still a valid OrderedSparse list (consumers mask entries >= N wherever they are), at half the
 // cost -- the shape the energy kernels of this library are fed with.
@@ -31,6 +32,8 @@ namespace mb {
 constexpr int kNlBlock = 128;
 constexpr int kMaxExcl = 4;
 constexpr int kNlUnroll = 4;      // candidates in flight per thread in the walk
+constexpr int kNlBitWords = 8;    // accept bits the count pass records per nucleotide for the fill pass (32 each)
+constexpr int kNlBitCap = 32 * kNlBitWords;
 constexpr int kScanChunk = 2048;  // elements per block of the multi-block scan (256 threads x 8)
 
 template <class T>
@@ -77,6 +80,7 @@ struct NlDev {
   int32_t* tmp_order;  // (F*N) ids in cell order, unsorted inside a cell
   NlRec<T>* srec;      // (F*N) cell-ordered (coordinates, id), ids ascending inside a cell
   int32_t* nbcount;    // (F*N + 1) per-nucleotide pair counts (cell order), then exclusive scan
+  uint32_t* bitbuf;    // (kNlBitWords, F*N) accept bits of the count pass, word-major
   int32_t* scan_tmp;   // block sums of the multi-block scan
 };
 
@@ -378,6 +382,50 @@ __global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
     out0 = a.pairs + (long long)f * 2 * a.capacity + (pos - (long long)f * a.n);
     out1 = out0 + a.capacity;
   }
+  const long long R = (long long)a.n * a.n_frames;
+  int ci = 0;        // running candidate index of this thread (same enumeration in the count and fill passes)
+  unsigned bw = 0u;  // current word of accept bits
+  // accept test of one candidate record; receiver = lower index (OrderedSparse keeps i < j): dR = R_low - R_high, as the
+  // reference evaluates it (in free space the two orders give exact negatives, whose squares are identical)
+  auto accept = [&](const NlRec<T>& c, int& j, bool& me_low) -> bool {
+    j = c.id;
+    me_low = i < j;
+    T ddx = xi - c.x, ddy = yi - c.y, ddz = zi - c.z;
+    if (PERIODIC) {
+      if (!me_low) {
+        ddx = c.x - xi;
+        ddy = c.y - yi;
+        ddz = c.z - zi;
+      }
+      ddx = wrap_nl(ddx, a.box[0]);
+      ddy = wrap_nl(ddy, a.box[1]);
+      ddz = wrap_nl(ddz, a.box[2]);
+    }
+    const T d2 = add_rn(add_rn(mul_rn(ddx, ddx), mul_rn(ddy, ddy)), mul_rn(ddz, ddz));
+    return d2 < a.cut2 && j != ex[0] && j != ex[1] && j != ex[2] && j != ex[3];
+  };
+  // fill pass: accepted pairs go out four at a time as 128-bit stores once the write position is 16-byte aligned
+  int l0 = 0, l1 = 0, l2 = 0, l3 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0, nbuf = 0;
+  const bool vec_ok = FILL && (a.capacity & 3) == 0 && (reinterpret_cast<unsigned long long>(a.pairs) & 15ull) == 0;
+  auto emit = [&](int lo, int hi) {
+    l0 = l1; l1 = l2; l2 = l3; l3 = lo;
+    h0 = h1; h1 = h2; h2 = h3; h3 = hi;
+    ++nbuf;
+    ++found;
+    if (!vec_ok || (wpos & 3) != 0 || wpos + 4 > a.capacity) {  // scalar: unaligned head, odd capacity, or the truncated end
+      if (wpos < a.capacity) {
+        out0[wpos] = lo;
+        out1[wpos] = hi;
+      }
+      ++wpos;
+      nbuf = 0;
+    } else if (nbuf == 4) {
+      *reinterpret_cast<int4*>(out0 + wpos) = make_int4(l0, l1, l2, l3);
+      *reinterpret_cast<int4*>(out1 + wpos) = make_int4(h0, h1, h2, h3);
+      wpos += 4;
+      nbuf = 0;
+    }
+  };
   const int S = g.S, n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
   const int n_rows = 1 + S + S * (2 * S + 1);
   for (int row = 0; row < n_rows; ++row) {
@@ -419,49 +467,80 @@ __global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
     if (row == 0) rs[0] = int(pos) + 1 > rs[0] ? int(pos) + 1 : rs[0];  // own cell: ids ascend, partners come after
 #pragma unroll
     for (int run = 0; run < 2; ++run) {
-      for (int q0 = rs[run]; q0 < re[run]; q0 += kNlUnroll) {
-        NlRec<T> c[kNlUnroll];
-#pragma unroll
-        for (int u = 0; u < kNlUnroll; ++u) {  // independent 128-bit loads first, tests after
-          const int q = q0 + u < re[run] ? q0 + u : re[run] - 1;
-          c[u] = a.srec[q];
-        }
-#pragma unroll
-        for (int u = 0; u < kNlUnroll; ++u) {
-          const int j = c[u].id;
-          // receiver = lower index (OrderedSparse keeps i < j): dR = R_low - R_high, as the reference evaluates it
-          const bool me_low = i < j;
-          // (in free space the two orders give exact negatives, whose squares are identical: no selects needed)
-          T ddx = xi - c[u].x, ddy = yi - c[u].y, ddz = zi - c[u].z;
-          if (PERIODIC) {
-            if (!me_low) {
-              ddx = c[u].x - xi;
-              ddy = c[u].y - yi;
-              ddz = c[u].z - zi;
+      if (FILL) {
+        // second pass: replay the accept bits of the count pass (no coordinates, no arithmetic); candidates beyond the
+        // recorded kNlBitCap are re-tested
+        int q = rs[run];
+        while (q < re[run]) {
+          if (ci >= kNlBitCap) {
+            for (; q < re[run]; ++q) {
+              int j;
+              bool me_low;
+              if (accept(a.srec[q], j, me_low)) emit(me_low ? i : j, me_low ? j : i);
             }
-            ddx = wrap_nl(ddx, a.box[0]);
-            ddy = wrap_nl(ddy, a.box[1]);
-            ddz = wrap_nl(ddz, a.box[2]);
+            break;
           }
-          const T d2 = add_rn(add_rn(mul_rn(ddx, ddx), mul_rn(ddy, ddy)), mul_rn(ddz, ddz));
-          const bool ok = q0 + u < re[run] && d2 < a.cut2 && j != ex[0] && j != ex[1] && j != ex[2] && j != ex[3];
-          if (ok) {
-            if (FILL) {
-              if (wpos < a.capacity) {
-                out0[wpos] = me_low ? i : j;
-                out1[wpos] = me_low ? j : i;
+          if ((ci & 31) == 0) bw = a.bitbuf[(long long)(ci >> 5) * R + pos];
+          int avail = 32 - (ci & 31);
+          avail = avail < re[run] - q ? avail : re[run] - q;
+          unsigned m = (bw >> (ci & 31)) & (avail == 32 ? 0xffffffffu : ((1u << avail) - 1u));
+          while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1u;
+            const int j = a.srec[q + bit].id;
+            emit(i < j ? i : j, i < j ? j : i);
+          }
+          q += avail;
+          ci += avail;
+        }
+      } else {
+        for (int q0 = rs[run]; q0 < re[run]; q0 += kNlUnroll) {
+          NlRec<T> c[kNlUnroll];
+#pragma unroll
+          for (int u = 0; u < kNlUnroll; ++u) {  // independent 128-bit loads first, tests after
+            const int q = q0 + u < re[run] ? q0 + u : re[run] - 1;
+            c[u] = a.srec[q];
+          }
+#pragma unroll
+          for (int u = 0; u < kNlUnroll; ++u) {
+            int j;
+            bool me_low;
+            const bool in = q0 + u < re[run];
+            const bool ok = accept(c[u], j, me_low) && in;
+            if (MODE == 0 && in) {  // record the decision for the fill pass
+              if (ci < kNlBitCap) {
+                bw |= (ok ? 1u : 0u) << (ci & 31);
+                if ((ci & 31) == 31) {
+                  a.bitbuf[(long long)(ci >> 5) * R + pos] = bw;
+                  bw = 0u;
+                }
               }
-              ++wpos;
+              ++ci;
             }
-            if (ROWS && found < row_width) {
-              out0[(long long)found * a.n] = me_low ? i : j;
-              out1[(long long)found * a.n] = me_low ? j : i;
+            if (ok) {
+              if (ROWS && found < row_width) {
+                out0[(long long)found * a.n] = me_low ? i : j;
+                out1[(long long)found * a.n] = me_low ? j : i;
+              }
+              ++found;
             }
-            ++found;
           }
         }
       }
     }
+  }
+  if (MODE == 0 && (ci & 31) != 0 && ci < kNlBitCap) a.bitbuf[(long long)(ci >> 5) * R + pos] = bw;
+  if (FILL) {  // the last 1..3 buffered pairs
+    const int lo_[4] = {l0, l1, l2, l3}, hi_[4] = {h0, h1, h2, h3};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k >= 4 - nbuf) {
+        if (wpos < a.capacity) {
+          out0[wpos] = lo_[k];
+          out1[wpos] = hi_[k];
+        }
+        ++wpos;
+      }
   }
   if (MODE == 0) a.nbcount[pos] = found;
   if (ROWS) {
@@ -522,11 +601,10 @@ __global__ void k_nl_finish(NlDev<T> a) {
     if (total > a.capacity) atomicOr(a.overflow, 1);
   }
   int32_t* out0 = a.pairs + (long long)f * 2 * a.capacity;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < a.capacity; k += (long long)gridDim.x * blockDim.x) {
-    if (k >= total) {
-      out0[k] = a.n;
-      out0[a.capacity + k] = a.n;
-    }
+  for (long long k = (long long)(total < 0 ? 0 : total) + blockIdx.x * blockDim.x + threadIdx.x; k < a.capacity;
+       k += (long long)gridDim.x * blockDim.x) {
+    out0[k] = a.n;
+    out0[a.capacity + k] = a.n;
   }
 }
 
@@ -566,6 +644,8 @@ static size_t carve(NlDev<T>* a, void* ws, int n, int F) {
   if (a) a->srec = static_cast<NlRec<T>*>(p);
   p = take(sizeof(int32_t) * (R + 1));
   if (a) a->nbcount = static_cast<int32_t*>(p);
+  p = take(sizeof(uint32_t) * kNlBitWords * R);
+  if (a) a->bitbuf = static_cast<uint32_t*>(p);
   const size_t longest = (F * C + 1 > R + 1) ? F * C + 1 : R + 1;
   p = take(sizeof(int32_t) * (longest / kScanChunk + 2));
   if (a) a->scan_tmp = static_cast<int32_t*>(p);
@@ -635,7 +715,7 @@ static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
     scan_exclusive(s, a.nbcount, R, a.scan_tmp);
     if (periodic) k_nl_walk<T, 1, true><<<gr, kNlBlock, 0, s>>>(a);
     else k_nl_walk<T, 1, false><<<gr, kNlBlock, 0, s>>>(a);
-    dim3 gf(min(ceil_div(x->capacity, 256), 1024), F);
+    dim3 gf(F > 64 ? 1 : 32, F);  // only the tail [count, capacity) is touched
     k_nl_finish<T><<<gf, 256, 0, s>>>(a);
   }
   MB_CUDA_CHECK(cudaGetLastError());

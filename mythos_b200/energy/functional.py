@@ -178,7 +178,7 @@ class CellListPairs:
         c = center.detach()
         if self.capacity <= 0:
             _, count, _, self.workspace = neighbors.build_pairs(c[:1], self.bonded, self.box, self.r_cutoff, 0.0, 1, self.workspace)
-            self.capacity = max(int(int(count.max().item()) * 1.06) + 64, 64)
+            self.capacity = (max(int(int(count.max().item()) * 1.06) + 64, 64) + 3) // 4 * 4  # multiple of 4: 128-bit pair stores
         pairs, count, overflow, self.workspace = neighbors.build_pairs(
             c, self.bonded, self.box, self.r_cutoff, 0.0, self.capacity, self.workspace
         )
@@ -197,7 +197,7 @@ class CellListPairs:
         self.max_count = max(self.max_count, worst)
         if worst <= self.capacity:
             return True
-        self.capacity = int(worst * 1.06) + 64  # jax_md would report did_buffer_overflow; here the pass re-runs
+        self.capacity = (int(worst * 1.06) + 64 + 3) // 4 * 4  # jax_md would report did_buffer_overflow; here the pass re-runs
         return False
 
 

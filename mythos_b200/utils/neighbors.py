@@ -101,7 +101,7 @@ class NeighborListFns:
         c = self._centers(position)
         probe, count, overflow, ws = build_pairs(c.unsqueeze(0), self.bonded_neighbors, self.box, self.r_cutoff, self.dr_threshold, 1)
         n_found = int(count.item())
-        capacity = max(int(n_found * self.capacity_multiplier) + extra_capacity, 1)
+        capacity = (max(int(n_found * self.capacity_multiplier) + extra_capacity, 1) + 3) // 4 * 4  # multiple of 4: 128-bit pair stores
         pairs, count, overflow, ws = build_pairs(
             c.unsqueeze(0), self.bonded_neighbors, self.box, self.r_cutoff, self.dr_threshold, capacity, ws
         )
