@@ -376,6 +376,7 @@ typedef struct mb_energy_args {
 } mb_energy_args;
 #define MB_FLAG_ACCUMULATE 0x1u /* add into the outputs instead of zeroing them first */
 #define MB_FLAG_GENERIC_KERNEL 0x2u /* force the one-thread-per-pair kernels even where the frame-resident kernel applies */
+#define MB_FLAG_TAGGED_PAIRS 0x8u /* `pairs` comes from mythos_b200_nl_build_* with MB_NL_TAG_SUPPORTS (frame-resident kernel only) */
 #define MB_FLAG_LIST_KERNEL 0x4u /* explicit lists with forces / several banks: use the phase-queued list kernels even for short lists (needs workspace) */
 
 size_t mythos_b200_energy_workspace_bytes(int32_t n, int32_t n_frames, int64_t pair_capacity, int32_t real_bytes /* 4 or 8 */);
@@ -404,7 +405,14 @@ typedef struct mb_nl_args {
   uint32_t flags;         /* MB_NL_* */
   uint32_t _pad;
   int32_t* max_row;       /* rows mode: out (F) longest row found (to size the rows), or NULL */
+  const void* site2;      /* MB_NL_TAG_SUPPORTS: (F,N,3) second site of each nucleotide (the backbone site) */
+  double r_inner;         /* MB_NL_TAG_SUPPORTS: inner centre cutoff (short-range terms)                     */
+  double r_site2;         /* MB_NL_TAG_SUPPORTS: cutoff on the second-site distance (Debye-Hueckel)          */
 } mb_nl_args;
+#define MB_NL_TAG_SUPPORTS 0x2u /* internal contract with mythos_b200_energy_* (MB_FLAG_TAGGED_PAIRS): of the pairs inside
+                         * r_cutoff keep only those whose centres are inside r_inner (bit 30 of pairs[1][k] set) or whose
+                         * second sites are inside r_site2 (bit 29 set); the index is pairs[1][k] & 0x1fffffff.  Not the
+                         * reference's pair set: every dropped pair contributes exactly zero to every term.           */
 #define MB_NL_ROWS 0x1u /* one-pass build: instead of a compact list, row k-major slots of width capacity / n per nucleotide
                          * (entry k * n + p = k-th partner of the p-th nucleotide in cell order), unused slots = n (the
                          * padding value); *overflow bit 0 is set if a row is too narrow; count = pairs found.  Consumers
@@ -412,6 +420,10 @@ typedef struct mb_nl_args {
 size_t mythos_b200_nl_workspace_bytes(int32_t n, int32_t n_frames);
 int mythos_b200_nl_build_f64(void* cuda_stream, const mb_nl_args* a);
 int mythos_b200_nl_build_f32(void* cuda_stream, const mb_nl_args* a);
+
+/* backbone interaction sites (F*N,3) of (center, quat): the second site MB_NL_TAG_SUPPORTS wants (single-flavour models) */
+int mythos_b200_backbone_sites_f64(void* cuda_stream, const mb_model* model, int64_t n_total, const void* center, const void* quat, void* out);
+int mythos_b200_backbone_sites_f32(void* cuda_stream, const mb_model* model, int64_t n_total, const void* center, const void* quat, void* out);
 
 /* ---- rigid-body Langevin (BAOAB) step -------------------------------------------------------------------------
  * One call = B(dt/2) A(dt/2) O A(dt/2) on the state, i.e. everything of a step up to the force evaluation, or

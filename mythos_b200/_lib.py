@@ -33,6 +33,8 @@ FLAG_ACCUMULATE = 0x1
 FLAG_GENERIC_KERNEL = 0x2
 FLAG_LIST_KERNEL = 0x4
 NL_ROWS = 0x1
+NL_TAG_SUPPORTS = 0x2
+FLAG_TAGGED_PAIRS = 0x8
 MAX_BANKS = 3
 STATUS = {0: "MB_OK", 1: "MB_EINVAL_SHAPE", 2: "MB_EINVAL_MODEL", 3: "MB_ECAPACITY", 4: "MB_ECUDA"}
 
@@ -121,6 +123,9 @@ class NlArgs(C.Structure):
         ("flags", C.c_uint32),
         ("_pad", C.c_uint32),
         ("max_row", C.c_void_p),
+        ("site2", C.c_void_p),
+        ("r_inner", C.c_double),
+        ("r_site2", C.c_double),
     ]
 
 
@@ -169,6 +174,8 @@ _SIGNATURES = {
     "mythos_b200_energy_f64": (C.c_int, [C.c_void_p, C.POINTER(EnergyArgs)]),
     "mythos_b200_energy_f32": (C.c_int, [C.c_void_p, C.POINTER(EnergyArgs)]),
     "mythos_b200_energy_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
+    "mythos_b200_backbone_sites_f64": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mythos_b200_backbone_sites_f32": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mythos_b200_nl_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "mythos_b200_nl_build_f64": (C.c_int, [C.c_void_p, C.POINTER(NlArgs)]),
     "mythos_b200_nl_build_f32": (C.c_int, [C.c_void_p, C.POINTER(NlArgs)]),

@@ -36,6 +36,7 @@ struct EnergyDev {
   unsigned long long* sr_list;  // list kernel workspace: (F, sr_capacity) short-range pairs (i | j << 32)
   int* sr_count;                // (F)
   long long sr_capacity;
+  int tagged;  // `pairs` carries support tags (MB_NL_TAG_SUPPORTS); frame-resident kernel only
 };
 
 // Parameter-gradient accumulator: warp-reduce, then one shared-memory atomic per warp and parameter.

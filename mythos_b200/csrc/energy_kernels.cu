@@ -191,6 +191,7 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
   a.sr_list = nullptr;
   a.sr_count = nullptr;
   a.sr_capacity = 0;
+  a.tagged = (x->flags & MB_FLAG_TAGGED_PAIRS) ? 1 : 0;
 
   const size_t np = (size_t)m.n_banks * MB_P_COUNT;
   if (!(x->flags & MB_FLAG_ACCUMULATE)) {
@@ -207,6 +208,8 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
   const bool wf = a.d_center || a.d_quat, wp = a.d_params != nullptr;
   // frame-resident path: one block per frame with the frame staged in shared memory (energies and dE/dparams only)
   if (!wf && !(x->flags & MB_FLAG_GENERIC_KERNEL) && frame_kernel_eligible<T>(a)) return launch_frame_kernel<T>(s, a, wp);
+  MB_REQUIRE(!a.tagged, MB_ECAPACITY, "energy: tagged pair lists need the frame-resident kernel (single bank, no position "
+             "gradients, frame fits in shared memory, n < 16384)");
   MB_REQUIRE(!(x->all_pairs_cutoff > 0), MB_ECAPACITY,
              "energy: all_pairs_cutoff needs the frame-resident kernel (single bank, no position gradients, frame fits in "
              "shared memory); build a neighbour list with mythos_b200_nl_build_* instead");
@@ -223,6 +226,36 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
 }
 
 }  // namespace mb
+
+namespace mb {
+template <class T>
+__global__ void k_backbone_sites(Geom<T> g, long long n_total, const T* __restrict__ center, const T* __restrict__ quat, T* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_total) return;
+  T q[4];
+  const Nuc<T> nu = load_nuc(center, quat, idx, q);
+  const V3<T> b = site(nu, g.back[0], g.back[1], g.back[2]);
+  out[3 * idx] = b.x;
+  out[3 * idx + 1] = b.y;
+  out[3 * idx + 2] = b.z;
+}
+template <class T>
+static int backbone_sites_impl(cudaStream_t s, const mb_model* m, int64_t n_total, const void* center, const void* quat, void* out) {
+  MB_REQUIRE(m && center && quat && out && n_total > 0, MB_EINVAL_SHAPE, "backbone_sites: missing arguments");
+  Geom<T> g;
+  g.load(m->geom[0]);
+  k_backbone_sites<T><<<ceil_div(n_total, 256), 256, 0, s>>>(g, n_total, static_cast<const T*>(center), static_cast<const T*>(quat),
+                                                              static_cast<T*>(out));
+  MB_CUDA_CHECK(cudaGetLastError());
+  return MB_OK;
+}
+}  // namespace mb
+extern "C" int mythos_b200_backbone_sites_f64(void* stream, const mb_model* m, int64_t n_total, const void* center, const void* quat, void* out) {
+  return mb::backbone_sites_impl<double>(static_cast<cudaStream_t>(stream), m, n_total, center, quat, out);
+}
+extern "C" int mythos_b200_backbone_sites_f32(void* stream, const mb_model* m, int64_t n_total, const void* center, const void* quat, void* out) {
+  return mb::backbone_sites_impl<float>(static_cast<cudaStream_t>(stream), m, n_total, center, quat, out);
+}
 
 extern "C" size_t mythos_b200_energy_workspace_bytes(int32_t n, int32_t n_frames, int64_t pair_capacity, int32_t real_bytes) {
   if (n <= 0 || n_frames <= 0 || pair_capacity <= 0) return 0;

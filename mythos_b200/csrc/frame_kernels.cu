@@ -568,17 +568,27 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
     // the row's two runs as start | length << 16, cell coordinates 10 bits each)
     unsigned st_a = unsigned(threadIdx.x) | (1u << 24), st_kl = 0u, st_r0 = 0u, st_r1 = 0u, st_c = 0u;
     // list mode: the NEXT producer step's entries (i | j << 16, all ones = none) are loaded one step ahead, so that the
-    // list, which streams from HBM, is never waited for
+    // list, which streams from HBM, is never waited for.  Tagged lists (MB_NL_TAG_SUPPORTS: the neighbour build already
+    // split the pairs by the terms' supports) pack i | j << 14 | Debye tag << 28 | short-range tag << 29.
+    const bool tagged = a.tagged != 0;
+    auto load_entry = [&](long long k) -> uint32_t {
+      if (k >= count) return 0xffffffffu;
+      const int i = pl[k];
+      int j = pl[a.pair_capacity + k];
+      uint32_t tg = 0u;
+      if (tagged) {
+        tg = (uint32_t(j) >> 29) & 3u;  // bit 0: second sites inside the Debye cutoff, bit 1: centres inside the short-range cutoff
+        j &= 0x1fffffff;
+      }
+      if (!(i >= 0 && j >= 0 && i < n && j < n)) return 0xffffffffu;
+      return tagged ? (uint32_t(i) | (uint32_t(j) << 14) | (tg << 28)) : (uint32_t(i) | (uint32_t(j) << 16));
+    };
     uint32_t pf[kSlice];
     if (!cells) {
 #pragma unroll
       for (int u = 0; u < kSlice; ++u) {
         const long long k = threadIdx.x + (long long)u * kFB;
-        pf[u] = 0xffffffffu;
-        if (k < count) {
-          const int i = pl[k], j = pl[a.pair_capacity + k];
-          if (i >= 0 && j >= 0 && i < n && j < n) pf[u] = uint32_t(i) | (uint32_t(j) << 16);
-        }
+        pf[u] = load_entry(k);
       }
     }
     const int n_rows = cells ? half_shell_rows(grid->S) : 0;
@@ -734,15 +744,12 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
 #pragma unroll
         for (int u = 0; u < kSlice; ++u) {
           const uint32_t cur = pf[u];
-          {  // issue the next step's loads before touching this step's entries
-            const long long k = base + threadIdx.x + (long long)u * kFB;
-            pf[u] = 0xffffffffu;
-            if (k < count) {
-              const int i2 = pl[k], j2 = pl[a.pair_capacity + k];
-              if (i2 >= 0 && j2 >= 0 && i2 < n && j2 < n) pf[u] = uint32_t(i2) | (uint32_t(j2) << 16);
-            }
-          }
-          if (cur != 0xffffffffu) {
+          pf[u] = load_entry(base + threadIdx.x + (long long)u * kFB);  // next step's loads first
+          if (cur != 0xffffffffu && tagged) {
+            found[u] = (cur & 0x3fffu) | (((cur >> 14) & 0x3fffu) << 16);
+            if (want_debye && (cur & (1u << 28))) acc_db |= 1u << u;
+            if (want_sr && (cur & (1u << 29))) acc_sr |= 1u << u;
+          } else if (cur != 0xffffffffu) {
             const int i = int(cur & 0xffffu), j = int(cur >> 16);
             {
               found[u] = cur;
@@ -919,7 +926,7 @@ static bool pick_layout(const EnergyDev<T>& a, bool wp, bool* cache_back, FrameS
 
 template <class T>
 bool frame_kernel_eligible(const EnergyDev<T>& a) {
-  if (a.M.n_banks != 1 || a.n > 60000) return false;  // 16-bit indices, with headroom for the producer stream position
+  if (a.M.n_banks != 1 || a.n > 60000 || (a.tagged && a.n >= 16384)) return false;  // 16-bit indices, with headroom for the producer stream position
   bool cb;
   FrameSmem L;
   return pick_layout(a, true, &cb, &L);

@@ -169,21 +169,38 @@ class CellListPairs:
     workspace: torch.Tensor | None = None
     max_count: int = 0
     in_kernel: bool = False  # True: let the frame-resident kernel find the pairs itself (in-kernel cell list) where it applies
+    # support tagging (MB_NL_TAG_SUPPORTS): (model, short-range centre cutoff, Debye backbone-site cutoff) or None.  With it
+    # the build keeps only pairs inside the support of some term and tags which; the frame-resident kernel then queues
+    # them without touching coordinates.  Used when that kernel applies (one bank, no position gradients).
+    tag: tuple | None = None
+    tagged_capacity: int = 0
+    _last_tagged: bool = False
     _pending: list = dc.field(default_factory=list)
 
-    def chunk(self, sl: slice, center: torch.Tensor):
+    def chunk(self, sl: slice, center: torch.Tensor, quat: torch.Tensor | None = None, tagged: bool = False):
         """Enqueue the build for one chunk of frames; overflow is checked once per pass by ``verify`` (one host sync)."""
         from mythos_b200.utils import neighbors
 
         c = center.detach()
-        if self.capacity <= 0:
-            _, count, _, self.workspace = neighbors.build_pairs(c[:1], self.bonded, self.box, self.r_cutoff, 0.0, 1, self.workspace)
-            self.capacity = (max(int(int(count.max().item()) * 1.06) + 64, 64) + 3) // 4 * 4  # multiple of 4: 128-bit pair stores
+        tagged = bool(tagged and self.tag is not None and quat is not None)
+        self._last_tagged = tagged
+        kw = {}
+        if tagged:
+            model, r_inner, r_site2 = self.tag
+            kw = dict(site2=backbone_sites(model, c, quat.detach()), r_inner=r_inner, r_site2=r_site2)
+        cap_attr = "tagged_capacity" if tagged else "capacity"
+        if getattr(self, cap_attr) <= 0:
+            kw1 = dict(kw)
+            if tagged:
+                kw1["site2"] = kw["site2"][:1]
+            _, count, _, self.workspace = neighbors.build_pairs(c[:1], self.bonded, self.box, self.r_cutoff, 0.0, 1, self.workspace, **kw1)
+            setattr(self, cap_attr, (max(int(int(count.max().item()) * 1.06) + 64, 64) + 3) // 4 * 4)  # multiple of 4: 128-bit pair stores
+        cap = getattr(self, cap_attr)
         pairs, count, overflow, self.workspace = neighbors.build_pairs(
-            c, self.bonded, self.box, self.r_cutoff, 0.0, self.capacity, self.workspace
+            c, self.bonded, self.box, self.r_cutoff, 0.0, cap, self.workspace, **kw
         )
         self._pending.append((count, overflow))
-        return pairs, 2 * self.capacity, count
+        return pairs, 2 * cap, count
 
     def verify(self) -> bool:
         """True if every list built since the last call fitted its capacity; otherwise grows the capacity."""
@@ -195,10 +212,21 @@ class CellListPairs:
         if flags & 2:
             raise _lib.MythosB200Error("neighbour build: a nucleotide has more than 4 bonded partners")
         self.max_count = max(self.max_count, worst)
-        if worst <= self.capacity:
+        cap_attr = "tagged_capacity" if self._last_tagged else "capacity"
+        if worst <= getattr(self, cap_attr):
             return True
-        self.capacity = (int(worst * 1.06) + 64 + 3) // 4 * 4  # jax_md would report did_buffer_overflow; here the pass re-runs
+        setattr(self, cap_attr, (int(worst * 1.06) + 64 + 3) // 4 * 4)  # jax_md would report did_buffer_overflow; here the pass re-runs
         return False
+
+
+def backbone_sites(model, center: torch.Tensor, quat: torch.Tensor) -> torch.Tensor:
+    """(F,N,3) backbone interaction sites of (center, quat) for a single-flavour model (one fused kernel)."""
+    out = torch.empty_like(center)
+    fn = getattr(_lib.lib(), f"mythos_b200_backbone_sites_{_lib.suffix(center.dtype)}")
+    with torch.cuda.device(center.device):
+        _lib.check(fn(_lib.current_stream(center.device), C.pointer(model), center.shape[0] * center.shape[1],
+                      center.contiguous().data_ptr(), quat.to(center.dtype).contiguous().data_ptr(), out.data_ptr()), "mythos_b200_backbone_sites")
+    return out
 
 
 FRAME_CHUNK = int(os.environ.get("MYTHOS_B200_FRAME_CHUNK", "1184"))  # frames per launch group (8 waves of one CTA per SM); bounds the pair-list buffer (~1.2 GB at N=2k)
@@ -224,14 +252,27 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
             if getattr(err, "status", None) != 3:  # MB_ECAPACITY: frame too large for shared memory -> device lists
                 raise
             source.in_kernel = False
+    tagged = (isinstance(source, CellListPairs) and source.tag is not None and not want_pos and model.n_banks == 1
+              and center.shape[1] < 16384 and not (flags & (_lib.FLAG_GENERIC_KERNEL | _lib.FLAG_LIST_KERNEL)))
     while True:
         outs = []
-        for sl in _chunks(center.shape[0], source):
-            pairs, stride, count = source.chunk(sl, center[sl])
-            outs.append(
-                _launch(model, topo, center[sl], quat[sl], params, pairs, stride, term_mask,
-                        None if cot is None else cot[sl], want_terms, want_pos, want_par, per_frame_par, count, flags)
-            )
+        try:
+            for sl in _chunks(center.shape[0], source):
+                if tagged:
+                    pairs, stride, count = source.chunk(sl, center[sl], quat[sl], tagged=True)
+                else:
+                    pairs, stride, count = source.chunk(sl, center[sl])
+                outs.append(
+                    _launch(model, topo, center[sl], quat[sl], params, pairs, stride, term_mask,
+                            None if cot is None else cot[sl], want_terms, want_pos, want_par, per_frame_par, count,
+                            flags | (_lib.FLAG_TAGGED_PAIRS if tagged else 0))
+                )
+        except _lib.MythosB200Error as err:
+            if not tagged or getattr(err, "status", None) != 3:  # MB_ECAPACITY: the frame-resident kernel does not apply
+                raise
+            tagged, source.tag = False, None
+            source._pending.clear()
+            continue
         if not isinstance(source, CellListPairs) or source.verify():
             break
     return _merge(outs, want_terms, want_pos, want_par, per_frame_par)

@@ -31,6 +31,9 @@ def build_pairs(
     workspace: torch.Tensor | None = None,
     rows: bool = False,
     max_row: torch.Tensor | None = None,
+    site2: torch.Tensor | None = None,
+    r_inner: float = 0.0,
+    r_site2: float = 0.0,
 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """Raw batched build.  center (F,N,3) on the device -> (pairs (F,2,capacity) int32, count (F,), overflow (1,), workspace).
 
@@ -61,6 +64,10 @@ def build_pairs(
     a.count, a.overflow = count.data_ptr(), overflow.data_ptr()
     a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
     a.flags = _lib.NL_ROWS if rows else 0
+    if site2 is not None:  # support tagging (internal contract with the frame-resident energy kernel)
+        site2 = site2.to(center.dtype).contiguous()
+        a.flags |= _lib.NL_TAG_SUPPORTS
+        a.site2, a.r_inner, a.r_site2 = site2.data_ptr(), float(r_inner), float(r_site2)
     a.max_row = max_row.data_ptr() if (rows and max_row is not None) else None
     fn = getattr(_lib.lib(), f"mythos_b200_nl_build_{_lib.suffix(center.dtype)}")
     with torch.cuda.device(dev):

@@ -158,19 +158,26 @@ def test_frame_resident_kernel_equals_pair_kernel(workload, dtype):
     params = plan.device_params(cd.device, dtype)
     cot = torch.tensor(np.random.default_rng(1).uniform(0.5, 1.5, size=(len(c), 8)), device=DEV, dtype=dtype)
     outs = []
-    for flags, in_kernel in ((0, True), (_lib.FLAG_GENERIC_KERNEL, False), (0, False)):
-        # 0/True: frame kernel finds its own pairs (shared-memory cell list); GENERIC: device lists + pair kernels;
-        # 0/False: device lists (rows layout) streamed through the frame kernel (the default)
+    for flags, in_kernel, tagged in ((0, True, False), (_lib.FLAG_GENERIC_KERNEL, False, False), (0, False, False), (0, False, True)):
+        # in_kernel: frame kernel finds its own pairs (shared-memory cell list); GENERIC: device lists + pair kernels;
+        # plain: device lists streamed through the frame kernel; tagged (the default): the neighbour build keeps only pairs
+        # inside the support of some term and tags which, the frame kernel queues them without touching coordinates
         src = plan.pairs(cd.device, topo)
         src.in_kernel = in_kernel
+        assert src.tag is not None
+        if not tagged:
+            src.tag = None
         terms, _, _, J = functional.energy_and_gradients(plan.model, topo, cd, qd, params, src, cot=cot, want_pos_grad=False,
                                                          want_param_grad=True, per_frame_param_grad=True, flags=flags)
+        if tagged:
+            assert src.tagged_capacity > 0 and src.tag is not None  # the tagged route really ran
         outs.append((terms.cpu().numpy(), J.cpu().numpy()))
     tol = 1e-11 if dtype == torch.float64 else 2e-4
     np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=tol, atol=tol * np.abs(outs[1][0]).max())
     np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=tol, atol=tol * np.abs(outs[1][1]).max())
-    np.testing.assert_allclose(outs[2][0], outs[1][0], rtol=tol, atol=tol * np.abs(outs[1][0]).max())
-    np.testing.assert_allclose(outs[2][1], outs[1][1], rtol=tol, atol=tol * np.abs(outs[1][1]).max())
+    for k in (2, 3):
+        np.testing.assert_allclose(outs[k][0], outs[1][0], rtol=tol, atol=tol * np.abs(outs[1][0]).max())
+        np.testing.assert_allclose(outs[k][1], outs[1][1], rtol=tol, atol=tol * np.abs(outs[1][1]).max())
 
 
 @pytest.mark.parametrize("in_kernel", [False, True])
