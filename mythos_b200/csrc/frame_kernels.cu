@@ -53,9 +53,10 @@ struct FrameSmem {
   // byte offsets into dynamic shared memory; computed on the host and passed as a kernel parameter so that the
   // kernel re-reads them from the constant bank instead of rematerialising the whole chain under register pressure
   unsigned c, q, back, p, acc, e, flags, q_nl, q_sr, q_bp, q_cx, wcnt, ctr, cstart, corder, excl, grid, total;
+  int acc_rows;  // copies of the parameter-gradient image: warps are spread over them so that their shared-memory atomics do not collide
 };
 template <class T>
-inline FrameSmem frame_smem_layout(int n, bool wp, bool cache_back, bool cells) {
+inline FrameSmem frame_smem_layout(int n, bool wp, bool cache_back, bool cells, int acc_rows) {
   FrameSmem L;
   unsigned off = 0;
   auto take = [&](size_t bytes) {
@@ -67,7 +68,8 @@ inline FrameSmem frame_smem_layout(int n, bool wp, bool cache_back, bool cells) 
   L.q = take(sizeof(T) * 4 * n);
   L.back = take(cache_back ? sizeof(T) * 3 * n : 0);
   L.p = take(sizeof(T) * MB_P_COUNT);
-  L.acc = take(wp ? sizeof(T) * MB_P_COUNT : 0);
+  L.acc_rows = acc_rows;
+  L.acc = take(wp ? sizeof(T) * MB_P_COUNT * acc_rows : 0);
   L.e = take(sizeof(T) * MB_N_TERMS * kFWarps);
   L.flags = take(n);
   L.q_nl = take(sizeof(uint32_t) * kNlCap);
@@ -304,10 +306,9 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   const long long fbase = (long long)frame * n;
   for (int k = threadIdx.x; k < 3 * n; k += kFB) sC[k] = a.center[3 * fbase + k];
   for (int k = threadIdx.x; k < 4 * n; k += kFB) sQ[k] = a.quat[4 * fbase + k];
-  for (int k = threadIdx.x; k < MB_P_COUNT; k += kFB) {
-    sP[k] = a.params[k];
-    if (WP) sAcc[k] = T(0);
-  }
+  for (int k = threadIdx.x; k < MB_P_COUNT; k += kFB) sP[k] = a.params[k];
+  if (WP)
+    for (int k = threadIdx.x; k < MB_P_COUNT * L.acc_rows; k += kFB) sAcc[k] = T(0);
   for (int k = threadIdx.x; k < n; k += kFB)
     sF[k] = (unsigned char)((a.seq[k] & 3) | ((a.is_end && a.is_end[k]) ? 4 : 0));
   if (threadIdx.x < 8) ctr[threadIdx.x] = 0;
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   T e[MB_N_TERMS];
 #pragma unroll
   for (int t = 0; t < MB_N_TERMS; ++t) e[t] = T(0);
-  SmemAcc<T> sacc{sAcc, false};
+  SmemAcc<T> sacc{sAcc + ((warp * L.acc_rows) / kFWarps) * MB_P_COUNT, false};  // this warp's copy of the image
   NullAcc nacc;
   NucGrad<T> G0, G1;  // unused (WF = false) but required by the pair drivers' signatures
 
@@ -903,7 +904,8 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   if (WP) {
     T* out = a.d_params + (long long)frame * a.d_params_frame_stride;
     for (int p = threadIdx.x; p < MB_P_COUNT; p += kFB) {
-      const T v = sAcc[p];
+      T v = T(0);
+      for (int r = 0; r < L.acc_rows; ++r) v += sAcc[r * MB_P_COUNT + p];
       if (v != T(0)) atomicAdd(&out[p], v);
     }
   }
@@ -915,10 +917,12 @@ static bool pick_layout(const EnergyDev<T>& a, bool wp, bool* cache_back, FrameS
   if ((long long)a.n * 11 * (long long)sizeof(T) > 227 * 1024) return false;
   if (cells && (size_t)a.n * 4 > sizeof(uint32_t) * (kSrCap + 2 * kQCap)) return false;  // sCell aliases the SR/BP/CX queues
   for (int cb = 1; cb >= 0; --cb) {
-    *L = frame_smem_layout<T>(a.n, wp, cb != 0, cells);
-    if (L->total <= 227u * 1024u) {
-      *cache_back = cb != 0;
-      return true;
+    for (int rows = wp ? kFWarps : 1; rows >= 1; rows >>= 1) {  // as many image copies as fit (16 = one per warp)
+      *L = frame_smem_layout<T>(a.n, wp, cb != 0, cells, rows);
+      if (L->total <= 227u * 1024u) {
+        *cache_back = cb != 0;
+        return true;
+      }
     }
   }
   return false;

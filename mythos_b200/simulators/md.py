@@ -269,9 +269,19 @@ class MDSimulator:
             one_step()  # first step eagerly (phase 0: opening half kick only)
             if n_steps > 1:
                 one_step()  # warm the allocator for the steady-state shape
-            graph = None
             done = min(2, n_steps)
-            if n_steps > 2:
+            # steady state: graphs of `block` steps (one host launch per block keeps the replay loop off the CPU's
+            # critical path), then single-step replays for the remainder
+            block = 16
+            if n_steps - done >= 2 * block:
+                big = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(big, stream=stream):
+                    for _ in range(block):
+                        one_step()
+                for _ in range((n_steps - done) // block):
+                    big.replay()
+                done += ((n_steps - done) // block) * block
+            if n_steps > done:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=stream):
                     one_step()
