@@ -405,14 +405,15 @@ typedef struct mb_nl_args {
   uint32_t flags;         /* MB_NL_* */
   uint32_t _pad;
   int32_t* max_row;       /* rows mode: out (F) longest row found (to size the rows), or NULL */
-  const void* site2;      /* MB_NL_TAG_SUPPORTS: (F,N,3) second site of each nucleotide (the backbone site) */
-  double r_inner;         /* MB_NL_TAG_SUPPORTS: inner centre cutoff (short-range terms)                     */
-  double r_site2;         /* MB_NL_TAG_SUPPORTS: cutoff on the second-site distance (Debye-Hueckel)          */
+  uint32_t tag_bits;      /* MB_NL_TAG_SUPPORTS: OR-ed into pairs[1][k] of every pair written (top 3 bits only)     */
+  uint32_t _pad2;
+  const int32_t* append_count; /* MB_NL_TAG_SUPPORTS: (F) entries already in each frame's list; this build appends after
+                                * them and `count` receives the new totals (may alias append_count), or NULL      */
 } mb_nl_args;
-#define MB_NL_TAG_SUPPORTS 0x2u /* internal contract with mythos_b200_energy_* (MB_FLAG_TAGGED_PAIRS): of the pairs inside
-                         * r_cutoff keep only those whose centres are inside r_inner (bit 30 of pairs[1][k] set) or whose
-                         * second sites are inside r_site2 (bit 29 set); the index is pairs[1][k] & 0x1fffffff.  Not the
-                         * reference's pair set: every dropped pair contributes exactly zero to every term.           */
+#define MB_NL_TAG_SUPPORTS 0x2u /* internal contract with mythos_b200_energy_* (MB_FLAG_TAGGED_PAIRS): `tag_bits` are OR-ed
+                         * into pairs[1][k] (the index is pairs[1][k] & 0x1fffffff) and the build may append to a list.  The
+                         * host builds the centres at the short-range cutoff (bit 30) and the backbone sites at the Debye
+                         * cutoff (bit 29) into one list: only pairs inside the support of some term, labelled with it.  */
 #define MB_NL_ROWS 0x1u /* one-pass build: instead of a compact list, row k-major slots of width capacity / n per nucleotide
                          * (entry k * n + p = k-th partner of the p-th nucleotide in cell order), unused slots = n (the
                          * padding value); *overflow bit 0 is set if a row is too narrow; count = pairs found.  Consumers

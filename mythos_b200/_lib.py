@@ -123,9 +123,9 @@ class NlArgs(C.Structure):
         ("flags", C.c_uint32),
         ("_pad", C.c_uint32),
         ("max_row", C.c_void_p),
-        ("site2", C.c_void_p),
-        ("r_inner", C.c_double),
-        ("r_site2", C.c_double),
+        ("tag_bits", C.c_uint32),
+        ("_pad2", C.c_uint32),
+        ("append_count", C.c_void_p),
     ]
 
 

@@ -22,10 +22,11 @@
 //   7. scan      exclusive scan of the per-nucleotide counts -> offsets; per-frame totals -> count[frame]
 //   8. fill      same walk replaying the accept bits the count pass recorded (no coordinates, no arithmetic), writing
 //                (min(i,j), max(i,j)) at the nucleotide's offset four pairs per 128-bit store; tail padded with N
-// Support tagging (MB_NL_TAG_SUPPORTS, an internal contract with this library's energy kernels): given a second site per
-// nucleotide (the backbone site), a pair is kept only if its centres are inside an inner cutoff (tag bit 30 of the
-// second index) or its second sites inside their own cutoff (tag bit 29) -- the exact supports of the short-range terms
-// and of Debye-Hueckel; everything else contributes exactly zero and is dropped before it is ever written.
+// Support tags (MB_NL_TAG_SUPPORTS, an internal contract with this library's frame-resident energy kernel): the build ORs
+// constant tag bits into the second index of every pair it writes and can append after the entries a previous build left
+// in the same list.  The host runs it twice -- on the centres with the short-range cutoff (tag bit 30) and on the backbone
+// sites with the Debye-Hueckel cutoff (tag bit 29) -- so that only pairs inside the support of some term are ever
+// written, each already labelled with the phase queue it belongs to; every other pair contributes exactly zero.
 // Rows mode (MB_NL_ROWS) replaces 6-8 by ONE walk that writes a fixed-width row per nucleotide with the unused slots set
 // to the padding value N: still a valid OrderedSparse list (consumers mask entries >= N wherever they are), at half the
 // cost -- the shape the energy kernels of this library are fed with.
@@ -60,12 +61,6 @@ struct alignas(16) NlRec<float> {
   int32_t id;
 };
 
-// second site of a nucleotide in cell order (support tagging)
-template <class T>
-struct alignas(16) NlSite {
-  T x, y, z, pad;
-};
-
 template <class T>
 struct NlDev {
   int n, n_frames, n_bonded, cmax;  // cmax = cell-table entries per frame
@@ -80,8 +75,8 @@ struct NlDev {
   int32_t* count;
   int32_t* overflow;
   int32_t* max_row;  // rows mode: (F) longest row found, or nullptr
-  const T* site2;    // support tagging: (F,N,3) second site of each nucleotide, or nullptr
-  T inner2, site2cut2;  // squares of the inner centre cutoff and of the site-2 cutoff
+  uint32_t tag_bits;             // OR-ed into the second index of every pair written (MB_NL_TAG_SUPPORTS)
+  const int32_t* append_count;   // (F) entries already in each frame's list: this build appends after them, or nullptr
   // workspace
   int32_t* excl;       // (N, kMaxExcl)
   unsigned long long* bounds;  // (F, 6) ordered-integer min / max corners
@@ -92,8 +87,7 @@ struct NlDev {
   int32_t* tmp_order;  // (F*N) ids in cell order, unsorted inside a cell
   NlRec<T>* srec;      // (F*N) cell-ordered (coordinates, id), ids ascending inside a cell
   int32_t* nbcount;    // (F*N + 1) per-nucleotide pair counts (cell order), then exclusive scan
-  uint32_t* bitbuf;    // (2 * kNlBitWords, F*N) accept bits of the count pass, word-major (second half: site-2 tags)
-  NlSite<T>* srec2;    // (F*N) cell-ordered second sites (support tagging)
+  uint32_t* bitbuf;    // (kNlBitWords, F*N) accept bits of the count pass, word-major
   int32_t* scan_tmp;   // block sums of the multi-block scan
 };
 
@@ -345,14 +339,6 @@ __global__ void k_nl_rank(NlDev<T> a) {
   r.z = ctr[2];
   r.id = id;
   a.srec[lo + rank] = r;
-  if (a.site2) {
-    const T* s2 = a.site2 + 3 * ((long long)f * a.n + id);
-    NlSite<T> t{};
-    t.x = s2[0];
-    t.y = s2[1];
-    t.z = s2[2];
-    a.srec2[lo + rank] = t;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------ walk
@@ -368,7 +354,7 @@ __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, 
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
 
 // MODE 0: count, 1: fill (compact list), 2: rows (one pass: fixed-width row per nucleotide, slot-major)
-template <class T, int MODE, bool PERIODIC, bool TAG>
+template <class T, int MODE, bool PERIODIC>
 __global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
   constexpr bool FILL = MODE == 1, ROWS = MODE == 2;
   const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,7 +378,7 @@ __global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
   int32_t* out0 = nullptr;
   int32_t* out1 = nullptr;
   if (FILL) {
-    wpos = a.nbcount[pos] - a.nbcount[(long long)f * a.n];
+    wpos = a.nbcount[pos] - a.nbcount[(long long)f * a.n] + (a.append_count ? a.append_count[f] : 0);
     out0 = a.pairs + (long long)f * 2 * a.capacity;
     out1 = out0 + a.capacity;
   }
@@ -408,11 +394,8 @@ __global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
   unsigned bw = 0u;  // current word of accept bits
   // accept test of one candidate record; receiver = lower index (OrderedSparse keeps i < j): dR = R_low - R_high, as the
   // reference evaluates it (in free space the two orders give exact negatives, whose squares are identical)
-  NlSite<T> me2{};
-  if (TAG) me2 = a.srec2[pos];
-  unsigned bw2 = 0u;  // TAG: current word of site-2 tags (bw then holds the inner-centre tags)
-  unsigned tags = 0u; // TAG: tags of the candidate accept() looked at last (bit 30 centre inside inner, bit 29 site 2 inside)
-  auto accept = [&](const NlRec<T>& c, long long q, int& j, bool& me_low) -> bool {
+  const int tag_bits = int(a.tag_bits);
+  auto accept = [&](const NlRec<T>& c, int& j, bool& me_low) -> bool {
     j = c.id;
     me_low = i < j;
     T ddx = xi - c.x, ddy = yi - c.y, ddz = zi - c.z;
@@ -427,22 +410,7 @@ __global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
       ddz = wrap_nl(ddz, a.box[2]);
     }
     const T d2 = add_rn(add_rn(mul_rn(ddx, ddx), mul_rn(ddy, ddy)), mul_rn(ddz, ddz));
-    const bool in = d2 < a.cut2 && j != ex[0] && j != ex[1] && j != ex[2] && j != ex[3];
-    if (!TAG) return in;
-    // support tagging: keep the pair only if its centres are inside the inner cutoff or its second sites inside theirs
-    tags = 0u;
-    if (in) {
-      if (d2 < a.inner2) tags |= 1u << 30;
-      const NlSite<T> o = a.srec2[q];
-      T ex_ = me2.x - o.x, ey_ = me2.y - o.y, ez_ = me2.z - o.z;
-      if (PERIODIC) {
-        ex_ = wrap_nl(ex_, a.box[0]);
-        ey_ = wrap_nl(ey_, a.box[1]);
-        ez_ = wrap_nl(ez_, a.box[2]);
-      }
-      if (ex_ * ex_ + ey_ * ey_ + ez_ * ez_ < a.site2cut2) tags |= 1u << 29;
-    }
-    return tags != 0u;
+    return d2 < a.cut2 && j != ex[0] && j != ex[1] && j != ex[2] && j != ex[3];
   };
   // fill pass: accepted pairs go out four at a time as 128-bit stores once the write position is 16-byte aligned
   int l0 = 0, l1 = 0, l2 = 0, l3 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0, nbuf = 0;
@@ -516,25 +484,19 @@ __global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
             for (; q < re[run]; ++q) {
               int j;
               bool me_low;
-              if (accept(a.srec[q], q, j, me_low)) emit(me_low ? i : j, (me_low ? j : i) | int(tags));
+              if (accept(a.srec[q], j, me_low)) emit(me_low ? i : j, (me_low ? j : i) | tag_bits);
             }
             break;
           }
-          if ((ci & 31) == 0) {
-            bw = a.bitbuf[(long long)(ci >> 5) * R + pos];
-            if (TAG) bw2 = a.bitbuf[(long long)(kNlBitWords + (ci >> 5)) * R + pos];
-          }
+          if ((ci & 31) == 0) bw = a.bitbuf[(long long)(ci >> 5) * R + pos];
           int avail = 32 - (ci & 31);
           avail = avail < re[run] - q ? avail : re[run] - q;
-          const unsigned window = avail == 32 ? 0xffffffffu : ((1u << avail) - 1u);
-          const unsigned m1 = (bw >> (ci & 31)) & window, m2 = TAG ? (bw2 >> (ci & 31)) & window : 0u;
-          unsigned m = m1 | m2;
+          unsigned m = (bw >> (ci & 31)) & (avail == 32 ? 0xffffffffu : ((1u << avail) - 1u));
           while (m) {
             const int bit = __ffs(m) - 1;
             m &= m - 1u;
             const int j = a.srec[q + bit].id;
-            const int tg = TAG ? int((((m1 >> bit) & 1u) << 30) | (((m2 >> bit) & 1u) << 29)) : 0;
-            emit(i < j ? i : j, (i < j ? j : i) | tg);
+            emit(i < j ? i : j, (i < j ? j : i) | tag_bits);
           }
           q += avail;
           ci += avail;
@@ -552,19 +514,13 @@ __global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
             int j;
             bool me_low;
             const bool in = q0 + u < re[run];
-            const bool ok = accept(c[u], q0 + u < re[run] ? q0 + u : re[run] - 1, j, me_low) && in;
+            const bool ok = accept(c[u], j, me_low) && in;
             if (MODE == 0 && in) {  // record the decision for the fill pass
               if (ci < kNlBitCap) {
-                if (TAG) {
-                  bw |= ((tags >> 30) & 1u) << (ci & 31);
-                  bw2 |= ((tags >> 29) & 1u) << (ci & 31);
-                } else {
-                  bw |= (ok ? 1u : 0u) << (ci & 31);
-                }
+                bw |= (ok ? 1u : 0u) << (ci & 31);
                 if ((ci & 31) == 31) {
                   a.bitbuf[(long long)(ci >> 5) * R + pos] = bw;
-                  if (TAG) a.bitbuf[(long long)(kNlBitWords + (ci >> 5)) * R + pos] = bw2;
-                  bw = bw2 = 0u;
+                  bw = 0u;
                 }
               }
               ++ci;
@@ -581,10 +537,7 @@ __global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
       }
     }
   }
-  if (MODE == 0 && (ci & 31) != 0 && ci < kNlBitCap) {
-    a.bitbuf[(long long)(ci >> 5) * R + pos] = bw;
-    if (TAG) a.bitbuf[(long long)(kNlBitWords + (ci >> 5)) * R + pos] = bw2;
-  }
+  if (MODE == 0 && (ci & 31) != 0 && ci < kNlBitCap) a.bitbuf[(long long)(ci >> 5) * R + pos] = bw;
   if (FILL) {  // the last 1..3 buffered pairs
     const int lo_[4] = {l0, l1, l2, l3}, hi_[4] = {h0, h1, h2, h3};
 #pragma unroll
@@ -650,7 +603,7 @@ template <class T>
 __global__ void k_nl_finish(NlDev<T> a) {
   // pad the tail with N and publish count / overflow
   const int f = blockIdx.y;
-  const int total = a.nbcount[(long long)(f + 1) * a.n] - a.nbcount[(long long)f * a.n];
+  const int total = a.nbcount[(long long)(f + 1) * a.n] - a.nbcount[(long long)f * a.n] + (a.append_count ? a.append_count[f] : 0);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.count[f] = total;
     if (total > a.capacity) atomicOr(a.overflow, 1);
@@ -699,10 +652,8 @@ static size_t carve(NlDev<T>* a, void* ws, int n, int F) {
   if (a) a->srec = static_cast<NlRec<T>*>(p);
   p = take(sizeof(int32_t) * (R + 1));
   if (a) a->nbcount = static_cast<int32_t*>(p);
-  p = take(sizeof(uint32_t) * 2 * kNlBitWords * R);
+  p = take(sizeof(uint32_t) * kNlBitWords * R);
   if (a) a->bitbuf = static_cast<uint32_t*>(p);
-  p = take(sizeof(NlSite<double>) * R);
-  if (a) a->srec2 = static_cast<NlSite<T>*>(p);
   const size_t longest = (F * C + 1 > R + 1) ? F * C + 1 : R + 1;
   p = take(sizeof(int32_t) * (longest / kScanChunk + 2));
   if (a) a->scan_tmp = static_cast<int32_t*>(p);
@@ -740,12 +691,10 @@ static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
   a.overflow = x->overflow;
   a.max_row = (x->flags & MB_NL_ROWS) ? x->max_row : nullptr;
   const bool tag = (x->flags & MB_NL_TAG_SUPPORTS) != 0;
-  MB_REQUIRE(!tag || (x->site2 && !(x->flags & MB_NL_ROWS)), MB_EINVAL_SHAPE, "nl_build: support tagging needs site2 and the compact layout");
-  MB_REQUIRE(!tag || x->n < (1 << 29), MB_EINVAL_SHAPE, "nl_build: support tagging needs n < 2^29");
-  a.site2 = tag ? static_cast<const T*>(x->site2) : nullptr;
-  a.inner2 = T(x->r_inner) * T(x->r_inner);
-  a.site2cut2 = T(x->r_site2) * T(x->r_site2);
-  MB_REQUIRE(!(x->flags & MB_NL_ROWS) || x->capacity >= x->n, MB_EINVAL_SHAPE, "nl_build: rows mode needs capacity >= n");
+  MB_REQUIRE(!tag || !(x->flags & MB_NL_ROWS), MB_EINVAL_SHAPE, "nl_build: support tags need the compact layout");
+  MB_REQUIRE(!tag || (x->n < (1 << 29) && !(x->tag_bits & 0x1fffffffu)), MB_EINVAL_SHAPE, "nl_build: tag bits must be in the top 3 bits, n < 2^29");
+  a.tag_bits = tag ? x->tag_bits : 0u;
+  a.append_count = tag ? x->append_count : nullptr;
   carve<T>(&a, x->workspace, x->n, x->n_frames);
 
   const int F = x->n_frames, n = x->n;
@@ -769,26 +718,16 @@ static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
   k_nl_rank<T><<<gr, kNlBlock, 0, s>>>(a);
   if (x->flags & MB_NL_ROWS) {
     k_nl_zero_counts<<<ceil_div(F, 256), 256, 0, s>>>(a.count, a.max_row, F);
-    if (periodic) k_nl_walk<T, 2, true, false><<<gr, kNlBlock, 0, s>>>(a);
-    else k_nl_walk<T, 2, false, false><<<gr, kNlBlock, 0, s>>>(a);
+    if (periodic) k_nl_walk<T, 2, true><<<gr, kNlBlock, 0, s>>>(a);
+    else k_nl_walk<T, 2, false><<<gr, kNlBlock, 0, s>>>(a);
     if (x->capacity % n) k_nl_rows_tail<T><<<dim3(1, F), 256, 0, s>>>(a);
   } else {
-    if (tag) {
-      if (periodic) k_nl_walk<T, 0, true, true><<<gr, kNlBlock, 0, s>>>(a);
-      else k_nl_walk<T, 0, false, true><<<gr, kNlBlock, 0, s>>>(a);
-    } else {
-      if (periodic) k_nl_walk<T, 0, true, false><<<gr, kNlBlock, 0, s>>>(a);
-      else k_nl_walk<T, 0, false, false><<<gr, kNlBlock, 0, s>>>(a);
-    }
+    if (periodic) k_nl_walk<T, 0, true><<<gr, kNlBlock, 0, s>>>(a);
+    else k_nl_walk<T, 0, false><<<gr, kNlBlock, 0, s>>>(a);
     scan_exclusive(s, a.nbcount, R, a.scan_tmp);
-    if (tag) {
-      if (periodic) k_nl_walk<T, 1, true, true><<<gr, kNlBlock, 0, s>>>(a);
-      else k_nl_walk<T, 1, false, true><<<gr, kNlBlock, 0, s>>>(a);
-    } else {
-      if (periodic) k_nl_walk<T, 1, true, false><<<gr, kNlBlock, 0, s>>>(a);
-      else k_nl_walk<T, 1, false, false><<<gr, kNlBlock, 0, s>>>(a);
-    }
-    dim3 gf(F > 64 ? 1 : 32, F);  // only the tail [count, capacity) is touched
+    if (periodic) k_nl_walk<T, 1, true><<<gr, kNlBlock, 0, s>>>(a);
+    else k_nl_walk<T, 1, false><<<gr, kNlBlock, 0, s>>>(a);
+    dim3 gf((F > 64 || a.append_count) ? 1 : 32, F);  // only the tail [count, capacity) is touched; one block when count aliases append_count
     k_nl_finish<T><<<gf, 256, 0, s>>>(a);
   }
   MB_CUDA_CHECK(cudaGetLastError());

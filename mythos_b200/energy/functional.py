@@ -178,29 +178,42 @@ class CellListPairs:
     _pending: list = dc.field(default_factory=list)
 
     def chunk(self, sl: slice, center: torch.Tensor, quat: torch.Tensor | None = None, tagged: bool = False):
-        """Enqueue the build for one chunk of frames; overflow is checked once per pass by ``verify`` (one host sync)."""
+        """Enqueue the build for one chunk of frames; overflow is checked once per pass by ``verify`` (one host sync).
+
+        ``tagged``: two builds into ONE list -- the centres at the short-range cutoff (tag bit 30) and the backbone sites
+        at the Debye-Hueckel cutoff (tag bit 29, appended) -- instead of one build at the full interaction range: only
+        pairs inside the support of some term are written, each labelled with the phase queue it belongs to."""
         from mythos_b200.utils import neighbors
 
         c = center.detach()
         tagged = bool(tagged and self.tag is not None and quat is not None)
         self._last_tagged = tagged
-        kw = {}
-        if tagged:
-            model, r_inner, r_site2 = self.tag
-            kw = dict(site2=backbone_sites(model, c, quat.detach()), r_inner=r_inner, r_site2=r_site2)
-        cap_attr = "tagged_capacity" if tagged else "capacity"
-        if getattr(self, cap_attr) <= 0:
-            kw1 = dict(kw)
-            if tagged:
-                kw1["site2"] = kw["site2"][:1]
-            _, count, _, self.workspace = neighbors.build_pairs(c[:1], self.bonded, self.box, self.r_cutoff, 0.0, 1, self.workspace, **kw1)
-            setattr(self, cap_attr, (max(int(int(count.max().item()) * 1.06) + 64, 64) + 3) // 4 * 4)  # multiple of 4: 128-bit pair stores
-        cap = getattr(self, cap_attr)
-        pairs, count, overflow, self.workspace = neighbors.build_pairs(
-            c, self.bonded, self.box, self.r_cutoff, 0.0, cap, self.workspace, **kw
-        )
+        if not tagged:
+            if self.capacity <= 0:
+                _, count, _, self.workspace = neighbors.build_pairs(c[:1], self.bonded, self.box, self.r_cutoff, 0.0, 1, self.workspace)
+                self.capacity = (max(int(int(count.max().item()) * 1.06) + 64, 64) + 3) // 4 * 4  # multiple of 4: 128-bit pair stores
+            pairs, count, overflow, self.workspace = neighbors.build_pairs(
+                c, self.bonded, self.box, self.r_cutoff, 0.0, self.capacity, self.workspace
+            )
+            self._pending.append((count, overflow))
+            return pairs, 2 * self.capacity, count
+        model, r_sr, r_db = self.tag
+        sites = backbone_sites(model, c, quat.detach()) if r_db > 0 else None
+
+        def both(cc, ss, cap):
+            pairs, count, overflow, self.workspace = neighbors.build_pairs(cc, self.bonded, self.box, max(r_sr, 1e-6), 0.0, cap,
+                                                                           self.workspace, tag_bits=1 << 30)
+            if ss is not None:
+                neighbors.build_pairs(ss, self.bonded, self.box, r_db, 0.0, cap, self.workspace, tag_bits=1 << 29,
+                                      out=(pairs, count, overflow), append=True)
+            return pairs, count, overflow
+
+        if self.tagged_capacity <= 0:
+            _, count, _ = both(c[:1], None if sites is None else sites[:1], 4)
+            self.tagged_capacity = (max(int(int(count.max().item()) * 1.06) + 64, 64) + 3) // 4 * 4
+        pairs, count, overflow = both(c, sites, self.tagged_capacity)
         self._pending.append((count, overflow))
-        return pairs, 2 * cap, count
+        return pairs, 2 * self.tagged_capacity, count
 
     def verify(self) -> bool:
         """True if every list built since the last call fitted its capacity; otherwise grows the capacity."""

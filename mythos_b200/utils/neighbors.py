@@ -31,9 +31,9 @@ def build_pairs(
     workspace: torch.Tensor | None = None,
     rows: bool = False,
     max_row: torch.Tensor | None = None,
-    site2: torch.Tensor | None = None,
-    r_inner: float = 0.0,
-    r_site2: float = 0.0,
+    tag_bits: int = 0,
+    out: tuple | None = None,
+    append: bool = False,
 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """Raw batched build.  center (F,N,3) on the device -> (pairs (F,2,capacity) int32, count (F,), overflow (1,), workspace).
 
@@ -48,9 +48,12 @@ def build_pairs(
     need = int(_lib.lib().mythos_b200_nl_workspace_bytes(N, F))
     if workspace is None or workspace.numel() < need or workspace.device != dev:
         workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-    pairs = torch.empty((F, 2, capacity), dtype=torch.int32, device=dev)
-    count = torch.empty((F,), dtype=torch.int32, device=dev)
-    overflow = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if out is not None:  # caller-owned (pairs, count, overflow): a second, tagged build appending to the same list
+        pairs, count, overflow = out
+    else:
+        pairs = torch.empty((F, 2, capacity), dtype=torch.int32, device=dev)
+        count = torch.empty((F,), dtype=torch.int32, device=dev)
+        overflow = torch.zeros((1,), dtype=torch.int32, device=dev)
     bonded = bonded.to(device=dev, dtype=torch.int32).contiguous().reshape(-1, 2)
     a = _lib.NlArgs()
     a.n, a.n_frames = N, F
@@ -64,10 +67,10 @@ def build_pairs(
     a.count, a.overflow = count.data_ptr(), overflow.data_ptr()
     a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
     a.flags = _lib.NL_ROWS if rows else 0
-    if site2 is not None:  # support tagging (internal contract with the frame-resident energy kernel)
-        site2 = site2.to(center.dtype).contiguous()
+    if tag_bits or append:  # support tags (internal contract with the frame-resident energy kernel)
         a.flags |= _lib.NL_TAG_SUPPORTS
-        a.site2, a.r_inner, a.r_site2 = site2.data_ptr(), float(r_inner), float(r_site2)
+        a.tag_bits = int(tag_bits)
+        a.append_count = count.data_ptr() if append else None
     a.max_row = max_row.data_ptr() if (rows and max_row is not None) else None
     fn = getattr(_lib.lib(), f"mythos_b200_nl_build_{_lib.suffix(center.dtype)}")
     with torch.cuda.device(dev):
