@@ -485,7 +485,10 @@ def main():
     alg_bytes = chunk * (n * 7 * 8 + 8 * u["kept_by_tagged_build"] + 232 * 8 + 64)  # frame + tagged pair list in, J row + terms row out
     roofline = {
         "bound": "fp64", "kernel": "k_frame_energy<double,WP=1> (all terms of a frame; support-tagged pair lists from the device neighbour build)", "achieved": achieved, "peak": best, "unit": "TFLOP/s",
-        "frac": achieved / best if best else None, "traffic": None,
+        "frac": achieved / best if best else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed ncu capture
+        # (profiles/r01_v5_k_frame_energy_details.csv: 542.4 MB + 11.7 MB); other shapes have no capture
+        "traffic": 0.5542e9 if (chunk == 1184 and n == 2040) else None,
         "peak_source": "measured in this run (library FMA micro-benchmark, 148x32 blocks x 256 threads)",
         "kernel_ms_per_launch": k_ms, "frames_per_launch": chunk, "neighbour_build_ms_per_chunk": nl_ms,
         "share_of_step": k_ms / (k_ms + nl_ms),
