@@ -373,10 +373,12 @@ typedef struct mb_energy_args {
                               * the phase-queued list kernels (per-nucleotide records, backbone-site gradient buffer, short-range list);
                               * NULL or too small = the one-thread-per-pair kernels                                        */
   size_t workspace_bytes;
+  const int32_t* pair_split; /* MB_FLAG_TAGGED_PAIRS with the list kernels: (F) entries of each list before this index are
+                              * the short-range pairs, the rest (up to pair_count) the Debye pairs; else NULL              */
 } mb_energy_args;
 #define MB_FLAG_ACCUMULATE 0x1u /* add into the outputs instead of zeroing them first */
 #define MB_FLAG_GENERIC_KERNEL 0x2u /* force the one-thread-per-pair kernels even where the frame-resident kernel applies */
-#define MB_FLAG_TAGGED_PAIRS 0x8u /* `pairs` comes from mythos_b200_nl_build_* with MB_NL_TAG_SUPPORTS (frame-resident kernel only) */
+#define MB_FLAG_TAGGED_PAIRS 0x8u /* `pairs` comes from mythos_b200_nl_build_* with MB_NL_TAG_SUPPORTS (frame-resident kernel, or the list kernels with pair_split) */
 #define MB_FLAG_LIST_KERNEL 0x4u /* explicit lists with forces / several banks: use the phase-queued list kernels even for short lists (needs workspace) */
 
 size_t mythos_b200_energy_workspace_bytes(int32_t n, int32_t n_frames, int64_t pair_capacity, int32_t real_bytes /* 4 or 8 */);
@@ -422,9 +424,12 @@ size_t mythos_b200_nl_workspace_bytes(int32_t n, int32_t n_frames);
 int mythos_b200_nl_build_f64(void* cuda_stream, const mb_nl_args* a);
 int mythos_b200_nl_build_f32(void* cuda_stream, const mb_nl_args* a);
 
-/* backbone interaction sites (F*N,3) of (center, quat): the second site MB_NL_TAG_SUPPORTS wants (single-flavour models) */
-int mythos_b200_backbone_sites_f64(void* cuda_stream, const mb_model* model, int64_t n_total, const void* center, const void* quat, void* out);
-int mythos_b200_backbone_sites_f32(void* cuda_stream, const mb_model* model, int64_t n_total, const void* center, const void* quat, void* out);
+/* backbone interaction sites (F*N,3) of (center, quat), the second point set of the support-tagged neighbour build;
+ * nt_type (N) selects the flavour per nucleotide for the 3-bank model (NULL otherwise) */
+int mythos_b200_backbone_sites_f64(void* cuda_stream, const mb_model* model, int64_t n_total, const void* center, const void* quat,
+                                   void* out, const int32_t* nt_type, int32_t n);
+int mythos_b200_backbone_sites_f32(void* cuda_stream, const mb_model* model, int64_t n_total, const void* center, const void* quat,
+                                   void* out, const int32_t* nt_type, int32_t n);
 
 /* ---- rigid-body Langevin (BAOAB) step -------------------------------------------------------------------------
  * One call = B(dt/2) A(dt/2) O A(dt/2) on the state, i.e. everything of a step up to the force evaluation, or

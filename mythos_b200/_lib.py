@@ -101,6 +101,7 @@ class EnergyArgs(C.Structure):
         ("all_pairs_cutoff", C.c_double),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
+        ("pair_split", C.c_void_p),
     ]
 
 
@@ -174,8 +175,8 @@ _SIGNATURES = {
     "mythos_b200_energy_f64": (C.c_int, [C.c_void_p, C.POINTER(EnergyArgs)]),
     "mythos_b200_energy_f32": (C.c_int, [C.c_void_p, C.POINTER(EnergyArgs)]),
     "mythos_b200_energy_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
-    "mythos_b200_backbone_sites_f64": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "mythos_b200_backbone_sites_f32": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mythos_b200_backbone_sites_f64": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "mythos_b200_backbone_sites_f32": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "mythos_b200_nl_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "mythos_b200_nl_build_f64": (C.c_int, [C.c_void_p, C.POINTER(NlArgs)]),
     "mythos_b200_nl_build_f32": (C.c_int, [C.c_void_p, C.POINTER(NlArgs)]),

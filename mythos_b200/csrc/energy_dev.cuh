@@ -36,7 +36,8 @@ struct EnergyDev {
   unsigned long long* sr_list;  // list kernel workspace: (F, sr_capacity) short-range pairs (i | j << 32)
   int* sr_count;                // (F)
   long long sr_capacity;
-  int tagged;  // `pairs` carries support tags (MB_NL_TAG_SUPPORTS); frame-resident kernel only
+  int tagged;  // `pairs` carries support tags (MB_NL_TAG_SUPPORTS)
+  const int32_t* pair_split;  // tagged lists: (F) entries before it are short-range pairs, after it Debye pairs (list kernels)
 };
 
 // Parameter-gradient accumulator: warp-reduce, then one shared-memory atomic per warp and parameter.

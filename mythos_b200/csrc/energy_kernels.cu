@@ -192,6 +192,7 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
   a.sr_count = nullptr;
   a.sr_capacity = 0;
   a.tagged = (x->flags & MB_FLAG_TAGGED_PAIRS) ? 1 : 0;
+  a.pair_split = x->pair_split;
 
   const size_t np = (size_t)m.n_banks * MB_P_COUNT;
   if (!(x->flags & MB_FLAG_ACCUMULATE)) {
@@ -208,15 +209,16 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
   const bool wf = a.d_center || a.d_quat, wp = a.d_params != nullptr;
   // frame-resident path: one block per frame with the frame staged in shared memory (energies and dE/dparams only)
   if (!wf && !(x->flags & MB_FLAG_GENERIC_KERNEL) && frame_kernel_eligible<T>(a)) return launch_frame_kernel<T>(s, a, wp);
-  MB_REQUIRE(!a.tagged, MB_ECAPACITY, "energy: tagged pair lists need the frame-resident kernel (single bank, no position "
-             "gradients, frame fits in shared memory, n < 16384)");
+  MB_REQUIRE(!a.tagged || (x->pair_split && x->pair_count && x->workspace), MB_ECAPACITY,
+             "energy: tagged pair lists need the frame-resident kernel (single bank, no position gradients, frame fits in "
+             "shared memory, n < 16384) or the list kernels (workspace, pair_count and pair_split)");
   MB_REQUIRE(!(x->all_pairs_cutoff > 0), MB_ECAPACITY,
              "energy: all_pairs_cutoff needs the frame-resident kernel (single bank, no position gradients, frame fits in "
              "shared memory); build a neighbour list with mythos_b200_nl_build_* instead");
   // phase-queued list kernel when the caller lends the workspace it needs; otherwise one thread per pair
   // (short lists -- the 60-bp MD duplex has 7 021 pairs -- are launch-latency bound: one generic launch beats four)
   void* lk = nullptr;
-  if (!(x->flags & MB_FLAG_GENERIC_KERNEL) && x->workspace && ((x->flags & MB_FLAG_LIST_KERNEL) || (long long)x->pair_capacity * x->n_frames >= kListKernelMinPairs) &&
+  if (!(x->flags & MB_FLAG_GENERIC_KERNEL) && x->workspace && (a.tagged || (x->flags & MB_FLAG_LIST_KERNEL) || (long long)x->pair_capacity * x->n_frames >= kListKernelMinPairs) &&
       x->workspace_bytes >= list_workspace_bytes<T>(x->n, x->n_frames, x->pair_capacity))
     lk = x->workspace;
   if (wf && wp) return launch_pairs<T, true, true>(s, a, lk);
@@ -229,32 +231,39 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
 
 namespace mb {
 template <class T>
-__global__ void k_backbone_sites(Geom<T> g, long long n_total, const T* __restrict__ center, const T* __restrict__ quat, T* __restrict__ out) {
+__global__ void k_backbone_sites(Geom<T> g0, Geom<T> g1, const int32_t* __restrict__ nt_type, int n, long long n_total,
+                                 const T* __restrict__ center, const T* __restrict__ quat, T* __restrict__ out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_total) return;
   T q[4];
   const Nuc<T> nu = load_nuc(center, quat, idx, q);
+  const Geom<T>& g = (nt_type && nt_type[idx % n] == 2) ? g1 : g0;
   const V3<T> b = site(nu, g.back[0], g.back[1], g.back[2]);
   out[3 * idx] = b.x;
   out[3 * idx + 1] = b.y;
   out[3 * idx + 2] = b.z;
 }
 template <class T>
-static int backbone_sites_impl(cudaStream_t s, const mb_model* m, int64_t n_total, const void* center, const void* quat, void* out) {
+static int backbone_sites_impl(cudaStream_t s, const mb_model* m, int64_t n_total, const void* center, const void* quat, void* out,
+                               const int32_t* nt_type, int32_t n) {
   MB_REQUIRE(m && center && quat && out && n_total > 0, MB_EINVAL_SHAPE, "backbone_sites: missing arguments");
-  Geom<T> g;
-  g.load(m->geom[0]);
-  k_backbone_sites<T><<<ceil_div(n_total, 256), 256, 0, s>>>(g, n_total, static_cast<const T*>(center), static_cast<const T*>(quat),
-                                                              static_cast<T*>(out));
+  MB_REQUIRE(m->n_banks == 1 || (nt_type && n > 0), MB_EINVAL_SHAPE, "backbone_sites: nt_type (N) required for the 3-bank model");
+  Geom<T> g0, g1;
+  g0.load(m->geom[0]);
+  g1.load(m->geom[1]);
+  k_backbone_sites<T><<<ceil_div(n_total, 256), 256, 0, s>>>(g0, g1, m->n_banks > 1 ? nt_type : nullptr, n > 0 ? n : 1, n_total,
+                                                              static_cast<const T*>(center), static_cast<const T*>(quat), static_cast<T*>(out));
   MB_CUDA_CHECK(cudaGetLastError());
   return MB_OK;
 }
 }  // namespace mb
-extern "C" int mythos_b200_backbone_sites_f64(void* stream, const mb_model* m, int64_t n_total, const void* center, const void* quat, void* out) {
-  return mb::backbone_sites_impl<double>(static_cast<cudaStream_t>(stream), m, n_total, center, quat, out);
+extern "C" int mythos_b200_backbone_sites_f64(void* stream, const mb_model* m, int64_t n_total, const void* center, const void* quat, void* out,
+                                              const int32_t* nt_type, int32_t n) {
+  return mb::backbone_sites_impl<double>(static_cast<cudaStream_t>(stream), m, n_total, center, quat, out, nt_type, n);
 }
-extern "C" int mythos_b200_backbone_sites_f32(void* stream, const mb_model* m, int64_t n_total, const void* center, const void* quat, void* out) {
-  return mb::backbone_sites_impl<float>(static_cast<cudaStream_t>(stream), m, n_total, center, quat, out);
+extern "C" int mythos_b200_backbone_sites_f32(void* stream, const mb_model* m, int64_t n_total, const void* center, const void* quat, void* out,
+                                              const int32_t* nt_type, int32_t n) {
+  return mb::backbone_sites_impl<float>(static_cast<cudaStream_t>(stream), m, n_total, center, quat, out, nt_type, n);
 }
 
 extern "C" size_t mythos_b200_energy_workspace_bytes(int32_t n, int32_t n_frames, int64_t pair_capacity, int32_t real_bytes) {

@@ -214,6 +214,10 @@ __global__ void __launch_bounds__(kDB) k_list_debye(const EnergyDev<T> a) {
   const NucRec<T>* rec = reinterpret_cast<const NucRec<T>*>(a.rec) + fbase;
   pk_t* sr_list = a.sr_list + (long long)frame * a.sr_capacity;
   int* sr_count = a.sr_count + frame;
+  // support-tagged list: entries [0, split) are the short-range pairs (k_list_sr reads them straight from the list),
+  // entries [split, count) the pairs inside the Debye support: this pass evaluates just those, and filters nothing
+  const bool tagged = a.tagged != 0;
+  const long long first = tagged ? (long long)a.pair_split[frame] : 0;
   constexpr int kTile = kDB * kDU;
   // the index loads of the NEXT tile are issued before the current tile is evaluated: the list streams from HBM
   // (~40 MB at 100k nucleotides), and index -> record -> arithmetic would otherwise be one dependent chain per step
@@ -221,11 +225,11 @@ __global__ void __launch_bounds__(kDB) k_list_debye(const EnergyDev<T> a) {
   int ni[kDU], nj[kDU];
 #pragma unroll
   for (int u = 0; u < kDU; ++u) {
-    const long long k = (long long)blockIdx.x * kTile + threadIdx.x + u * kDB;
+    const long long k = first + (long long)blockIdx.x * kTile + threadIdx.x + u * kDB;
     ni[u] = k < count ? pl[k] : -1;
-    nj[u] = k < count ? pl[a.pair_capacity + k] : -1;
+    nj[u] = k < count ? (pl[a.pair_capacity + k] & 0x1fffffff) : -1;
   }
-  for (long long base = (long long)blockIdx.x * kTile; base < count; base += stride) {
+  for (long long base = first + (long long)blockIdx.x * kTile; base < count; base += stride) {
     int pi[kDU], pj[kDU];
     bool pv[kDU];
 #pragma unroll
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(kDB) k_list_debye(const EnergyDev<T> a) {
       pv[u] = base + threadIdx.x + u * kDB < count;
       const long long k = base + stride + threadIdx.x + u * kDB;
       ni[u] = k < count ? pl[k] : -1;
-      nj[u] = k < count ? pl[a.pair_capacity + k] : -1;
+      nj[u] = k < count ? (pl[a.pair_capacity + k] & 0x1fffffff) : -1;
     }
     bool sr[kDU];
 #pragma unroll
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(kDB) k_list_debye(const EnergyDev<T> a) {
         bank = (rna_i && rna_j) ? MB_BANK_RNA : ((rna_i != rna_j) ? MB_BANK_DRH : MB_BANK_DNA);
       }
       const V3<T> dc = disp(v3<T>(rj.c[0], rj.c[1], rj.c[2]), v3<T>(ri.c[0], ri.c[1], ri.c[2]), M.box);
-      sr[u] = valid && dot(dc, dc) < sD[bank][5];
+      sr[u] = !tagged && valid && dot(dc, dc) < sD[bank][5];
       if (any_debye) {
         const bool act = valid && (!MULTI || M.forms[bank].has_debye);
         const V3<T> db = disp(v3<T>(rj.b[0], rj.b[1], rj.b[2]), v3<T>(ri.b[0], ri.b[1], ri.b[2]), M.box);
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(kDB) k_list_debye(const EnergyDev<T> a) {
         }
       }
     }
-    if (want_sr) {
+    if (want_sr && !tagged) {
 #pragma unroll
       for (int u = 0; u < kDU; ++u) {  // warp-aggregated append to the short-range list
         const unsigned m = __ballot_sync(kFull, sr[u]);
@@ -388,8 +392,16 @@ __global__ void __launch_bounds__(kLB, MB_LIST_MINBLOCKS) k_list_sr(const Energy
   xacc.zero();
 
   const pk_t* sr_list = a.sr_list + (long long)frame * a.sr_capacity;
-  long long count = a.sr_count[frame];
-  count = count < a.sr_capacity ? count : a.sr_capacity;
+  const bool tagged = a.tagged != 0;
+  const int32_t* pl = a.pairs + (long long)frame * a.pair_frame_stride;
+  long long count;
+  if (tagged) {  // the short-range pairs are the head of the support-tagged list
+    count = a.pair_split[frame];
+    count = count < a.pair_capacity ? count : a.pair_capacity;
+  } else {
+    count = a.sr_count[frame];
+    count = count < a.sr_capacity ? count : a.sr_capacity;
+  }
   long long base = (long long)blockIdx.x * kLB;
   bool flush = false;
 
@@ -455,7 +467,8 @@ __global__ void __launch_bounds__(kLB, MB_LIST_MINBLOCKS) k_list_sr(const Energy
       const long long k = base + threadIdx.x;
       base += (long long)gridDim.x * kLB;
       const bool valid = k < count;
-      const pk_t pk = valid ? sr_list[k] : 0ull;
+      pk_t pk = 0ull;
+      if (valid) pk = tagged ? pk_make(pl[k], pl[a.pair_capacity + k] & 0x1fffffff) : sr_list[k];
       const int i = int(pk & 0xffffffffu), j = int(pk >> 32);
       T qi[4], qj[4];
       const Nuc<T> ni = load_nuc(a.center, a.quat, fbase + i, qi), nj = load_nuc(a.center, a.quat, fbase + j, qj);

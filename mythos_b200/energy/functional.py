@@ -70,6 +70,7 @@ def _launch(
     flags: int = 0,
     all_pairs_cutoff: float = 0.0,
     out: tuple | None = None,
+    pair_split: torch.Tensor | None = None,
 ):
     _lib.require_cuda(center, "center")
     F, N = center.shape[0], center.shape[1]
@@ -127,7 +128,8 @@ def _launch(
     a.d_params = _lib.ptr(d_params)
     a.d_params_frame_stride = stride
     ws = None
-    if cap and (cap * F >= 65536 or (flags & _lib.FLAG_LIST_KERNEL)) and not (flags & _lib.FLAG_GENERIC_KERNEL):
+    a.pair_split = _lib.ptr(pair_split) if cap else None
+    if cap and (cap * F >= 65536 or (flags & (_lib.FLAG_LIST_KERNEL | _lib.FLAG_TAGGED_PAIRS))) and not (flags & _lib.FLAG_GENERIC_KERNEL):
         # scratch of the phase-queued list kernel (caller-owned, as everywhere in the C-ABI); the caching allocator
         # makes this a pointer bump, and it is graph-capture safe
         need = int(_lib.lib().mythos_b200_energy_workspace_bytes(N, F, cap, 8 if dtype == torch.float64 else 4))
@@ -173,7 +175,9 @@ class CellListPairs:
     # the build keeps only pairs inside the support of some term and tags which; the frame-resident kernel then queues
     # them without touching coordinates.  Used when that kernel applies (one bank, no position gradients).
     tag: tuple | None = None
+    tag_for_list_kernels: bool = False  # opt-in: support-tagged lists also on the list-kernel route (forces, large systems)
     tagged_capacity: int = 0
+    last_split: torch.Tensor | None = None  # (F) of the last tagged chunk: entries before it are short-range pairs
     _last_tagged: bool = False
     _pending: list = dc.field(default_factory=list)
 
@@ -197,21 +201,24 @@ class CellListPairs:
             )
             self._pending.append((count, overflow))
             return pairs, 2 * self.capacity, count
-        model, r_sr, r_db = self.tag
-        sites = backbone_sites(model, c, quat.detach()) if r_db > 0 else None
+        model, r_sr, r_db = self.tag[:3]
+        nt_type = self.tag[3] if len(self.tag) > 3 else None
+        sites = backbone_sites(model, c, quat.detach(), nt_type) if r_db > 0 else None
 
         def both(cc, ss, cap):
-            pairs, count, overflow, self.workspace = neighbors.build_pairs(cc, self.bonded, self.box, max(r_sr, 1e-6), 0.0, cap,
+            pairs, split, overflow, self.workspace = neighbors.build_pairs(cc, self.bonded, self.box, max(r_sr, 1e-6), 0.0, cap,
                                                                            self.workspace, tag_bits=1 << 30)
+            count = split
             if ss is not None:
+                count = torch.empty_like(split)
                 neighbors.build_pairs(ss, self.bonded, self.box, r_db, 0.0, cap, self.workspace, tag_bits=1 << 29,
-                                      out=(pairs, count, overflow), append=True)
-            return pairs, count, overflow
+                                      out=(pairs, count, overflow), append_count=split)
+            return pairs, count, overflow, split
 
         if self.tagged_capacity <= 0:
-            _, count, _ = both(c[:1], None if sites is None else sites[:1], 4)
+            _, count, _, _ = both(c[:1], None if sites is None else sites[:1], 4)
             self.tagged_capacity = (max(int(int(count.max().item()) * 1.06) + 64, 64) + 3) // 4 * 4
-        pairs, count, overflow = both(c, sites, self.tagged_capacity)
+        pairs, count, overflow, self.last_split = both(c, sites, self.tagged_capacity)
         self._pending.append((count, overflow))
         return pairs, 2 * self.tagged_capacity, count
 
@@ -232,13 +239,15 @@ class CellListPairs:
         return False
 
 
-def backbone_sites(model, center: torch.Tensor, quat: torch.Tensor) -> torch.Tensor:
-    """(F,N,3) backbone interaction sites of (center, quat) for a single-flavour model (one fused kernel)."""
+def backbone_sites(model, center: torch.Tensor, quat: torch.Tensor, nt_type: torch.Tensor | None = None) -> torch.Tensor:
+    """(F,N,3) backbone interaction sites of (center, quat) (one fused kernel); ``nt_type`` (N) int32 picks the flavour
+    per nucleotide for the three-bank model."""
     out = torch.empty_like(center)
     fn = getattr(_lib.lib(), f"mythos_b200_backbone_sites_{_lib.suffix(center.dtype)}")
     with torch.cuda.device(center.device):
         _lib.check(fn(_lib.current_stream(center.device), C.pointer(model), center.shape[0] * center.shape[1],
-                      center.contiguous().data_ptr(), quat.to(center.dtype).contiguous().data_ptr(), out.data_ptr()), "mythos_b200_backbone_sites")
+                      center.contiguous().data_ptr(), quat.to(center.dtype).contiguous().data_ptr(), out.data_ptr(),
+                      _lib.ptr(nt_type), center.shape[1]), "mythos_b200_backbone_sites")
     return out
 
 
@@ -265,8 +274,12 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
             if getattr(err, "status", None) != 3:  # MB_ECAPACITY: frame too large for shared memory -> device lists
                 raise
             source.in_kernel = False
-    tagged = (isinstance(source, CellListPairs) and source.tag is not None and not want_pos and model.n_banks == 1
-              and center.shape[1] < 16384 and not (flags & (_lib.FLAG_GENERIC_KERNEL | _lib.FLAG_LIST_KERNEL)))
+    # support-tagged lists: for the frame-resident kernel (one bank, no position gradients, small frames); the list
+    # kernels of large systems take them too (any bank count, forces), but for ONE configuration the second build's fixed
+    # launch cost outweighs the pairs it saves (measured: 0.92 vs 0.85 ms at 100k nucleotides), so that is opt-in
+    tagged = (isinstance(source, CellListPairs) and source.tag is not None
+              and not (flags & (_lib.FLAG_GENERIC_KERNEL | _lib.FLAG_LIST_KERNEL))
+              and ((not want_pos and model.n_banks == 1 and center.shape[1] < 16384) or source.tag_for_list_kernels))
     while True:
         outs = []
         try:
@@ -278,7 +291,7 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
                 outs.append(
                     _launch(model, topo, center[sl], quat[sl], params, pairs, stride, term_mask,
                             None if cot is None else cot[sl], want_terms, want_pos, want_par, per_frame_par, count,
-                            flags | (_lib.FLAG_TAGGED_PAIRS if tagged else 0))
+                            flags | (_lib.FLAG_TAGGED_PAIRS if tagged else 0), 0.0, None, source.last_split if tagged else None)
                 )
         except _lib.MythosB200Error as err:
             if not tagged or getattr(err, "status", None) != 3:  # MB_ECAPACITY: the frame-resident kernel does not apply

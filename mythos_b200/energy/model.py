@@ -159,10 +159,8 @@ class Plan:
             # the in-kernel cell list keeps 2 bonded partners per nucleotide (like the reference's (N,2) mask)
             if in_kernel and topo.bonded.numel() and int(torch.bincount(topo.bonded.reshape(-1).long()).max()) > 2:
                 in_kernel = False
-            tag = None
-            if self.model.n_banks == 1:
-                r_sr, r_db = support_cutoffs(self)
-                tag = (self.model, r_sr, r_db)
+            r_sr, r_db = support_cutoffs(self)
+            tag = (self.model, r_sr, r_db, topo.nt_type if self.model.n_banks > 1 else None)
             return functional.CellListPairs(bonded=topo.bonded, box=box, r_cutoff=interaction_range(self), in_kernel=in_kernel, tag=tag)
         return functional.StaticPairs(device_pairs(ub, device))
 
@@ -223,29 +221,35 @@ def interaction_range(plan: "Plan") -> float:
 
 
 def support_cutoffs(plan: "Plan") -> tuple[float, float]:
-    """(centre cutoff of the short-range terms, backbone-site cutoff of Debye-Hueckel) of a single-bank plan: the supports
-    the neighbour build tags pairs with (MB_NL_TAG_SUPPORTS).  Same formula as the kernels' own short-range cutoff."""
+    """(centre cutoff of the short-range terms, backbone-site cutoff of Debye-Hueckel), maxima over banks and flavours: the
+    supports the neighbour build tags pairs with (MB_NL_TAG_SUPPORTS).  Same formula as the kernels' own short-range cutoff."""
     vec = plan.params_vector().detach()
+    P = _lib.param_count()
     idx = {n: i for i, n in enumerate(_lib.param_names())}
-
-    def p(name):
-        return float(vec[idx[name]])
-
-    g = plan.model.geom[0]
-    ob = float(sum(x * x for x in g.back) ** 0.5)
-    oh, os_ = abs(g.base), abs(g.stack)
+    ob = oh = os_ = 0.0
+    for k in range(2 if plan.hybrid else 1):
+        g = plan.model.geom[k]
+        ob = max(ob, float(sum(x * x for x in g.back) ** 0.5))
+        oh, os_ = max(oh, abs(g.base)), max(os_, abs(g.stack))
     m = plan.term_mask
-    r = 0.0
-    if m & (1 << 3):
-        r = max(r, p("unbonded_excluded_volume.dr_c_backbone") + 2 * ob, p("unbonded_excluded_volume.dr_c_base") + 2 * oh,
-                max(p("unbonded_excluded_volume.dr_c_back_base"), p("unbonded_excluded_volume.dr_c_base_back")) + ob + oh)
-    if m & (1 << 4):
-        r = max(r, p("hydrogen_bonding.dr_c_high_hb") + 2 * oh)
-    if m & (1 << 5):
-        r = max(r, p("cross_stacking.dr_c_high_cross") + 2 * oh)
-    if m & (1 << 6):
-        r = max(r, p("coaxial_stacking.dr_c_high_coax") + 2 * os_)
-    r_db = p("debye.r_cut") * (1.0 + 1e-9) + 1e-12 if (m & (1 << 7)) and plan.model.forms[0].has_debye else 0.0
+    r = r_db = 0.0
+    for b in range(plan.model.n_banks):
+        v = vec[b * P:(b + 1) * P]
+
+        def p(name):
+            return float(v[idx[name]])
+
+        if m & (1 << 3):
+            r = max(r, p("unbonded_excluded_volume.dr_c_backbone") + 2 * ob, p("unbonded_excluded_volume.dr_c_base") + 2 * oh,
+                    max(p("unbonded_excluded_volume.dr_c_back_base"), p("unbonded_excluded_volume.dr_c_base_back")) + ob + oh)
+        if m & (1 << 4):
+            r = max(r, p("hydrogen_bonding.dr_c_high_hb") + 2 * oh)
+        if m & (1 << 5):
+            r = max(r, p("cross_stacking.dr_c_high_cross") + 2 * oh)
+        if m & (1 << 6):
+            r = max(r, p("coaxial_stacking.dr_c_high_coax") + 2 * os_)
+        if (m & (1 << 7)) and plan.model.forms[b].has_debye:
+            r_db = max(r_db, p("debye.r_cut") * (1.0 + 1e-9) + 1e-12)
     return r * (1.0 + 2e-6) + 1e-9, r_db
 
 

@@ -33,7 +33,7 @@ def build_pairs(
     max_row: torch.Tensor | None = None,
     tag_bits: int = 0,
     out: tuple | None = None,
-    append: bool = False,
+    append_count: torch.Tensor | None = None,
 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """Raw batched build.  center (F,N,3) on the device -> (pairs (F,2,capacity) int32, count (F,), overflow (1,), workspace).
 
@@ -67,10 +67,10 @@ def build_pairs(
     a.count, a.overflow = count.data_ptr(), overflow.data_ptr()
     a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
     a.flags = _lib.NL_ROWS if rows else 0
-    if tag_bits or append:  # support tags (internal contract with the frame-resident energy kernel)
+    if tag_bits or append_count is not None:  # support tags (internal contract with this library's energy kernels)
         a.flags |= _lib.NL_TAG_SUPPORTS
         a.tag_bits = int(tag_bits)
-        a.append_count = count.data_ptr() if append else None
+        a.append_count = append_count.data_ptr() if append_count is not None else None
     a.max_row = max_row.data_ptr() if (rows and max_row is not None) else None
     fn = getattr(_lib.lib(), f"mythos_b200_nl_build_{_lib.suffix(center.dtype)}")
     with torch.cuda.device(dev):

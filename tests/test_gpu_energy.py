@@ -187,3 +187,40 @@ def test_list_kernels_equal_generic_kernels(name, dtype):
     for got, want in zip(outs[0], outs[1]):
         got, want = got.cpu().numpy(), want.cpu().numpy()
         np.testing.assert_allclose(got, want, rtol=tol, atol=tol * np.abs(want).max())
+
+
+@pytest.mark.parametrize("model", ["dna2", "na1"])
+def test_tagged_lists_through_list_kernels_equal_plain_lists(model):
+    """Large-system route of the AllPairs sentinel with forces (N >= 4096): two support-tagged neighbour builds (centres at
+    the short-range cutoff, backbone sites at the Debye cutoff) feeding the list kernels, against one plain build at the
+    interaction range through the list kernels and through the one-thread-per-pair kernels."""
+    from mythos_b200 import _lib
+    from mythos_b200.energy import dna2, functional, na1
+    from mythos_b200.energy import model as kmodel
+    from mythos_b200.input.topology import AllPairs
+    from mythos_b200.utils import synthetic
+
+    pattern = ((1, 1), (2, 2), (1, 2)) if model == "na1" else None
+    s = synthetic.assembly(36, seed=4, nt_pattern=pattern)
+    n = s.center.shape[0]
+    assert n >= 4096
+    efn = (na1 if model == "na1" else dna2).create_default_energy_fn(s.topology).with_props(unbonded_neighbors=AllPairs(n))
+    plan = kmodel.plan_for(efn.energy_fns)
+    cd = torch.tensor(s.center[None], device=DEV)
+    qd = torch.tensor(s.quat[None], device=DEV)
+    topo = plan.topology(n, cd.device)
+    params = plan.device_params(cd.device, torch.float64)
+    cot = torch.tensor(np.random.default_rng(5).uniform(0.5, 1.5, size=(1, 8)), device=DEV)
+    outs = []
+    for tagged, flags in ((True, 0), (False, 0), (False, _lib.FLAG_GENERIC_KERNEL)):
+        src = plan.pairs(cd.device, topo)
+        assert src.tag is not None
+        src.tag_for_list_kernels = tagged
+        outs.append(functional.energy_and_gradients(plan.model, topo, cd, qd, params, src, cot=cot, want_pos_grad=True,
+                                                    want_param_grad=True, flags=flags))
+        if tagged:
+            assert src.tagged_capacity > 0 and src.last_split is not None
+    for k in (0, 1):
+        for got, want in zip(outs[k], outs[2]):
+            got, want = got.cpu().numpy(), want.cpu().numpy()
+            np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-10 * np.abs(want).max())
