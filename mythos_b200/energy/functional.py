@@ -204,6 +204,13 @@ class CellListPairs:
         model, r_sr, r_db = self.tag[:3]
         nt_type = self.tag[3] if len(self.tag) > 3 else None
         sites = backbone_sites(model, c, quat.detach(), nt_type) if r_db > 0 else None
+        # The tagged builds only have to be SUPERSETS of the supports (the kernels apply the exact tests again), so they run
+        # in float32 with the cutoffs widened by far more than the rounding of the coordinates: half the record bytes and
+        # FP32 instead of FP64 distance arithmetic in the walks.
+        if c.dtype == torch.float64:
+            c = c.float()
+            sites = None if sites is None else sites.float()
+            r_sr, r_db = r_sr + 1e-3, (r_db + 1e-3 if r_db > 0 else r_db)
 
         def both(cc, ss, cap):
             pairs, split, overflow, self.workspace = neighbors.build_pairs(cc, self.bonded, self.box, max(r_sr, 1e-6), 0.0, cap,
