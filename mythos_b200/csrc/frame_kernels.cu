@@ -572,26 +572,26 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
     // list, which streams from HBM, is never waited for.  Tagged lists (MB_NL_TAG_SUPPORTS: the neighbour build already
     // split the pairs by the terms' supports) pack i | j << 14 | Debye tag << 28 | short-range tag << 29.
     const bool tagged = a.tagged != 0;
-    auto load_entry = [&](long long k) -> uint32_t {
-      if (k >= count) return 0xffffffffu;
-      const int i = pl[k];
-      int j = pl[a.pair_capacity + k];
+    // (the RAW indices are what is kept across steps: decoding a value in the step that loads it would wait for the load)
+    int pfi[kSlice], pfj[kSlice];
+    auto issue_loads = [&](long long b0) {
+#pragma unroll
+      for (int u = 0; u < kSlice; ++u) {
+        const long long k = b0 + threadIdx.x + (long long)u * kFB;
+        pfi[u] = k < count ? pl[k] : -1;
+        pfj[u] = k < count ? pl[a.pair_capacity + k] : -1;
+      }
+    };
+    auto decode = [&](int i, int j) -> uint32_t {
       uint32_t tg = 0u;
-      if (tagged) {
+      if (tagged && j >= 0) {
         tg = (uint32_t(j) >> 29) & 3u;  // bit 0: second sites inside the Debye cutoff, bit 1: centres inside the short-range cutoff
         j &= 0x1fffffff;
       }
       if (!(i >= 0 && j >= 0 && i < n && j < n)) return 0xffffffffu;
       return tagged ? (uint32_t(i) | (uint32_t(j) << 14) | (tg << 28)) : (uint32_t(i) | (uint32_t(j) << 16));
     };
-    uint32_t pf[kSlice];
-    if (!cells) {
-#pragma unroll
-      for (int u = 0; u < kSlice; ++u) {
-        const long long k = threadIdx.x + (long long)u * kFB;
-        pf[u] = load_entry(k);
-      }
-    }
+    if (!cells) issue_loads(0);
     const int n_rows = cells ? half_shell_rows(grid->S) : 0;
     const T rc_debye2 = want_debye ? sP[MB_P_DEBYE_RCUT] * sP[MB_P_DEBYE_RCUT] : T(-1);
     bool flush = false;
@@ -742,10 +742,13 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
           continue;
         }
         base += (long long)kFB * kSlice;
+        uint32_t cur_[kSlice];
+#pragma unroll
+        for (int u = 0; u < kSlice; ++u) cur_[u] = decode(pfi[u], pfj[u]);  // loaded one step ago
+        issue_loads(base);                                                  // the next step's entries, used one step from now
 #pragma unroll
         for (int u = 0; u < kSlice; ++u) {
-          const uint32_t cur = pf[u];
-          pf[u] = load_entry(base + threadIdx.x + (long long)u * kFB);  // next step's loads first
+          const uint32_t cur = cur_[u];
           if (cur != 0xffffffffu && tagged) {
             found[u] = (cur & 0x3fffu) | (((cur >> 14) & 0x3fffu) << 16);
             if (want_debye && (cur & (1u << 28))) acc_db |= 1u << u;
