@@ -9,8 +9,9 @@ frames are sharded contiguously over the ranks (total fixed -> "strong"), energi
 all-reduced over NCCL.
 
   value   frames/s with frames resident in HBM and the packed parameter bank on the device (CUDA events, max over ranks)
-  e2e     frames/s through the public API ``compute_loss_and_grad`` with HOST (pinned) frame buffers: H2D of the frames,
-          theta -> bank chain on the host, kernels, D2H of loss and gradients inside the timed region
+  e2e     frames/s through the public API ``compute_loss_and_grad`` with HOST (pinned) frame buffers: H2D of the frames
+          (streamed chunk by chunk, overlapped with the kernels), theta -> bank chain on the host, kernels, D2H of loss
+          and gradients inside the timed region
   roofline  dominant kernel (k_frame_energy: all terms of a frame, E + dE/dparams, pair lists streamed from the per-frame
           device neighbour build): algorithmic flop-equivalents / CUDA-event time vs the FP64 FMA issue peak measured in
           this run by the library's micro-benchmark (and HBM bytes vs measured copy BW)
@@ -416,6 +417,29 @@ def main():
             ms = float(t.item())
         return ms, out
 
+    # FP64 FMA issue peak, measured
+    scratch = torch.empty(148 * 32 * 256, dtype=torch.float64, device=dev)
+    lib = _lib.lib()
+    best = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.mythos_b200_fma_peak_f64(_lib.current_stream(dev), scratch.data_ptr(), 148 * 32, 4096), "fma_peak")
+        e1.record()
+        torch.cuda.synchronize(dev)
+        best = max(best, 148 * 32 * 256 * 4096 * 16 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    # The single-GPU legs of the other configurations run FIRST, on a quiet process: MD at N = 120 is bound by launch and
+    # dependency latency, and measured 4x slower after the big passes (allocator state of the 936 MB streaming buffers) or
+    # after the CPU oracle (its OpenMP workers keep spinning and slow the launch thread).
+    md_line = forces_8k = forces_100k = None
+    if world == 1 and rank == 0:
+        md_line = md_benchmark(dev)
+        forces_8k = force_benchmark(dev, 68, "dna2", 0, best,
+                                    "configs[2]: oxDNA2 + Debye, synthetic 68-duplex assembly (N=8160), neighbour list, float64")
+        forces_100k = force_benchmark(dev, 834, "na1", 2, best,
+                                      "configs[4]: NA1 hybrid DNA/RNA, synthetic 834-duplex assembly (N=100080), neighbour rebuild + forces, float64")
+
+    torch.cuda.empty_cache()
     for _ in range(args.warmup):
         device_pass(e_ref)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -429,9 +453,9 @@ def main():
         return measured, (("obs", measured), None)
 
     def e2e_step():
-        cd = c_host.to(dev, non_blocking=True)
-        qd = q_host.to(dev, non_blocking=True)
-        states = SimulatorTrajectory(center=cd, orientation=Quaternion(qd), temperature=temperature, shard=(lo, hi, F))
+        # the frames stay in pinned host memory: the public API streams them to the device chunk by chunk (copy stream),
+        # overlapped with the kernels of the previous chunk; every byte crosses PCIe inside the timed region
+        states = SimulatorTrajectory(center=c_host, orientation=Quaternion(q_host), temperature=temperature, shard=(lo, hi, F))
         (l, aux), grads = objective.compute_loss_and_grad(theta, efn, beta, loss_fn, states, e_ref, [])
         host = torch.stack([grads[k] for k in sorted(grads)]).cpu()
         return float(l), host
@@ -483,17 +507,6 @@ def main():
     flop_eq = 2 * 2.5 * slots_fwd  # E + params-only backward = 2.5 x forward; 1 FMA slot = 2 flop
     achieved = flop_eq / (k_ms * 1e-3) / 1e12
 
-    # FP64 FMA issue peak, measured
-    scratch = torch.empty(148 * 32 * 256, dtype=torch.float64, device=dev)
-    lib = _lib.lib()
-    best = 0.0
-    for _ in range(4):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _lib.check(lib.mythos_b200_fma_peak_f64(_lib.current_stream(dev), scratch.data_ptr(), 148 * 32, 4096), "fma_peak")
-        e1.record()
-        torch.cuda.synchronize(dev)
-        best = max(best, 148 * 32 * 256 * 4096 * 16 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     alg_bytes = chunk * (n * 7 * 8 + 8 * u["kept_by_tagged_build"] + 232 * 8 + 64)  # frame + tagged pair list in, J row + terms row out
@@ -511,15 +524,6 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         "work_model": "SURVEY 8d per-pair counts split per term, each term counted only inside its radial support (supports measured on 16 frames); x2.5 for E + dE/dparams; fp64 special weights div16 sqrt16 exp40 log50 acos70",
     }
-
-    # (the GPU legs run before the CPU oracle: its OpenMP workers keep spinning afterwards and slow the launch thread)
-    md_line = forces_8k = forces_100k = None
-    if world == 1:
-        md_line = md_benchmark(dev)
-        forces_8k = force_benchmark(dev, 68, "dna2", 0, best,
-                                    "configs[2]: oxDNA2 + Debye, synthetic 68-duplex assembly (N=8160), neighbour list, float64")
-        forces_100k = force_benchmark(dev, 834, "na1", 2, best,
-                                      "configs[4]: NA1 hybrid DNA/RNA, synthetic 834-duplex assembly (N=100080), neighbour rebuild + forces, float64")
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

@@ -75,6 +75,54 @@ struct RegAcc {
   __device__ __forceinline__ void add_scatter(int, int, T, bool) {}
 };
 
+// Angular pre-screen of the hydrogen-bonding / cross-stacking queue.  Both terms carry the plain factors
+// f4(theta1) f4(theta2) f4(theta3) with theta_k = acos(clamp(x_k)), x1 = -a1i.a1j, x2 = -a1j.dh, x3 = a1i.dh; f4 is non-zero
+// only for |theta - theta0| < delta_c, i.e. for x inside a cosine window that depends on the parameters alone.  A pair
+// whose x_k miss the windows of BOTH terms contributes exactly zero (value and every gradient) and never needs the six
+// acos of the full evaluation.  Windows are widened by 1e-9 so that rounding can only let extra pairs through.
+template <class T>
+struct CosWin {
+  T lo, hi;
+};
+template <class T>
+__device__ __forceinline__ CosWin<T> f4_cos_window(const T* p /* f4 block: theta0, delta_star, delta_c, a, b */) {
+  const T pi = Consts<T>::pi();
+  const T t_lo = p[0] - p[2], t_hi = p[0] + p[2];
+  CosWin<T> w;
+  if (t_lo >= pi || t_hi <= T(0)) {  // empty
+    w.lo = T(2);
+    w.hi = T(-2);
+    return w;
+  }
+  w.hi = (t_lo <= T(0)) ? T(2) : cos(t_lo) + T(1e-9);
+  w.lo = (t_hi >= pi) ? T(-2) : cos(t_hi) - T(1e-9);
+  return w;
+}
+// six windows of one bank: [0..2] hydrogen bonding theta1,2,3; [3..5] cross stacking theta1,2,3
+template <class T>
+__device__ __forceinline__ void bp_windows(const T* P, CosWin<T> w[6]) {
+  w[0] = f4_cos_window(P + MB_P_HB_T1_TH0);
+  w[1] = f4_cos_window(P + MB_P_HB_T2_TH0);
+  w[2] = f4_cos_window(P + MB_P_HB_T3_TH0);
+  w[3] = f4_cos_window(P + MB_P_CROSS_T1_TH0);
+  w[4] = f4_cos_window(P + MB_P_CROSS_T2_TH0);
+  w[5] = f4_cos_window(P + MB_P_CROSS_T3_TH0);
+}
+// true if hydrogen bonding or cross stacking of the pair can be non-zero (d = base_j - base_i, r2 = |d|^2)
+template <class T>
+__device__ __forceinline__ bool bp_screen(const T* P, const CosWin<T>* w, unsigned mask, const V3<T>& d, T r2, const V3<T>& a1i,
+                                          const V3<T>& a1j, int tab) {
+  const T r = sqrt(r2);
+  const bool rad_hb = (mask & (1u << MB_TERM_HB)) && P[MB_P_HB_RCLOW] < r && r < P[MB_P_HB_RCHIGH] && P[MB_P_HB_W00 + tab] != T(0);
+  const bool rad_cr = (mask & (1u << MB_TERM_CROSS)) && P[MB_P_CROSS_RCLOW] < r && r < P[MB_P_CROSS_RCHIGH];
+  if (!(rad_hb || rad_cr) || !(r > T(0))) return false;
+  const T ir = T(1) / r;
+  const T x1 = -dot(a1i, a1j), x2 = -dot(a1j, d) * ir, x3 = dot(a1i, d) * ir;
+  const bool hb = rad_hb && w[0].lo < x1 && x1 < w[0].hi && w[1].lo < x2 && x2 < w[1].hi && w[2].lo < x3 && x3 < w[2].hi;
+  const bool cr = rad_cr && w[3].lo < x1 && x1 < w[3].hi && w[4].lo < x2 && x2 < w[4].hi && w[5].lo < x3 && x3 < w[5].hi;
+  return hb || cr;
+}
+
 template <class T>
 __device__ __forceinline__ Nuc<T> load_nuc(const T* __restrict__ center, const T* __restrict__ quat, long long idx,
                                            T q[4]) {

@@ -52,7 +52,7 @@ constexpr int kExcl = 2;                // bonded partners per nucleotide (as th
 struct FrameSmem {
   // byte offsets into dynamic shared memory; computed on the host and passed as a kernel parameter so that the
   // kernel re-reads them from the constant bank instead of rematerialising the whole chain under register pressure
-  unsigned c, q, back, p, acc, e, flags, q_nl, q_sr, q_bp, q_cx, wcnt, ctr, cstart, corder, excl, grid, total;
+  unsigned c, q, back, p, acc, e, flags, q_nl, q_sr, q_bp, q_cx, wcnt, ctr, cstart, corder, excl, grid, win, total;
   int acc_rows;  // copies of the parameter-gradient image: warps are spread over them so that their shared-memory atomics do not collide
 };
 template <class T>
@@ -82,6 +82,7 @@ inline FrameSmem frame_smem_layout(int n, bool wp, bool cache_back, bool cells, 
   L.corder = take(cells ? sizeof(uint16_t) * n : 0);
   L.excl = take(cells ? sizeof(uint16_t) * kExcl * n : 0);
   L.grid = take(sizeof(T) * 8 + sizeof(int) * 8);
+  L.win = take(sizeof(CosWin<T>) * 6);
   L.total = off;
   return L;
 }
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   uint16_t* sCorder = reinterpret_cast<uint16_t*>(smem + L.corder);
   uint16_t* sExcl = reinterpret_cast<uint16_t*>(smem + L.excl);
   CellGrid<T>* grid = reinterpret_cast<CellGrid<T>*>(smem + L.grid);
+  CosWin<T>* sWin = reinterpret_cast<CosWin<T>*>(smem + L.win);  // angular pre-screen of the hydrogen-bond / cross queue
   int* sCursor = reinterpret_cast<int*>(smem + L.q_nl);  // per-cell fill cursors; aliases queue NL, used only during the cell build
 
 #ifdef MB_FRAME_PROFILE
@@ -313,6 +315,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
     sF[k] = (unsigned char)((a.seq[k] & 3) | ((a.is_end && a.is_end[k]) ? 4 : 0));
   if (threadIdx.x < 8) ctr[threadIdx.x] = 0;
   __syncthreads();
+  if (threadIdx.x == 0) bp_windows(sP, sWin);  // visible after the next barrier (bonded phase / cell build / loop top)
 
   const ModelT<T>& M = a.M;
   const Geom<T>& g = M.geom[0];
@@ -683,7 +686,10 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
           e[MB_TERM_UEXC] += ex;
         }
         const T r2 = dot(d_base, d_base);
-        const bool to_bp = valid && bp_hi > T(0) && r2 > bp_lo * bp_lo && r2 < bp_hi * bp_hi;
+        bool to_bp = valid && bp_hi > T(0) && r2 > bp_lo * bp_lo && r2 < bp_hi * bp_hi;
+        // radial window passed: cheap cosine tests of the three plain angles decide whether the six-acos evaluation can
+        // be non-zero at all (most pairs inside the window have the wrong orientation)
+        if (to_bp) to_bp = bp_screen(sP, sWin, mask, d_base, r2, ni.a1, nj.a1, (sF[i] & 3) * 4 + (sF[j] & 3));
         bool to_cx = false;
         if (mask & (1u << MB_TERM_COAX)) {
           const V3<T> ds = disp(site(nj, g.stack, T(0), T(0)), site(ni, g.stack, T(0), T(0)), M.box);

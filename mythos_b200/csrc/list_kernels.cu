@@ -342,7 +342,8 @@ __global__ void __launch_bounds__(kLB, MB_LIST_MINBLOCKS) k_list_sr(const Energy
   T* sAcc = sP + np;                            // np reals when WP
   T* sE = sAcc + (WP ? np : 0);                 // kLWarps x 8
   BankCuts<T>* sCut = reinterpret_cast<BankCuts<T>*>(sE + kLWarps * MB_N_TERMS);  // MB_MAX_BANKS
-  int* ctr = reinterpret_cast<int*>(sCut + MB_MAX_BANKS);  // [1] n_bp [2] n_cx
+  CosWin<T>* sWin = reinterpret_cast<CosWin<T>*>(sCut + MB_MAX_BANKS);             // 6 per bank: angular pre-screen of queue BP
+  int* ctr = reinterpret_cast<int*>(sWin + 6 * MB_MAX_BANKS);  // [1] n_bp [2] n_cx
 
   const int frame = blockIdx.y;
   const int n = a.n;
@@ -376,6 +377,7 @@ __global__ void __launch_bounds__(kLB, MB_LIST_MINBLOCKS) k_list_sr(const Energy
       c.cx_hi2 = P[MB_P_COAX_RCHIGH] * P[MB_P_COAX_RCHIGH];
     }
     sCut[threadIdx.x] = c;
+    bp_windows(P, sWin + 6 * threadIdx.x);
   }
   __syncthreads();
 
@@ -497,7 +499,9 @@ __global__ void __launch_bounds__(kLB, MB_LIST_MINBLOCKS) k_list_sr(const Energy
       const Geom<T>&gi = M.geom[fi], &gj = M.geom[fj];
       const V3<T> d_base = disp(site(nj, gj.base, T(0), T(0)), site(ni, gi.base, T(0), T(0)), M.box);
       const T r2 = dot(d_base, d_base);
-      const bool to_bp = valid && r2 > cut.bp_lo2 && r2 < cut.bp_hi2;
+      bool to_bp = valid && r2 > cut.bp_lo2 && r2 < cut.bp_hi2;
+      if (to_bp)  // cosine tests of the three plain angles: can hydrogen bonding or cross stacking be non-zero at all?
+        to_bp = bp_screen(sP + bank * MB_P_COUNT, sWin + 6 * bank, mask, d_base, r2, ni.a1, nj.a1, (a.seq[i] & 3) * 4 + (a.seq[j] & 3));
       const V3<T> ds = disp(site(nj, gj.stack, T(0), T(0)), site(ni, gi.stack, T(0), T(0)), M.box);
       const T s2 = dot(ds, ds);
       const bool to_cx = valid && s2 > cut.cx_lo2 && s2 < cut.cx_hi2;
@@ -554,7 +558,7 @@ static int launch_list(cudaStream_t s, const EnergyDev<T>& a) {
   const int nb = MULTI ? a.M.n_banks : 1;
   const size_t np = (size_t)nb * MB_P_COUNT;
   const size_t smem = sizeof(pk_t) * (2 * kLQCap) + sizeof(T) * (np * (WP ? 2 : 1) + kLWarps * MB_N_TERMS) +
-                      sizeof(BankCuts<T>) * MB_MAX_BANKS + sizeof(int) * 8;
+                      sizeof(BankCuts<T>) * MB_MAX_BANKS + sizeof(CosWin<T>) * 6 * MB_MAX_BANKS + sizeof(int) * 8;
   static int sms = 0;
   if (!sms) {
     int dev = 0;

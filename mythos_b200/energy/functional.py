@@ -287,16 +287,31 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
     tagged = (isinstance(source, CellListPairs) and source.tag is not None
               and not (flags & (_lib.FLAG_GENERIC_KERNEL | _lib.FLAG_LIST_KERNEL))
               and ((not want_pos and model.n_banks == 1 and center.shape[1] < 16384) or source.tag_for_list_kernels))
+    # frames in pinned host memory are streamed: chunk k+1 is copied on a side stream while chunk k is evaluated
+    streamed = not center.is_cuda
+    if streamed and want_pos:
+        raise _lib.MythosB200Error("position gradients need device-resident frames")
+    dev = params.device
     while True:
         outs = []
         try:
-            for sl in _chunks(center.shape[0], source):
-                if tagged:
-                    pairs, stride, count = source.chunk(sl, center[sl], quat[sl], tagged=True)
+            chunks = _chunks(center.shape[0], source)
+            nxt = _fetch(center, quat, chunks[0], dev) if streamed else None
+            for k, sl in enumerate(chunks):
+                if streamed:
+                    c_sl, q_sl, ready = nxt
+                    nxt = _fetch(center, quat, chunks[k + 1], dev) if k + 1 < len(chunks) else None
+                    torch.cuda.current_stream(dev).wait_event(ready)
+                    c_sl.record_stream(torch.cuda.current_stream(dev))
+                    q_sl.record_stream(torch.cuda.current_stream(dev))
                 else:
-                    pairs, stride, count = source.chunk(sl, center[sl])
+                    c_sl, q_sl = center[sl], quat[sl]
+                if tagged:
+                    pairs, stride, count = source.chunk(sl, c_sl, q_sl, tagged=True)
+                else:
+                    pairs, stride, count = source.chunk(sl, c_sl)
                 outs.append(
-                    _launch(model, topo, center[sl], quat[sl], params, pairs, stride, term_mask,
+                    _launch(model, topo, c_sl, q_sl, params, pairs, stride, term_mask,
                             None if cot is None else cot[sl], want_terms, want_pos, want_par, per_frame_par, count,
                             flags | (_lib.FLAG_TAGGED_PAIRS if tagged else 0), 0.0, None, source.last_split if tagged else None)
                 )
@@ -309,6 +324,22 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
         if not isinstance(source, CellListPairs) or source.verify():
             break
     return _merge(outs, want_terms, want_pos, want_par, per_frame_par)
+
+
+_COPY_STREAMS: dict = {}
+
+
+def _fetch(center: torch.Tensor, quat: torch.Tensor, sl: slice, dev):
+    """Enqueue the host -> device copy of one chunk of frames on the device's copy stream; -> (center, quat, event)."""
+    stream = _COPY_STREAMS.get(dev)
+    if stream is None:
+        stream = _COPY_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        c = center[sl].to(dev, non_blocking=True)
+        q = quat[sl].to(dev, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(stream)
+    return c, q, ready
 
 
 def _merge(outs, want_terms, want_pos, want_par, per_frame_par):
@@ -359,7 +390,7 @@ class _FrameEnergy(torch.autograd.Function):
     @staticmethod
     def forward(ctx, center, quat, params, weights, model, topo, source, term_mask):
         F = center.shape[0]
-        cot = weights.to(device=center.device, dtype=center.dtype).reshape(1, -1).expand(F, -1).contiguous()
+        cot = weights.to(device=params.device, dtype=center.dtype).reshape(1, -1).expand(F, -1).contiguous()
         jac_now = ctx.needs_input_grad[2] and not (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         terms, _, _, J = _run(model, topo, center, quat, params, source, term_mask, cot, True, False, jac_now, True)
         ctx.jac_now = jac_now

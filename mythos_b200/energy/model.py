@@ -174,9 +174,17 @@ class Plan:
         )
 
     def evaluate_total(self, center: torch.Tensor, quat: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
-        """(F,) weighted total energies with the parameter-gradient rows produced in the same pass (DiffTRe shape)."""
-        _lib.require_cuda(center, "RigidBody.center")
-        dev, dtype = center.device, center.dtype
+        """(F,) weighted total energies with the parameter-gradient rows produced in the same pass (DiffTRe shape).
+
+        ``center`` / ``quat`` may also be PINNED HOST tensors (stored trajectory frames): they are then streamed to the
+        current CUDA device chunk by chunk on a copy stream, overlapped with the kernels of the previous chunk."""
+        if center.is_cuda:
+            dev = center.device
+        elif center.is_pinned() and quat.is_pinned() and torch.cuda.is_available():
+            dev = torch.device("cuda", torch.cuda.current_device())
+        else:
+            _lib.require_cuda(center, "RigidBody.center (or pinned host memory, which is streamed)")
+        dtype = center.dtype
         topo = self.topology(center.shape[1], dev)
         return functional.frame_energies(
             self.model, topo, center, quat, self.device_params(dev, dtype), self.pairs(dev, topo), weights, self.term_mask

@@ -198,3 +198,32 @@ def test_all_pairs_sentinel_equals_explicit_all_pairs_list(box, in_kernel):
     want = efn.compute_terms_frames(states)
     got = efn.with_props(unbonded_neighbors=AllPairs(top.n_nucleotides, in_kernel=in_kernel)).compute_terms_frames(states)
     np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-10, atol=1e-10)
+
+
+def test_pinned_host_frames_are_streamed_and_give_identical_results(workload):
+    """``map`` over frames that live in pinned host memory (streamed to the device chunk by chunk on a copy stream) must
+    reproduce the device-resident result bit for bit, energies and theta-gradients; pageable host memory is refused."""
+    from mythos_b200 import _lib
+    from mythos_b200.energy import functional
+
+    s, c, q = workload
+    efn = dna2.create_default_energy_fn(s.topology)
+    theta = {"eps_hb": torch.tensor(float(efn.params_dict(include_dependent=False)["eps_hb"]), dtype=torch.float64, requires_grad=True)}
+    old = functional.FRAME_CHUNK
+    functional.FRAME_CHUNK = 2  # three chunks for the six test frames
+    try:
+        outs = []
+        for host in (False, True):
+            th = {k: v.detach().clone().requires_grad_(True) for k, v in theta.items()}
+            cc, qq = torch.tensor(c), torch.tensor(q)
+            cc, qq = (cc.pin_memory(), qq.pin_memory()) if host else (cc.to(DEV), qq.to(DEV))
+            e = efn.with_params(th).map(RigidBody(cc, Quaternion(qq)))
+            assert e.is_cuda
+            (e * torch.arange(1, e.shape[0] + 1, device=e.device, dtype=e.dtype)).sum().backward()
+            outs.append((e.detach().cpu().numpy(), float(th["eps_hb"].grad)))
+        np.testing.assert_array_equal(outs[0][0], outs[1][0])
+        assert outs[0][1] == outs[1][1]
+        with pytest.raises(_lib.MythosB200Error):
+            efn.map(RigidBody(torch.tensor(c), Quaternion(torch.tensor(q))))
+    finally:
+        functional.FRAME_CHUNK = old
