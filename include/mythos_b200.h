@@ -431,6 +431,15 @@ int mythos_b200_backbone_sites_f64(void* cuda_stream, const mb_model* model, int
 int mythos_b200_backbone_sites_f32(void* cuda_stream, const mb_model* model, int64_t n_total, const void* center, const void* quat,
                                    void* out, const int32_t* nt_type, int32_t n);
 
+/* the two point sets of the support-tagged build in one pass: centres and backbone sites of all frames as float32, brought
+ * near the origin (model->box periodic: primary image; free space: relative to each frame's first nucleotide), and the
+ * largest coordinate magnitude written (float, atomically maxed into *extent, which the caller zeroes): float32 builds
+ * with cutoffs widened by 1e-3 are supersets of the float64 supports as long as *extent stays below ~1500 */
+int mythos_b200_support_points_f64(void* cuda_stream, const mb_model* model, int32_t n, int32_t n_frames, const void* center,
+                                   const void* quat, const int32_t* nt_type, void* out_center_f32, void* out_site_f32, void* extent_f32);
+int mythos_b200_support_points_f32(void* cuda_stream, const mb_model* model, int32_t n, int32_t n_frames, const void* center,
+                                   const void* quat, const int32_t* nt_type, void* out_center_f32, void* out_site_f32, void* extent_f32);
+
 /* ---- rigid-body Langevin (BAOAB) step -------------------------------------------------------------------------
  * One call = B(dt/2) A(dt/2) O A(dt/2) on the state, i.e. everything of a step up to the force evaluation, or
  * the closing B(dt/2) kick; the caller evaluates the new force (mythos_b200_energy_*) in between. */

@@ -177,6 +177,8 @@ _SIGNATURES = {
     "mythos_b200_energy_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
     "mythos_b200_backbone_sites_f64": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "mythos_b200_backbone_sites_f32": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "mythos_b200_support_points_f64": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int32, C.c_int32] + [C.c_void_p] * 6),
+    "mythos_b200_support_points_f32": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int32, C.c_int32] + [C.c_void_p] * 6),
     "mythos_b200_nl_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "mythos_b200_nl_build_f64": (C.c_int, [C.c_void_p, C.POINTER(NlArgs)]),
     "mythos_b200_nl_build_f32": (C.c_int, [C.c_void_p, C.POINTER(NlArgs)]),

@@ -257,6 +257,79 @@ static int backbone_sites_impl(cudaStream_t s, const mb_model* m, int64_t n_tota
   return MB_OK;
 }
 }  // namespace mb
+namespace mb {
+// centres and backbone sites of all frames as float32, brought near the origin (periodic: primary image; free space:
+// relative to the frame's first nucleotide / its backbone site), plus the largest coordinate magnitude written
+template <class T>
+__global__ void k_support_points(Geom<T> g0, Geom<T> g1, const int32_t* __restrict__ nt_type, int n, long long n_total,
+                                 const T* __restrict__ center, const T* __restrict__ quat, T bx, T by, T bz,
+                                 float* __restrict__ out_c, float* __restrict__ out_s, float* __restrict__ extent) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float m = 0.f;
+  if (idx < n_total) {
+    const long long first = idx - idx % n;
+    T q[4], q0[4];
+    const Nuc<T> nu = load_nuc(center, quat, idx, q);
+    const Geom<T>& g = (nt_type && nt_type[idx % n] == 2) ? g1 : g0;
+    V3<T> c = nu.c, b = site(nu, g.back[0], g.back[1], g.back[2]);
+    const T box[3] = {bx, by, bz};
+    if (bx > T(0)) {
+      T* pc[3] = {&c.x, &c.y, &c.z};
+      T* pb[3] = {&b.x, &b.y, &b.z};
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        T v = fmod(*pc[d], box[d]);
+        *pc[d] = v < T(0) ? v + box[d] : v;
+        v = fmod(*pb[d], box[d]);
+        *pb[d] = v < T(0) ? v + box[d] : v;
+      }
+    } else {
+      const Nuc<T> n0 = load_nuc(center, quat, first, q0);
+      const Geom<T>& gf = (nt_type && nt_type[0] == 2) ? g1 : g0;
+      const V3<T> b0 = site(n0, gf.back[0], gf.back[1], gf.back[2]);
+      c = c - n0.c;
+      b = b - b0;
+    }
+    out_c[3 * idx] = float(c.x);
+    out_c[3 * idx + 1] = float(c.y);
+    out_c[3 * idx + 2] = float(c.z);
+    out_s[3 * idx] = float(b.x);
+    out_s[3 * idx + 1] = float(b.y);
+    out_s[3 * idx + 2] = float(b.z);
+    m = fmaxf(fmaxf(fmaxf(fabsf(float(c.x)), fabsf(float(c.y))), fabsf(float(c.z))),
+              fmaxf(fmaxf(fabsf(float(b.x)), fabsf(float(b.y))), fabsf(float(b.z))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(extent), __float_as_int(m));  // non-negative floats order like ints
+}
+template <class T>
+static int support_points_impl(cudaStream_t s, const mb_model* m, int32_t n, int32_t n_frames, const void* center, const void* quat,
+                               const int32_t* nt_type, void* out_center, void* out_site, void* extent) {
+  MB_REQUIRE(m && center && quat && out_center && out_site && extent && n > 0 && n_frames > 0, MB_EINVAL_SHAPE,
+             "support_points: missing arguments");
+  MB_REQUIRE(m->n_banks == 1 || nt_type, MB_EINVAL_SHAPE, "support_points: nt_type (N) required for the 3-bank model");
+  Geom<T> g0, g1;
+  g0.load(m->geom[0]);
+  g1.load(m->geom[1]);
+  const long long total = (long long)n * n_frames;
+  k_support_points<T><<<ceil_div(total, 256), 256, 0, s>>>(g0, g1, m->n_banks > 1 ? nt_type : nullptr, n, total,
+                                                            static_cast<const T*>(center), static_cast<const T*>(quat), T(m->box[0]),
+                                                            T(m->box[1]), T(m->box[2]), static_cast<float*>(out_center),
+                                                            static_cast<float*>(out_site), static_cast<float*>(extent));
+  MB_CUDA_CHECK(cudaGetLastError());
+  return MB_OK;
+}
+}  // namespace mb
+extern "C" int mythos_b200_support_points_f64(void* stream, const mb_model* m, int32_t n, int32_t n_frames, const void* center,
+                                              const void* quat, const int32_t* nt_type, void* out_center, void* out_site, void* extent) {
+  return mb::support_points_impl<double>(static_cast<cudaStream_t>(stream), m, n, n_frames, center, quat, nt_type, out_center, out_site, extent);
+}
+extern "C" int mythos_b200_support_points_f32(void* stream, const mb_model* m, int32_t n, int32_t n_frames, const void* center,
+                                              const void* quat, const int32_t* nt_type, void* out_center, void* out_site, void* extent) {
+  return mb::support_points_impl<float>(static_cast<cudaStream_t>(stream), m, n, n_frames, center, quat, nt_type, out_center, out_site, extent);
+}
+
 extern "C" int mythos_b200_backbone_sites_f64(void* stream, const mb_model* m, int64_t n_total, const void* center, const void* quat, void* out,
                                               const int32_t* nt_type, int32_t n) {
   return mb::backbone_sites_impl<double>(static_cast<cudaStream_t>(stream), m, n_total, center, quat, out, nt_type, n);

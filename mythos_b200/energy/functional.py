@@ -175,6 +175,8 @@ class CellListPairs:
     # the build keeps only pairs inside the support of some term and tags which; the frame-resident kernel then queues
     # them without touching coordinates.  Used when that kernel applies (one bank, no position gradients).
     tag: tuple | None = None
+    tag_float32: bool = True  # run the (superset) tagged builds in float32; cleared by verify() if the system is too extended
+    _extents: list = dc.field(default_factory=list)
     tag_for_list_kernels: bool = False  # opt-in: support-tagged lists also on the list-kernel route (forces, large systems)
     tagged_capacity: int = 0
     last_split: torch.Tensor | None = None  # (F) of the last tagged chunk: entries before it are short-range pairs
@@ -203,14 +205,24 @@ class CellListPairs:
             return pairs, 2 * self.capacity, count
         model, r_sr, r_db = self.tag[:3]
         nt_type = self.tag[3] if len(self.tag) > 3 else None
-        sites = backbone_sites(model, c, quat.detach(), nt_type) if r_db > 0 else None
         # The tagged builds only have to be SUPERSETS of the supports (the kernels apply the exact tests again), so they run
-        # in float32 with the cutoffs widened by far more than the rounding of the coordinates: half the record bytes and
-        # FP32 instead of FP64 distance arithmetic in the walks.
-        if c.dtype == torch.float64:
-            c = c.float()
-            sites = None if sites is None else sites.float()
+        # in float32 with the cutoffs widened by 1e-3: half the record bytes and FP32 instead of FP64 distance arithmetic in
+        # the walks.  One kernel writes both point sets as float32 brought near the origin (periodic: primary image; free
+        # space: relative to the frame's first nucleotide -- distances do not change) and their largest magnitude, which
+        # verify() checks: beyond 1500 length units float32 could not resolve 1e-3 and the pass is redone in float64.
+        extent = None
+        if self.tag_float32:
+            extent = torch.zeros(1, dtype=torch.float32, device=c.device)
+            c32, s32 = torch.empty(c.shape, dtype=torch.float32, device=c.device), torch.empty(c.shape, dtype=torch.float32, device=c.device)
+            fn = getattr(_lib.lib(), f"mythos_b200_support_points_{_lib.suffix(c.dtype)}")
+            with torch.cuda.device(c.device):
+                _lib.check(fn(_lib.current_stream(c.device), C.pointer(model), c.shape[1], c.shape[0], c.contiguous().data_ptr(),
+                              quat.detach().to(c.dtype).contiguous().data_ptr(), _lib.ptr(nt_type), c32.data_ptr(), s32.data_ptr(),
+                              extent.data_ptr()), "mythos_b200_support_points")
+            c, sites = c32, (s32 if r_db > 0 else None)
             r_sr, r_db = r_sr + 1e-3, (r_db + 1e-3 if r_db > 0 else r_db)
+        else:
+            sites = backbone_sites(model, c, quat.detach(), nt_type) if r_db > 0 else None
 
         def both(cc, ss, cap):
             pairs, split, overflow, self.workspace = neighbors.build_pairs(cc, self.bonded, self.box, max(r_sr, 1e-6), 0.0, cap,
@@ -227,12 +239,21 @@ class CellListPairs:
             self.tagged_capacity = (max(int(int(count.max().item()) * 1.06) + 64, 64) + 3) // 4 * 4
         pairs, count, overflow, self.last_split = both(c, sites, self.tagged_capacity)
         self._pending.append((count, overflow))
+        if extent is not None:
+            self._extents.append(extent)
         return pairs, 2 * self.tagged_capacity, count
 
     def verify(self) -> bool:
         """True if every list built since the last call fitted its capacity; otherwise grows the capacity."""
         if not self._pending:
             return True
+        if self._extents:
+            too_far = float(torch.stack(self._extents).max().item()) > 1500.0
+            self._extents.clear()
+            if too_far:  # float32 cannot resolve the 1e-3 margin out there: redo the pass with float64 builds
+                self.tag_float32 = False
+                self._pending.clear()
+                return False
         worst = int(torch.stack([c.max() for c, _ in self._pending]).max().item())
         flags = int(torch.stack([o[0] for _, o in self._pending]).max().item())
         self._pending.clear()
@@ -320,6 +341,7 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
                 raise
             tagged, source.tag = False, None
             source._pending.clear()
+            source._extents.clear()
             continue
         if not isinstance(source, CellListPairs) or source.verify():
             break

@@ -227,3 +227,34 @@ def test_pinned_host_frames_are_streamed_and_give_identical_results(workload):
             efn.map(RigidBody(torch.tensor(c), Quaternion(torch.tensor(q))))
     finally:
         functional.FRAME_CHUNK = old
+
+
+def test_tagged_float32_builds_are_safe_far_from_the_origin_and_for_extended_systems():
+    """The support-tagged builds run in float32 on recentred coordinates: a trajectory far from the origin must give the
+    energies of the same trajectory at the origin, and a system too extended for float32 (two duplexes 4000 length units
+    apart) must fall back to float64 builds and still agree with plain lists."""
+    from mythos_b200.energy import functional
+    from mythos_b200.energy import model as kmodel
+    from mythos_b200.input.topology import AllPairs
+
+    s = synthetic.assembly(2, seed=6)
+    n = s.center.shape[0]
+    efn = dna2.create_default_energy_fn(s.topology).with_props(unbonded_neighbors=AllPairs(n))
+    c, q = synthetic.rejittered_frames(s, 4, seed0=21)
+    here = efn.map(RigidBody(torch.tensor(c, device=DEV), Quaternion(torch.tensor(q, device=DEV)))).cpu().numpy()
+    far = efn.map(RigidBody(torch.tensor(c + np.array([1.0e5, -3.0e4, 7.0e3]), device=DEV), Quaternion(torch.tensor(q, device=DEV)))).cpu().numpy()
+    np.testing.assert_allclose(far, here, rtol=1e-8)
+
+    c2 = c.copy()
+    c2[:, n // 2:, 0] += 4000.0  # second duplex far away: extent > 1500 -> float64 builds
+    plan = kmodel.plan_for(efn.energy_fns)
+    cd, qd = torch.tensor(c2, device=DEV), torch.tensor(q, device=DEV)
+    topo = plan.topology(n, cd.device)
+    params = plan.device_params(cd.device, torch.float64)
+    src = plan.pairs(cd.device, topo)
+    got = functional.energy_and_gradients(plan.model, topo, cd, qd, params, src, want_pos_grad=False)[0].cpu().numpy()
+    assert src.tag is not None and src.tag_float32 is False
+    plain = plan.pairs(cd.device, topo)
+    plain.tag = None
+    want = functional.energy_and_gradients(plan.model, topo, cd, qd, params, plain, want_pos_grad=False)[0].cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-11)
