@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=8192)
     ap.add_argument("--cpu-frames", type=int, default=6, help="frames in the CPU-oracle sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the md / forces_8k / forces_100k legs (profiling runs)")
     return ap.parse_args()
 
 
@@ -432,7 +433,7 @@ def main():
     # dependency latency, and measured 4x slower after the big passes (allocator state of the 936 MB streaming buffers) or
     # after the CPU oracle (its OpenMP workers keep spinning and slow the launch thread).
     md_line = forces_8k = forces_100k = None
-    if world == 1 and rank == 0:
+    if world == 1 and rank == 0 and not args.no_legs:
         md_line = md_benchmark(dev)
         forces_8k = force_benchmark(dev, 68, "dna2", 0, best,
                                     "configs[2]: oxDNA2 + Debye, synthetic 68-duplex assembly (N=8160), neighbour list, float64")
@@ -514,8 +515,8 @@ def main():
         "bound": "fp64", "kernel": "k_frame_energy<double,WP=1> (all terms of a frame; support-tagged pair lists from the device neighbour build)", "achieved": achieved, "peak": best, "unit": "TFLOP/s",
         "frac": achieved / best if best else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed ncu capture
-        # (profiles/r01_v5_k_frame_energy_details.csv: 542.4 MB + 11.7 MB); other shapes have no capture
-        "traffic": 0.5542e9 if (chunk == 1184 and n == 2040) else None,
+        # (profiles/r01_v6_k_frame_energy_details.csv: 543.8 MB + 15.4 MB), in bytes; other shapes have no capture
+        "traffic": 0.5592e9 if (chunk == 1184 and n == 2040) else None,
         "peak_source": "measured in this run (library FMA micro-benchmark, 148x32 blocks x 256 threads)",
         "kernel_ms_per_launch": k_ms, "frames_per_launch": chunk, "neighbour_build_ms_per_chunk": nl_ms,
         "share_of_step": k_ms / (k_ms + nl_ms),
