@@ -99,9 +99,13 @@ __device__ __forceinline__ void pairs_body(const EnergyDev<T>& a, long long k, u
 // ONE launch for bonded and unbonded pairs: blocks [0, 3 * bonded_chunks) evaluate one bonded term each for one chunk of
 // bonds (the three terms of a bond run in different blocks: the per-thread dependency chain -- what bounds small
 // systems such as the 60-bp MD duplex -- is a single term long), the remaining blocks one chunk of listed pairs each.
-// `split_unbonded`: short lists (the MD duplex) also spread the unbonded terms of a chunk of pairs over three blocks
-// (excluded volume + Debye | hydrogen bonding + cross stacking | coaxial stacking): the longest per-thread chain drops
-// from the sum of the terms to the longest group, at the price of loading each pair three times.
+// `split_unbonded`: short lists (the MD duplex) also spread the unbonded terms of a chunk of pairs over kSplit blocks
+// (excluded volume + Debye | hydrogen bonding | cross stacking | coaxial stacking): the longest per-thread chain drops
+// from the sum of the terms to the longest single term, at the price of loading each pair kSplit times (and of
+// computing the six shared angles in both the hydrogen-bonding and the cross-stacking block).
+constexpr int kSplit = 4;
+__constant__ unsigned kUnbondedGroups[kSplit] = {(1u << MB_TERM_UEXC) | (1u << MB_TERM_DEBYE), 1u << MB_TERM_HB, 1u << MB_TERM_CROSS,
+                                                 1u << MB_TERM_COAX};
 template <class T, bool WF, bool WP>
 __global__ void __launch_bounds__(kBlock) k_pairs(const EnergyDev<T> a, int bonded_chunks, int split_unbonded) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -115,9 +119,7 @@ __global__ void __launch_bounds__(kBlock) k_pairs(const EnergyDev<T> a, int bond
     mask &= 1u << (blockIdx.x % 3);  // MB_TERM_FENE, MB_TERM_BEXC, MB_TERM_STACK = 0, 1, 2
     if (!mask) return;
   } else if (split_unbonded) {
-    const unsigned groups[3] = {(1u << MB_TERM_UEXC) | (1u << MB_TERM_DEBYE), (1u << MB_TERM_HB) | (1u << MB_TERM_CROSS),
-                                1u << MB_TERM_COAX};
-    if (!(mask & groups[(blockIdx.x - 3 * bonded_chunks) % 3])) return;  // this block's term group is not enabled
+    if (!(mask & kUnbondedGroups[(blockIdx.x - 3 * bonded_chunks) % kSplit])) return;  // this block's term group is not enabled
   }
   for (int k = threadIdx.x; k < np; k += kBlock) {
     sP[k] = a.params[k];
@@ -129,10 +131,8 @@ __global__ void __launch_bounds__(kBlock) k_pairs(const EnergyDev<T> a, int bond
   } else {
     long long chunk = blockIdx.x - 3 * bonded_chunks;
     if (split_unbonded) {
-      const unsigned groups[3] = {(1u << MB_TERM_UEXC) | (1u << MB_TERM_DEBYE), (1u << MB_TERM_HB) | (1u << MB_TERM_CROSS),
-                                  1u << MB_TERM_COAX};
-      mask &= groups[chunk % 3];
-      chunk /= 3;
+      mask &= kUnbondedGroups[chunk % kSplit];
+      chunk /= kSplit;
     }
     pairs_body<T, WF, WP, false>(a, chunk * kBlock + threadIdx.x, mask, sP, sE, sAcc, np);
   }
@@ -146,7 +146,7 @@ static int launch_pairs(cudaStream_t s, const EnergyDev<T>& a, void* list_ws) {
   const bool lists = unbonded && list_ws != nullptr;  // phase-queued list kernels (list_kernels.cu) take the unbonded part
   long long pair_chunks = (unbonded && !lists) ? ceil_div(a.pair_capacity, kBlock) : 0;
   const int split = (pair_chunks > 0 && a.pair_capacity * a.n_frames < kListKernelMinPairs) ? 1 : 0;  // latency-bound sizes only
-  if (split) pair_chunks *= 3;
+  if (split) pair_chunks *= kSplit;
   if (3 * bonded_chunks + pair_chunks > 0) {
     dim3 grid((unsigned)(3 * bonded_chunks + pair_chunks), a.n_frames);
     k_pairs<T, WF, WP><<<grid, kBlock, smem, s>>>(a, bonded_chunks, split);
