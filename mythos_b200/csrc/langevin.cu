@@ -10,6 +10,8 @@
 //      L_k <- c1' L_k + sqrt(kT (1-c1'^2) I_k) xi_k;  p_q <- 2 S(q) [0, L]
 // Noise: counter-based Philox4x32-10 keyed by (seed, step, nucleotide), Box-Muller; or caller-injected normals
 // (used by the parity tests, since jax's threefry stream cannot be reproduced).
+#include <cmath>
+
 #include "common.cuh"
 
 namespace mb {
@@ -74,6 +76,8 @@ struct LangevinDev {
   const T* noise;
   int zero_forces;
   T dt, kT, gamma_c, gamma_q, mass, inertia[3], box[3];
+  // uniform constants hoisted off the per-nucleotide dependency chain (computed once on the host, in double)
+  T inv_mass, inv4I[3], ou_c1, ou_c2, ou_r1, ou_r2[3];
   uint64_t seed, step;
   unsigned long long* step_ptr;        // device-side step counter (CUDA-graph replays), overrides `step`; [1] = block counter
   int advance;                         // add 1 to *step_ptr once every block has read it
@@ -94,11 +98,11 @@ __device__ __forceinline__ void perm(int k, const T q[4], T o[4]) {
   }
 }
 template <class T>
-__device__ __forceinline__ void free_rotor(int k, T step, T Ik, T q[4], T p[4]) {
+__device__ __forceinline__ void free_rotor(int k, T step, T inv4Ik, T q[4], T p[4]) {
   T pq[4], pp[4];
   perm(k, q, pq);
   perm(k, p, pp);
-  const T zeta = step * (p[0] * pq[0] + p[1] * pq[1] + p[2] * pq[2] + p[3] * pq[3]) / (T(4) * Ik);
+  const T zeta = step * (p[0] * pq[0] + p[1] * pq[1] + p[2] * pq[2] + p[3] * pq[3]) * inv4Ik;
   T s, c;
   const T z2 = zeta * zeta;
   if (z2 < T(0.0625)) {
@@ -171,12 +175,12 @@ __device__ __forceinline__ void langevin_body(const LangevinDev<T>& a, int i, un
   if (a.phase != 1) {
     for (int half = 0; half < 2; ++half) {
       // A(dt/2)
-      for (int d = 0; d < 3; ++d) c[d] = shift1(c[d] + h * pc[d] / a.mass, a.box[d]);
-      free_rotor(3, T(0.5) * h, a.inertia[2], q, pq);
-      free_rotor(2, T(0.5) * h, a.inertia[1], q, pq);
-      free_rotor(1, h, a.inertia[0], q, pq);
-      free_rotor(2, T(0.5) * h, a.inertia[1], q, pq);
-      free_rotor(3, T(0.5) * h, a.inertia[2], q, pq);
+      for (int d = 0; d < 3; ++d) c[d] = shift1(c[d] + h * pc[d] * a.inv_mass, a.box[d]);
+      free_rotor(3, T(0.5) * h, a.inv4I[2], q, pq);
+      free_rotor(2, T(0.5) * h, a.inv4I[1], q, pq);
+      free_rotor(1, h, a.inv4I[0], q, pq);
+      free_rotor(2, T(0.5) * h, a.inv4I[1], q, pq);
+      free_rotor(3, T(0.5) * h, a.inv4I[2], q, pq);
       if (half == 0) {
         // O(dt)
         double z[6];
@@ -185,16 +189,15 @@ __device__ __forceinline__ void langevin_body(const LangevinDev<T>& a, int i, un
         } else {
           normals6(a.seed, (uint64_t)step_now, uint32_t(i), z);
         }
-        const T c1 = exp(-a.gamma_c * a.dt);
-        const T c2 = sqrt(a.kT * (T(1) - c1 * c1) * a.mass);
+        const T c1 = a.ou_c1, c2 = a.ou_c2;
         for (int d = 0; d < 3; ++d) pc[d] = c1 * pc[d] + c2 * T(z[d]);
-        const T r1 = exp(-a.gamma_q * a.dt);
+        const T r1 = a.ou_r1;
         T L[3];
         for (int k = 1; k <= 3; ++k) {
           T pk[4];
           perm(k, q, pk);
           const T Lk = T(0.5) * (pq[0] * pk[0] + pq[1] * pk[1] + pq[2] * pk[2] + pq[3] * pk[3]);
-          L[k - 1] = r1 * Lk + sqrt(a.kT * (T(1) - r1 * r1) * a.inertia[k - 1]) * T(z[2 + k]);
+          L[k - 1] = r1 * Lk + a.ou_r2[k - 1] * T(z[2 + k]);
         }
         // p = 2 S(q) [0, L] = 2 sum_k L_k P_k q
         for (int d = 0; d < 4; ++d) pq[d] = T(0);
@@ -246,6 +249,17 @@ static int langevin_impl(cudaStream_t s, const mb_langevin_args* x) {
   for (int d = 0; d < 3; ++d) {
     a.inertia[d] = T(x->inertia[d]);
     a.box[d] = T(x->box[d]);
+  }
+  {
+    const double c1 = exp(-x->gamma_center * x->dt), r1 = exp(-x->gamma_quat * x->dt);
+    a.inv_mass = T(1.0 / x->mass);
+    a.ou_c1 = T(c1);
+    a.ou_c2 = T(sqrt(x->kT * (1.0 - c1 * c1) * x->mass));
+    a.ou_r1 = T(r1);
+    for (int d = 0; d < 3; ++d) {
+      a.inv4I[d] = T(1.0 / (4.0 * x->inertia[d]));
+      a.ou_r2[d] = T(sqrt(x->kT * (1.0 - r1 * r1) * x->inertia[d]));
+    }
   }
   a.seed = x->seed;
   a.step = x->step;
