@@ -443,7 +443,7 @@ def main():
     torch.cuda.empty_cache()
     for _ in range(args.warmup):
         device_pass(e_ref)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("MB_NO_CLOCK_SAMPLER")) else None
     ms_total, (loss, neff, dp, _) = timed(lambda: device_pass(e_ref), args.steps)
     ms_step = ms_total / args.steps
     value = F / (ms_step * 1e-3)
@@ -485,13 +485,14 @@ def main():
     launches, nl_launches = [], []
     src = plan.pairs(dev, topo)  # the step's own pair source: support-tagged device lists
     tagged = src.tag is not None
-    tpairs, tstride, tcount = src.chunk(slice(0, chunk), cc, qq, tagged=True)
-    u["kept_by_tagged_build"] = float(tcount.double().mean())
+    tpairs, tstride, tcount = src.chunk(slice(0, chunk), cc, qq, tagged=True, slots=True)
+    u["kept_by_tagged_build"] = float(src.last_valid_count.double().mean())
+    u["list_entries_with_slot_padding"] = tstride // 2
     for _ in range(5):
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         torch.cuda.synchronize(dev)
         e0.record()
-        src.chunk(slice(0, chunk), cc, qq, tagged=True)
+        src.chunk(slice(0, chunk), cc, qq, tagged=True, slots=True)
         e1.record()
         # the hot kernel exactly as the timed step runs it: all terms, E + J rows, the chunk's device pair lists streamed
         functional._launch(plan.model, topo, cc, qq, params_dev, tpairs, tstride, _lib.ALL_TERMS, ones[:chunk], True, False, True, True,
@@ -510,7 +511,7 @@ def main():
 
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    alg_bytes = chunk * (n * 7 * 8 + 8 * u["kept_by_tagged_build"] + 232 * 8 + 64)  # frame + tagged pair list in, J row + terms row out
+    alg_bytes = chunk * (n * 7 * 8 + 8 * u["kept_by_tagged_build"] + 232 * 8 + 64)  # frame + tagged pairs in, J row + terms row out (slot padding not counted)
     roofline = {
         "bound": "fp64", "kernel": "k_frame_energy<double,WP=1> (all terms of a frame; support-tagged pair lists from the device neighbour build)", "achieved": achieved, "peak": best, "unit": "TFLOP/s",
         "frac": achieved / best if best else None,
@@ -534,7 +535,7 @@ def main():
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                         "sample": f"{args.cpu_frames} frames of the same workload (oracle: torch-f64 restatement of the reference algorithm, autograd for dE/dparams)"}
 
-    n_chunks = -(-(hi - lo) // functional.FRAME_CHUNK)  # per chunk: backbone sites + 18 neighbour-build kernels + 1 frame kernel
+    n_chunks = -(-(hi - lo) // functional.FRAME_CHUNK)  # per chunk: support points + 2 x 11 neighbour-build kernels + 1 frame kernel
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -543,7 +544,7 @@ def main():
                    "l2": "inputs larger than L2 (frames 936 MB + 0.8 GB of pair lists per 1184-frame chunk)", "n_theta": len(theta),
                    "loss": float(loss.detach()), "n_eff": float(neff.detach()), "grad_norm": float(dp.norm())},
         "e2e": {"value": F / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": args.steps * (n_chunks * 20 + 1),  # k_nl_* + k_frame_energy per chunk, k_weights per step (torch glue not counted)
+        "gpu_launches": args.steps * (n_chunks * 24 + 1),  # k_nl_* + k_frame_energy per chunk, k_weights per step (torch glue not counted)
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "md": md_line, "forces_8k": forces_8k,
         "forces_100k": forces_100k,
     }

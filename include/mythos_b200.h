@@ -411,11 +411,21 @@ typedef struct mb_nl_args {
   uint32_t _pad2;
   const int32_t* append_count; /* MB_NL_TAG_SUPPORTS: (F) entries already in each frame's list; this build appends after
                                 * them and `count` receives the new totals (may alias append_count), or NULL      */
+  int32_t lane_slots;     /* MB_NL_WARP_SLOTS: partners staged per nucleotide (<= 256)                              */
+  int32_t _pad3;
+  int64_t slot_base;      /* MB_NL_WARP_SLOTS: first entry of this build's slots in each frame's list               */
+  int64_t slot_width;     /* MB_NL_WARP_SLOTS: entries per warp slot; slot_base + ceil(n/32)*slot_width <= capacity */
 } mb_nl_args;
 #define MB_NL_TAG_SUPPORTS 0x2u /* internal contract with mythos_b200_energy_* (MB_FLAG_TAGGED_PAIRS): `tag_bits` are OR-ed
                          * into pairs[1][k] (the index is pairs[1][k] & 0x1fffffff) and the build may append to a list.  The
                          * host builds the centres at the short-range cutoff (bit 30) and the backbone sites at the Debye
                          * cutoff (bit 29) into one list: only pairs inside the support of some term, labelled with it.  */
+#define MB_NL_WARP_SLOTS 0x4u /* one-pass build: warp w (32 consecutive nucleotides in cell order) writes its pairs into entries
+                         * [slot_base + w*slot_width, +slot_width) of the frame's list and pads the rest of the slot with n;
+                         * `capacity` is the list stride; tag_bits are honoured; count accumulates over the builds sharing
+                         * a list (zeroed when slot_base == 0); *overflow bit 0: a slot was too narrow, bit 2: a nucleotide
+                         * had more than lane_slots partners; max_row (F,2) = longest nucleotide row, largest warp total.
+                         * Consumers scan the whole capacity (pair_count = NULL).                                       */
 #define MB_NL_ROWS 0x1u /* one-pass build: instead of a compact list, row k-major slots of width capacity / n per nucleotide
                          * (entry k * n + p = k-th partner of the p-th nucleotide in cell order), unused slots = n (the
                          * padding value); *overflow bit 0 is set if a row is too narrow; count = pairs found.  Consumers

@@ -34,6 +34,7 @@ FLAG_GENERIC_KERNEL = 0x2
 FLAG_LIST_KERNEL = 0x4
 NL_ROWS = 0x1
 NL_TAG_SUPPORTS = 0x2
+NL_WARP_SLOTS = 0x4
 FLAG_TAGGED_PAIRS = 0x8
 MAX_BANKS = 3
 STATUS = {0: "MB_OK", 1: "MB_EINVAL_SHAPE", 2: "MB_EINVAL_MODEL", 3: "MB_ECAPACITY", 4: "MB_ECUDA"}
@@ -127,6 +128,10 @@ class NlArgs(C.Structure):
         ("tag_bits", C.c_uint32),
         ("_pad2", C.c_uint32),
         ("append_count", C.c_void_p),
+        ("lane_slots", C.c_int32),
+        ("_pad3", C.c_int32),
+        ("slot_base", C.c_int64),
+        ("slot_width", C.c_int64),
     ]
 
 

@@ -27,6 +27,9 @@
 // in the same list.  The host runs it twice -- on the centres with the short-range cutoff (tag bit 30) and on the backbone
 // sites with the Debye-Hueckel cutoff (tag bit 29) -- so that only pairs inside the support of some term are ever
 // written, each already labelled with the phase queue it belongs to; every other pair contributes exactly zero.
+// Warp-slot mode (MB_NL_WARP_SLOTS) replaces 6-8 by ONE walk: the partners a lane accepts are staged in shared memory and
+// the warp writes its pairs, coalesced and in a fixed order, into its own fixed-width slot of the list, padding the rest of
+// the slot with N.  No count pass, no scan, no replay -- at the price of ~20 % padding entries the consumers skip.
 // Rows mode (MB_NL_ROWS) replaces 6-8 by ONE walk that writes a fixed-width row per nucleotide with the unused slots set
 // to the padding value N: still a valid OrderedSparse list (consumers mask entries >= N wherever they are), at half the
 // cost -- the shape the energy kernels of this library are fed with.
@@ -75,6 +78,8 @@ struct NlDev {
   int32_t* count;
   int32_t* overflow;
   int32_t* max_row;  // rows mode: (F) longest row found, or nullptr
+  int lane_slots;                // warp-slot mode: partner ids staged per lane in shared memory
+  long long slot_base, slot_width;  // warp-slot mode: this build's slots start at slot_base of each frame's list
   uint32_t tag_bits;             // OR-ed into the second index of every pair written (MB_NL_TAG_SUPPORTS)
   const int32_t* append_count;   // (F) entries already in each frame's list: this build appends after them, or nullptr
   // workspace
@@ -356,10 +361,25 @@ __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, 
 // MODE 0: count, 1: fill (compact list), 2: rows (one pass: fixed-width row per nucleotide, slot-major)
 template <class T, int MODE, bool PERIODIC>
 __global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
-  constexpr bool FILL = MODE == 1, ROWS = MODE == 2;
-  const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= (long long)a.n * a.n_frames) return;
-  const int f = int(pos / a.n);
+  constexpr bool FILL = MODE == 1, ROWS = MODE == 2, SLOTS = MODE == 3;
+  extern __shared__ int32_t stage_raw[];  // SLOTS: per warp, 32 lanes x lane_slots partner ids
+  long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int f;
+  bool live = true;
+  long long gw = 0;  // SLOTS: warp index within the frame
+  if (SLOTS) {
+    // warps never straddle two frames: warp w of frame f covers cell-order positions [32 w, 32 w + 32) of that frame
+    const long long wpf = (a.n + 31) / 32, warp_id = pos >> 5;
+    f = int(warp_id / wpf);
+    gw = warp_id - (long long)f * wpf;
+    if (f >= a.n_frames) return;  // whole warp
+    const long long in_frame = gw * 32 + (threadIdx.x & 31);
+    live = in_frame < a.n;
+    pos = (long long)f * a.n + (live ? in_frame : 0);
+  } else {
+    if (pos >= (long long)a.n * a.n_frames) return;
+    f = int(pos / a.n);
+  }
   const NlGrid<T> g = a.grid[f];
   const NlRec<T> me = a.srec[pos];
   const int i = me.id;
@@ -435,7 +455,9 @@ __global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
     }
   };
   const int S = g.S, n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
-  const int n_rows = 1 + S + S * (2 * S + 1);
+  const int n_rows = live ? 1 + S + S * (2 * S + 1) : 0;
+  const int lane_slots = SLOTS ? a.lane_slots : 0;
+  int32_t* stage = SLOTS ? stage_raw + ((threadIdx.x >> 5) * 32 + (threadIdx.x & 31)) * lane_slots : nullptr;
   for (int row = 0; row < n_rows; ++row) {
     int dy = row, dz = 0;
     if (row > S) {
@@ -530,6 +552,7 @@ __global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
                 out0[(long long)found * a.n] = me_low ? i : j;
                 out1[(long long)found * a.n] = me_low ? j : i;
               }
+              if (SLOTS && found < lane_slots) stage[found] = j;
               ++found;
             }
           }
@@ -551,6 +574,55 @@ __global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
       }
   }
   if (MODE == 0) a.nbcount[pos] = found;
+  if (SLOTS) {
+    // One pass, no scan, no second walk: the warp's pairs go into the warp's own fixed-width slot of the frame's list
+    // (slot w = entries [slot_base + w * slot_width, + slot_width)); what is left of the slot is padded with N, which every
+    // consumer skips.  Deterministic (lane-major inside the slot).  A lane with more partners than lane_slots or a warp with
+    // more pairs than slot_width sets overflow bits 2 / 0; the longest lane row / warp total go to max_row for resizing.
+    const int lane = threadIdx.x & 31;
+    const int mine = found < lane_slots ? found : lane_slots;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int longest = found;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int y = __shfl_xor_sync(0xffffffffu, longest, o);
+      longest = y > longest ? y : longest;
+    }
+    int32_t* o0 = a.pairs + (long long)f * 2 * a.capacity + a.slot_base + gw * a.slot_width;
+    int32_t* o1 = o0 + a.capacity;
+    __syncwarp();
+    const int32_t* wstage = stage_raw + (threadIdx.x >> 5) * 32 * lane_slots;
+    for (int L = 0; L < 32; ++L) {  // owner by owner: the owner's partners are one coalesced run
+      const int cnt = __shfl_sync(0xffffffffu, mine, L), off = __shfl_sync(0xffffffffu, incl - mine, L);
+      const int iL = __shfl_sync(0xffffffffu, i, L);
+      for (int k = lane; k < cnt; k += 32) {
+        if (off + k < a.slot_width) {
+          const int j = wstage[L * lane_slots + k];
+          o0[off + k] = iL < j ? iL : j;
+          o1[off + k] = (iL < j ? j : iL) | tag_bits;
+        }
+      }
+    }
+    for (int k = total + lane; k < a.slot_width; k += 32) {
+      o0[k] = a.n;
+      o1[k] = a.n;
+    }
+    if (lane == 0) {
+      if (total > a.slot_width) atomicOr(a.overflow, 1);
+      if (longest > lane_slots) atomicOr(a.overflow, 4);
+      atomicAdd(&a.count[f], total < a.slot_width ? total : a.slot_width);
+      if (a.max_row) {
+        atomicMax(&a.max_row[2 * f], longest);
+        atomicMax(&a.max_row[2 * f + 1], total);
+      }
+    }
+  }
   if (ROWS) {
     for (int k = found; k < row_width; ++k) {  // unused slots carry the padding value N, as the tail of a compact list
       out0[(long long)k * a.n] = a.n;
@@ -591,11 +663,12 @@ __global__ void k_nl_rows_tail(NlDev<T> a) {
     out0[a.capacity + k] = a.n;
   }
 }
-__global__ void k_nl_zero_counts(int32_t* count, int32_t* max_row, int n_frames) {
+__global__ void k_nl_zero_counts(int32_t* count, int32_t* max_row, int n_frames, int per_frame) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n_frames) {
-    count[k] = 0;
-    if (max_row) max_row[k] = 0;
+    if (count) count[k] = 0;
+    if (max_row)
+      for (int m = 0; m < per_frame; ++m) max_row[per_frame * k + m] = 0;
   }
 }
 
@@ -691,7 +764,9 @@ static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
   a.overflow = x->overflow;
   a.max_row = (x->flags & MB_NL_ROWS) ? x->max_row : nullptr;
   const bool tag = (x->flags & MB_NL_TAG_SUPPORTS) != 0;
-  MB_REQUIRE(!tag || !(x->flags & MB_NL_ROWS), MB_EINVAL_SHAPE, "nl_build: support tags need the compact layout");
+  MB_REQUIRE(!tag || !(x->flags & MB_NL_ROWS), MB_EINVAL_SHAPE, "nl_build: support tags need the compact or the warp-slot layout");
+  a.lane_slots = 0;
+  a.slot_base = a.slot_width = 0;
   MB_REQUIRE(!tag || (x->n < (1 << 29) && !(x->tag_bits & 0x1fffffffu)), MB_EINVAL_SHAPE, "nl_build: tag bits must be in the top 3 bits, n < 2^29");
   a.tag_bits = tag ? x->tag_bits : 0u;
   a.append_count = tag ? x->append_count : nullptr;
@@ -716,8 +791,30 @@ static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
   scan_exclusive(s, a.cstart, FC, a.scan_tmp);
   k_nl_scatter<T><<<gr, kNlBlock, 0, s>>>(a);
   k_nl_rank<T><<<gr, kNlBlock, 0, s>>>(a);
-  if (x->flags & MB_NL_ROWS) {
-    k_nl_zero_counts<<<ceil_div(F, 256), 256, 0, s>>>(a.count, a.max_row, F);
+  if (x->flags & MB_NL_WARP_SLOTS) {
+    const long long wpf = (n + 31) / 32;
+    MB_REQUIRE(x->lane_slots > 0 && x->lane_slots <= 256 && x->slot_width > 0 && x->slot_base >= 0 &&
+                   x->slot_base + wpf * x->slot_width <= x->capacity,
+               MB_EINVAL_SHAPE, "nl_build: warp-slot mode needs 0 < lane_slots <= 256 and slot_base + ceil(n/32) * slot_width <= capacity");
+    a.lane_slots = x->lane_slots;
+    a.slot_base = x->slot_base;
+    a.slot_width = x->slot_width;
+    a.max_row = x->max_row;
+    a.tag_bits = x->tag_bits & 0xe0000000u;
+    // counts accumulate over the builds that share a list: only the first one (slot_base == 0) zeroes them
+    k_nl_zero_counts<<<ceil_div(F, 256), 256, 0, s>>>(x->slot_base == 0 ? a.count : nullptr, a.max_row, F, 2);
+    const long long warps = wpf * F;
+    const size_t smem = sizeof(int32_t) * (kNlBlock / 32) * 32 * (size_t)x->lane_slots;
+    const int blocks = ceil_div(warps * 32, kNlBlock);
+    if (periodic) {
+      MB_CUDA_CHECK(cudaFuncSetAttribute(k_nl_walk<T, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_nl_walk<T, 3, true><<<blocks, kNlBlock, smem, s>>>(a);
+    } else {
+      MB_CUDA_CHECK(cudaFuncSetAttribute(k_nl_walk<T, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_nl_walk<T, 3, false><<<blocks, kNlBlock, smem, s>>>(a);
+    }
+  } else if (x->flags & MB_NL_ROWS) {
+    k_nl_zero_counts<<<ceil_div(F, 256), 256, 0, s>>>(a.count, a.max_row, F, 1);
     if (periodic) k_nl_walk<T, 2, true><<<gr, kNlBlock, 0, s>>>(a);
     else k_nl_walk<T, 2, false><<<gr, kNlBlock, 0, s>>>(a);
     if (x->capacity % n) k_nl_rows_tail<T><<<dim3(1, F), 256, 0, s>>>(a);

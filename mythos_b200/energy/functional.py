@@ -155,6 +155,9 @@ class StaticPairs:
         return self.pairs, 0, None
 
 
+_SLOT_GEOMETRY: dict = {}  # (n, r_sr, r_db, box) -> ((lane_slots, slot_width) x 2) of the warp-slot tagged builds
+
+
 @dc.dataclass
 class CellListPairs:
     """All-pairs semantics (the reference's ``topology.unbonded_neighbors``) realised per frame on the device.
@@ -175,6 +178,9 @@ class CellListPairs:
     # the build keeps only pairs inside the support of some term and tags which; the frame-resident kernel then queues
     # them without touching coordinates.  Used when that kernel applies (one bank, no position gradients).
     tag: tuple | None = None
+    last_valid_count: torch.Tensor | None = None
+    slot_geometry: tuple | None = None  # warp-slot builds: ((lane_slots, slot_width) of the short-range build, of the Debye build)
+    _slot_stats: list = dc.field(default_factory=list)
     tag_float32: bool = True  # run the (superset) tagged builds in float32; cleared by verify() if the system is too extended
     _extents: list = dc.field(default_factory=list)
     tag_for_list_kernels: bool = False  # opt-in: support-tagged lists also on the list-kernel route (forces, large systems)
@@ -183,7 +189,52 @@ class CellListPairs:
     _last_tagged: bool = False
     _pending: list = dc.field(default_factory=list)
 
-    def chunk(self, sl: slice, center: torch.Tensor, quat: torch.Tensor | None = None, tagged: bool = False):
+    def _slot_chunk(self, c, sites, r_sr, r_db):
+        """The two tagged builds in the one-pass warp-slot layout (``MB_NL_WARP_SLOTS``): every warp of 32 cell-ordered
+        nucleotides writes its pairs into its own fixed-width slot of the list and pads the rest with N.  No count pass, no
+        scan, no second walk; the frame-resident kernel skips the padding entries like any padded OrderedSparse list."""
+        from mythos_b200.utils import neighbors
+
+        n = c.shape[1]
+        wpf = (n + 31) // 32
+
+        def run(cc, ss, geo):
+            (ka, wa), (kb, wb) = geo
+            cap = wpf * (wa + (wb if ss is not None else 0))
+            F = cc.shape[0]
+            pairs = torch.empty((F, 2, cap), dtype=torch.int32, device=cc.device)
+            count = torch.empty((F,), dtype=torch.int32, device=cc.device)
+            overflow = torch.zeros((1,), dtype=torch.int32, device=cc.device)
+            mra = torch.empty((F, 2), dtype=torch.int32, device=cc.device)
+            mrb = torch.empty((F, 2), dtype=torch.int32, device=cc.device) if ss is not None else None
+            _, _, _, self.workspace = neighbors.build_pairs(cc, self.bonded, self.box, max(r_sr, 1e-6), 0.0, cap, self.workspace,
+                                                            tag_bits=1 << 30, out=(pairs, count, overflow), max_row=mra,
+                                                            warp_slots=(ka, 0, wa))
+            if ss is not None:
+                neighbors.build_pairs(ss, self.bonded, self.box, r_db, 0.0, cap, self.workspace, tag_bits=1 << 29,
+                                      out=(pairs, count, overflow), max_row=mrb, warp_slots=(kb, wpf * wa, wb))
+            self.last_valid_count = count  # (F) pairs actually written (the kernels scan the whole padded capacity)
+            return pairs, cap, overflow, mra, mrb
+
+        def sized(lane_max, warp_max):
+            return min(max(int(lane_max * 1.5) + 4, 8), 256), (max(int(warp_max * 1.35) + 16, 32) + 3) // 4 * 4
+
+        # slot sizes are remembered per (system size, cutoffs, box): energy functions are rebuilt by every with_params(),
+        # and a fresh pair source must not pay a probe -- or worse, an overflow and a repeated pass -- on every step
+        self._geometry_key = (n, round(r_sr, 5), round(r_db, 5), tuple(self.box))
+        if self.slot_geometry is None:
+            self.slot_geometry = _SLOT_GEOMETRY.get(self._geometry_key)
+        if self.slot_geometry is None:  # probe the first frame with generous slots, size from what it needed
+            _, _, _, mra, mrb = run(c[:1], None if sites is None else sites[:1], ((256, 32 * 128), (256, 32 * 128)))
+            a_l, a_w = (int(v) for v in mra.max(0).values.tolist())
+            b_l, b_w = (int(v) for v in mrb.max(0).values.tolist()) if mrb is not None else (0, 0)
+            self.slot_geometry = _SLOT_GEOMETRY[self._geometry_key] = (sized(a_l, a_w), sized(b_l, b_w))
+        pairs, cap, overflow, mra, mrb = run(c, sites, self.slot_geometry)
+        self._pending.append((torch.zeros((1,), dtype=torch.int32, device=c.device), overflow))
+        self._slot_stats.append((mra, mrb))
+        return pairs, 2 * cap, None
+
+    def chunk(self, sl: slice, center: torch.Tensor, quat: torch.Tensor | None = None, tagged: bool = False, slots: bool = False):
         """Enqueue the build for one chunk of frames; overflow is checked once per pass by ``verify`` (one host sync).
 
         ``tagged``: two builds into ONE list -- the centres at the short-range cutoff (tag bit 30) and the backbone sites
@@ -224,6 +275,11 @@ class CellListPairs:
         else:
             sites = backbone_sites(model, c, quat.detach(), nt_type) if r_db > 0 else None
 
+        if slots:
+            if extent is not None:
+                self._extents.append(extent)
+            return self._slot_chunk(c, sites, r_sr, r_db)
+
         def both(cc, ss, cap):
             pairs, split, overflow, self.workspace = neighbors.build_pairs(cc, self.bonded, self.box, max(r_sr, 1e-6), 0.0, cap,
                                                                            self.workspace, tag_bits=1 << 30)
@@ -257,6 +313,27 @@ class CellListPairs:
         worst = int(torch.stack([c.max() for c, _ in self._pending]).max().item())
         flags = int(torch.stack([o[0] for _, o in self._pending]).max().item())
         self._pending.clear()
+        if self._slot_stats:  # warp-slot builds: bit 0 = a slot was too narrow, bit 2 = a lane row was too short
+            stats, self._slot_stats = self._slot_stats, []
+            if flags & 2:
+                raise _lib.MythosB200Error("neighbour build: a nucleotide has more than 4 bonded partners")
+            a = torch.stack([m.max(0).values for m, _ in stats]).max(0).values.tolist()
+            b = torch.stack([m.max(0).values for _, m in stats if m is not None]).max(0).values.tolist() if stats[0][1] is not None else [0, 0]
+            (ka, wa), (kb, wb) = self.slot_geometry
+
+            def fit(lane, warp, k, w, grow_only):
+                # wanted sizes: a comfortable margin over what this whole pass needed; slots are also tightened when they
+                # turn out much wider than that (padding entries cost the consumer a queue step per 3072 of them)
+                k2, w2 = min(int(lane * 1.5) + 4, 256), (int(warp * 1.12) + 16 + 3) // 4 * 4
+                if grow_only:
+                    return max(k, k2), max(w, w2)
+                return max(k, k2), (w2 if w > 1.1 * w2 else max(w, w2))
+
+            over = bool(flags & 5)
+            self.slot_geometry = (fit(a[0], a[1], ka, wa, over), fit(b[0], b[1], kb, wb, over))
+            if getattr(self, "_geometry_key", None) is not None:
+                _SLOT_GEOMETRY[self._geometry_key] = self.slot_geometry
+            return not over
         if flags & 2:
             raise _lib.MythosB200Error("neighbour build: a nucleotide has more than 4 bonded partners")
         self.max_count = max(self.max_count, worst)
@@ -308,6 +385,7 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
     tagged = (isinstance(source, CellListPairs) and source.tag is not None
               and not (flags & (_lib.FLAG_GENERIC_KERNEL | _lib.FLAG_LIST_KERNEL))
               and ((not want_pos and model.n_banks == 1 and center.shape[1] < 16384) or source.tag_for_list_kernels))
+    frame_route = tagged and not want_pos and model.n_banks == 1 and center.shape[1] < 16384 and not source.tag_for_list_kernels
     # frames in pinned host memory are streamed: chunk k+1 is copied on a side stream while chunk k is evaluated
     streamed = not center.is_cuda
     if streamed and want_pos:
@@ -328,7 +406,7 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
                 else:
                     c_sl, q_sl = center[sl], quat[sl]
                 if tagged:
-                    pairs, stride, count = source.chunk(sl, c_sl, q_sl, tagged=True)
+                    pairs, stride, count = source.chunk(sl, c_sl, q_sl, tagged=True, slots=frame_route)
                 else:
                     pairs, stride, count = source.chunk(sl, c_sl)
                 outs.append(
@@ -342,9 +420,12 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
             tagged, source.tag = False, None
             source._pending.clear()
             source._extents.clear()
+            source._slot_stats.clear()
             continue
         if not isinstance(source, CellListPairs) or source.verify():
             break
+        if os.environ.get("MYTHOS_B200_DEBUG"):
+            print("[mythos_b200] pair-list pass repeated:", source.slot_geometry, source.capacity, source.tagged_capacity, flush=True)
     return _merge(outs, want_terms, want_pos, want_par, per_frame_par)
 
 

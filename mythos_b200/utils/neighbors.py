@@ -34,6 +34,7 @@ def build_pairs(
     tag_bits: int = 0,
     out: tuple | None = None,
     append_count: torch.Tensor | None = None,
+    warp_slots: tuple[int, int, int] | None = None,
 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """Raw batched build.  center (F,N,3) on the device -> (pairs (F,2,capacity) int32, count (F,), overflow (1,), workspace).
 
@@ -67,11 +68,15 @@ def build_pairs(
     a.count, a.overflow = count.data_ptr(), overflow.data_ptr()
     a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
     a.flags = _lib.NL_ROWS if rows else 0
+    a.max_row = max_row.data_ptr() if (rows and max_row is not None) else None
+    if warp_slots is not None:  # one-pass layout: (lane_slots, slot_base, slot_width); max_row is (F,2)
+        a.flags |= _lib.NL_WARP_SLOTS
+        a.lane_slots, a.slot_base, a.slot_width = int(warp_slots[0]), int(warp_slots[1]), int(warp_slots[2])
+        a.max_row = max_row.data_ptr() if max_row is not None else None
     if tag_bits or append_count is not None:  # support tags (internal contract with this library's energy kernels)
         a.flags |= _lib.NL_TAG_SUPPORTS
         a.tag_bits = int(tag_bits)
         a.append_count = append_count.data_ptr() if append_count is not None else None
-    a.max_row = max_row.data_ptr() if (rows and max_row is not None) else None
     fn = getattr(_lib.lib(), f"mythos_b200_nl_build_{_lib.suffix(center.dtype)}")
     with torch.cuda.device(dev):
         _lib.check(fn(_lib.current_stream(dev), C.byref(a)), "mythos_b200_nl_build")

@@ -170,7 +170,7 @@ def test_frame_resident_kernel_equals_pair_kernel(workload, dtype):
         terms, _, _, J = functional.energy_and_gradients(plan.model, topo, cd, qd, params, src, cot=cot, want_pos_grad=False,
                                                          want_param_grad=True, per_frame_param_grad=True, flags=flags)
         if tagged:
-            assert src.tagged_capacity > 0 and src.tag is not None  # the tagged route really ran
+            assert src.slot_geometry is not None and src.tag is not None  # the tagged (warp-slot) route really ran
         outs.append((terms.cpu().numpy(), J.cpu().numpy()))
     tol = 1e-11 if dtype == torch.float64 else 2e-4
     np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=tol, atol=tol * np.abs(outs[1][0]).max())

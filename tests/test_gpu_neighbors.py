@@ -90,6 +90,49 @@ def test_rows_layout_same_pair_set(periodic):
     assert int(rov2.item()) & 1
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("periodic", [False, True])
+def test_warp_slot_layout_same_pair_set(periodic, dtype):
+    """MB_NL_WARP_SLOTS (one pass: each warp of 32 cell-ordered nucleotides fills its own fixed-width slot, rest padded with
+    N) holds the compact list's pair set, carries the tag bits, reports the sizes it needed and flags slots / lane rows
+    that are too small; two builds share one list through slot_base."""
+    s = synthetic.assembly(6, seed=3)
+    box = (9.5, 8.0, 26.0) if periodic else (0.0, 0.0, 0.0)
+    c = torch.tensor(np.stack([s.center, s.center + 0.3]), device=DEV, dtype=dtype)
+    bonded = torch.tensor(s.topology.bonded_neighbors)
+    n = s.center.shape[0]
+    wpf = (n + 31) // 32
+    ref, rcount, _, ws = neighbors.build_pairs(c, bonded, box, 2.0, 0.2, 60000)
+    ref2, _, _, ws = neighbors.build_pairs(c, bonded, box, 1.2, 0.0, 60000, ws)
+    W1, W2 = 32 * 64, 32 * 32
+    cap = wpf * (W1 + W2)
+    pairs = torch.empty((2, 2, cap), dtype=torch.int32, device=DEV)
+    count = torch.empty((2,), dtype=torch.int32, device=DEV)
+    ov = torch.zeros((1,), dtype=torch.int32, device=DEV)
+    mr1, mr2 = (torch.empty((2, 2), dtype=torch.int32, device=DEV) for _ in range(2))
+    neighbors.build_pairs(c, bonded, box, 2.0, 0.2, cap, ws, tag_bits=1 << 30, out=(pairs, count, ov), max_row=mr1, warp_slots=(96, 0, W1))
+    neighbors.build_pairs(c, bonded, box, 1.2, 0.0, cap, ws, tag_bits=1 << 29, out=(pairs, count, ov), max_row=mr2, warp_slots=(96, wpf * W1, W2))
+    assert int(ov.item()) == 0
+    for f in range(2):
+        p = pairs[f].cpu().numpy()
+        valid = p[0] < n
+        assert np.all(p[1][~valid] == n)
+        tag = p[1][valid] >> 29
+        idx = np.stack([p[0][valid], p[1][valid] & 0x1FFFFFFF])
+        first = set(zip(idx[0][tag == 2].tolist(), idx[1][tag == 2].tolist()))
+        second = set(zip(idx[0][tag == 1].tolist(), idx[1][tag == 1].tolist()))
+        assert first == to_set(ref[f], n) and second == to_set(ref2[f], n)
+        assert int(count[f]) == len(first) + len(second)
+        # the first build's entries all sit in its own slots
+        assert np.all(np.nonzero(valid)[0][tag == 2] < wpf * W1)
+    lane_max, warp_max = (int(x) for x in mr1.max(0).values.tolist())
+    assert 0 < lane_max <= 96 and lane_max <= warp_max <= W1
+    _, _, ov2, _ = neighbors.build_pairs(c, bonded, box, 2.0, 0.2, wpf * (warp_max - 1), ws, max_row=mr1, warp_slots=(96, 0, warp_max - 1))
+    assert int(ov2.item()) & 1
+    _, _, ov3, _ = neighbors.build_pairs(c, bonded, box, 2.0, 0.2, cap, ws, max_row=mr1, warp_slots=(lane_max - 1, 0, W1))
+    assert int(ov3.item()) & 4
+
+
 def test_capacity_overflow_is_reported_and_list_truncated():
     s = synthetic.assembly(2, seed=1)
     c = torch.tensor(s.center[None], device=DEV)
