@@ -258,3 +258,24 @@ def test_tagged_float32_builds_are_safe_far_from_the_origin_and_for_extended_sys
     plain.tag = None
     want = functional.energy_and_gradients(plan.model, topo, cd, qd, params, plain, want_pos_grad=False)[0].cpu().numpy()
     np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.parametrize("model", ["dna1", "rna2"])
+def test_all_pairs_route_for_models_without_and_with_debye(model):
+    """The default AllPairs route (support-tagged warp-slot lists + frame kernel) for oxDNA1 (no Debye-Hueckel: only the
+    short-range build runs) and RNA2, against the explicit all-pairs list through the one-thread-per-pair kernels."""
+    import mythos_b200.energy.dna1 as dna1
+    import mythos_b200.energy.rna2 as rna2
+    from mythos_b200.input.topology import AllPairs, unbonded_pairs
+
+    s = synthetic.assembly(5, seed=9)
+    top = s.topology
+    n = top.n_nucleotides
+    mod = dna1 if model == "dna1" else rna2
+    efn = mod.create_default_energy_fn(top)
+    c, q = synthetic.rejittered_frames(s, 3, seed0=31)
+    states = RigidBody(torch.tensor(c, device=DEV), Quaternion(torch.tensor(q, device=DEV)))
+    got = efn.with_props(unbonded_neighbors=AllPairs(n)).compute_terms_frames(states).cpu().numpy()
+    explicit = np.ascontiguousarray(unbonded_pairs(n, top.bonded_neighbors).T)
+    want = efn.with_props(unbonded_neighbors=explicit).compute_terms_frames(states).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-10 * np.abs(want).max())
