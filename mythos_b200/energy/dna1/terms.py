@@ -30,12 +30,23 @@ def _f4_fields(fam: str, ks: str | tuple) -> tuple[tuple[str, ...], tuple[str, .
     return tuple(req), tuple(dep)
 
 
+def _stacked(cfg, names) -> torch.Tensor:
+    vals = [bsf.as_t(getattr(cfg, nm)) for nm in names]
+    return torch.stack([v if v.dim() == 0 else v.reshape(()) for v in vals])
+
+
 def _f4_init(cfg, fam: str, ks) -> dict:
+    """All f4 blocks of one term in ONE vectorised evaluation of the smoothing formulas (same arithmetic per element): the
+    autograd graph the theta -> bank chain leaves behind is what the end-to-end DiffTRe step pays for on the host, and it
+    is a third as long this way."""
+    ks = list(ks)
+    b, dc = bsf.get_f4_smoothing_params(
+        _stacked(cfg, [f"a_{fam}_{k}" for k in ks]), _stacked(cfg, [f"theta0_{fam}_{k}" for k in ks]),
+        _stacked(cfg, [f"delta_theta_star_{fam}_{k}" for k in ks]),
+    )
     out = {}
-    for k in ks:
-        out[f"b_{fam}_{k}"], out[f"delta_theta_{fam}_{k}_c"] = bsf.get_f4_smoothing_params(
-            getattr(cfg, f"a_{fam}_{k}"), getattr(cfg, f"theta0_{fam}_{k}"), getattr(cfg, f"delta_theta_star_{fam}_{k}")
-        )
+    for k, bk, dk in zip(ks, b.unbind(0), dc.unbind(0)):
+        out[f"b_{fam}_{k}"], out[f"delta_theta_{fam}_{k}_c"] = bk, dk
     return out
 
 
@@ -69,9 +80,12 @@ class BondedExcludedVolumeConfiguration(BaseConfiguration):
     dependent_params = ("b_base", "dr_c_base", "b_back_base", "dr_c_back_base", "b_base_back", "dr_c_base_back")
 
     def init_params(self):
+        b, rc = bsf.get_f3_smoothing_params(  # all sites in one vectorised evaluation (see _f4_init)
+            _stacked(self, [f"dr_star_{s}" for s in self._sites]), _stacked(self, [f"sigma_{s}" for s in self._sites])
+        )
         out = {}
-        for s in self._sites:
-            out[f"b_{s}"], out[f"dr_c_{s}"] = bsf.get_f3_smoothing_params(getattr(self, f"dr_star_{s}"), getattr(self, f"sigma_{s}"))
+        for s, bs, rs in zip(self._sites, b.unbind(0), rc.unbind(0)):
+            out[f"b_{s}"], out[f"dr_c_{s}"] = bs, rs
         return self.replace(**out)
 
 
@@ -138,10 +152,11 @@ class StackingConfiguration(BaseConfiguration):
             self.dr0_stack, self.a_stack, self.dr_c_stack, self.dr_low_stack, self.dr_high_stack
         )
         out.update(_f4_init(self, "stack", self._f4))
-        for k in ("1", "2"):
-            out[f"b_neg_cos_phi{k}_stack"], out[f"neg_cos_phi{k}_c_stack"] = bsf.get_f5_smoothing_params(
-                getattr(self, f"a_stack_{k}"), getattr(self, f"neg_cos_phi{k}_star_stack")
-            )
+        b5, c5 = bsf.get_f5_smoothing_params(
+            _stacked(self, ["a_stack_1", "a_stack_2"]), _stacked(self, ["neg_cos_phi1_star_stack", "neg_cos_phi2_star_stack"])
+        )
+        for k, bk, ck in zip(("1", "2"), b5.unbind(0), c5.unbind(0)):
+            out[f"b_neg_cos_phi{k}_stack"], out[f"neg_cos_phi{k}_c_stack"] = bk, ck
         return self.replace(**out)
 
 

@@ -55,8 +55,11 @@ def pack_bank(configs: list[Any]) -> torch.Tensor:
             v = getattr(cfg, field, None) if field in cfg else None
             if v is None:
                 continue
-            v = as_t(v).to(torch.float64)
-            vals[idx] = v[sub] if sub is not None else v.reshape(())
+            v = as_t(v)
+            if v.dtype != torch.float64:
+                v = v.to(torch.float64)
+            # (no-op views would each leave a node in the autograd graph of the theta -> bank chain)
+            vals[idx] = v[sub] if sub is not None else (v if v.dim() == 0 else v.reshape(()))
     return torch.stack(vals)
 
 
