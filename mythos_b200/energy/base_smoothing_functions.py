@@ -33,6 +33,10 @@ def get_f1_smoothing_params(x0, a, xc, x_low, x_high):
         lead = a * x * (e(a * (x + 2 * xc)) - e(a * (x0 + 2 * xc)))
         return (lead + denom(x)) * e(-2 * a * xc) / (a * (e(a * x) - e(a * x0)))
 
+    if x_low.dim() == 0 and x_high.dim() == 0:  # both ends in one vectorised evaluation: half the autograd nodes
+        x = torch.stack([x_low, x_high])
+        b, c = solve_b(x), solve_xc(x)
+        return b[0], c[0], b[1], c[1]
     return solve_b(x_low), solve_xc(x_low), solve_b(x_high), solve_xc(x_high)
 
 
@@ -46,6 +50,10 @@ def get_f2_smoothing_params(x0, xc, x_low, x_high):
     def solve_xc(x):
         return (x * x0 - 2 * x0 * xc + xc**2) / (x - x0)
 
+    if x_low.dim() == 0 and x_high.dim() == 0:
+        x = torch.stack([x_low, x_high])
+        b, c = solve_b(x), solve_xc(x)
+        return b[0], c[0], b[1], c[1]
     return solve_b(x_low), solve_xc(x_low), solve_b(x_high), solve_xc(x_high)
 
 
