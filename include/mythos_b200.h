@@ -382,6 +382,8 @@ typedef struct mb_energy_args {
 #define MB_FLAG_LIST_KERNEL 0x4u /* explicit lists with forces / several banks: use the phase-queued list kernels even for short lists (needs workspace) */
 
 size_t mythos_b200_energy_workspace_bytes(int32_t n, int32_t n_frames, int64_t pair_capacity, int32_t real_bytes /* 4 or 8 */);
+int mythos_b200_frame_kernel_fits(int32_t n, int32_t real_bytes, int32_t want_params); /* 1 if a frame of n nucleotides fits the
+                                                  * frame-resident kernel's shared memory (single bank, explicit list) */
 int mythos_b200_energy_f64(void* cuda_stream, const mb_energy_args* a);
 int mythos_b200_energy_f32(void* cuda_stream, const mb_energy_args* a);
 

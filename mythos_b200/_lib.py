@@ -179,6 +179,7 @@ class WeightsArgs(C.Structure):
 _SIGNATURES = {
     "mythos_b200_energy_f64": (C.c_int, [C.c_void_p, C.POINTER(EnergyArgs)]),
     "mythos_b200_energy_f32": (C.c_int, [C.c_void_p, C.POINTER(EnergyArgs)]),
+    "mythos_b200_frame_kernel_fits": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     "mythos_b200_energy_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
     "mythos_b200_backbone_sites_f64": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "mythos_b200_backbone_sites_f32": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),

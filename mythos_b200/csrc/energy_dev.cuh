@@ -158,6 +158,8 @@ __device__ __forceinline__ void scatter_nuc_grad(const EnergyDev<T>& a, long lon
 template <class T>
 bool frame_kernel_eligible(const EnergyDev<T>& a);
 template <class T>
+bool frame_kernel_fits(int n, bool want_params);
+template <class T>
 int launch_frame_kernel(cudaStream_t s, const EnergyDev<T>& a, bool want_params);
 // unbonded terms of explicit pair lists of any size, phase-queued (list_kernels.cu)
 template <class T>

@@ -356,6 +356,10 @@ extern "C" int mythos_b200_backbone_sites_f32(void* stream, const mb_model* m, i
   return mb::backbone_sites_impl<float>(static_cast<cudaStream_t>(stream), m, n_total, center, quat, out, nt_type, n);
 }
 
+extern "C" int mythos_b200_frame_kernel_fits(int32_t n, int32_t real_bytes, int32_t want_params) {
+  if (n <= 0) return 0;
+  return (real_bytes == 4 ? mb::frame_kernel_fits<float>(n, want_params != 0) : mb::frame_kernel_fits<double>(n, want_params != 0)) ? 1 : 0;
+}
 extern "C" size_t mythos_b200_energy_workspace_bytes(int32_t n, int32_t n_frames, int64_t pair_capacity, int32_t real_bytes) {
   if (n <= 0 || n_frames <= 0 || pair_capacity <= 0) return 0;
   return real_bytes == 4 ? mb::list_workspace_bytes<float>(n, n_frames, pair_capacity)

@@ -966,6 +966,18 @@ int launch_frame_kernel(cudaStream_t s, const EnergyDev<T>& a, bool wp) {
   return cb ? launch_one<T, false, true>(s, a, L) : launch_one<T, false, false>(s, a, L);
 }
 
+template <class T>
+bool frame_kernel_fits(int n, bool wp) {
+  EnergyDev<T> a{};
+  a.n = n;
+  a.M.n_banks = 1;
+  a.all_pairs_cutoff = T(0);
+  bool cb;
+  FrameSmem L;
+  return n <= 60000 && pick_layout(a, wp, &cb, &L);
+}
+template bool frame_kernel_fits<float>(int, bool);
+template bool frame_kernel_fits<double>(int, bool);
 template bool frame_kernel_eligible<float>(const EnergyDev<float>&);
 template bool frame_kernel_eligible<double>(const EnergyDev<double>&);
 template int launch_frame_kernel<float>(cudaStream_t, const EnergyDev<float>&, bool);

@@ -384,7 +384,9 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
     # launch cost outweighs the pairs it saves (measured: 0.92 vs 0.85 ms at 100k nucleotides), so that is opt-in
     tagged = (isinstance(source, CellListPairs) and source.tag is not None
               and not (flags & (_lib.FLAG_GENERIC_KERNEL | _lib.FLAG_LIST_KERNEL))
-              and ((not want_pos and model.n_banks == 1 and center.shape[1] < 16384) or source.tag_for_list_kernels))
+              and ((not want_pos and model.n_banks == 1 and center.shape[1] < 16384
+                    and _lib.lib().mythos_b200_frame_kernel_fits(center.shape[1], center.element_size(), 1 if want_par else 0))
+                   or source.tag_for_list_kernels))
     frame_route = tagged and not want_pos and model.n_banks == 1 and center.shape[1] < 16384 and not source.tag_for_list_kernels
     # frames in pinned host memory are streamed: chunk k+1 is copied on a side stream while chunk k is evaluated
     streamed = not center.is_cuda

@@ -279,3 +279,30 @@ def test_all_pairs_route_for_models_without_and_with_debye(model):
     explicit = np.ascontiguousarray(unbonded_pairs(n, top.bonded_neighbors).T)
     want = efn.with_props(unbonded_neighbors=explicit).compute_terms_frames(states).cpu().numpy()
     np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-10 * np.abs(want).max())
+
+
+def test_map_of_a_system_too_large_for_the_frame_kernel_falls_back_to_the_list_kernels():
+    """N = 4320 does not fit the frame-resident kernel's shared memory in float64: the default AllPairs route must fall back
+    (plain device lists + list kernels) and still give the explicit-route energies and dE/dtheta."""
+    from mythos_b200 import _lib
+    from mythos_b200.energy import functional
+    from mythos_b200.energy import model as kmodel
+    from mythos_b200.input.topology import AllPairs
+
+    s = synthetic.assembly(36, seed=4)
+    n = s.center.shape[0]
+    efn = dna2.create_default_energy_fn(s.topology).with_props(unbonded_neighbors=AllPairs(n))
+    c, q = synthetic.rejittered_frames(s, 2, seed0=3)
+    th = {"k_cross": torch.tensor(float(efn.params_dict(include_dependent=False)["k_cross"]), dtype=torch.float64, requires_grad=True)}
+    e = efn.with_params(th).map(RigidBody(torch.tensor(c, device=DEV), Quaternion(torch.tensor(q, device=DEV))))
+    e.sum().backward()
+    plan = kmodel.plan_for(efn.energy_fns)
+    cd, qd = torch.tensor(c, device=DEV), torch.tensor(q, device=DEV)
+    topo = plan.topology(n, cd.device)
+    src = plan.pairs(cd.device, topo)
+    src.tag = None
+    terms, _, _, dp = functional.energy_and_gradients(plan.model, topo, cd, qd, plan.device_params(cd.device, torch.float64), src,
+                                                      want_pos_grad=False, want_param_grad=True, flags=_lib.FLAG_GENERIC_KERNEL)
+    np.testing.assert_allclose(e.detach().cpu().numpy(), terms.sum(1).cpu().numpy(), rtol=1e-11)
+    k = _lib.param_names().index("cross_stacking.k_cross")
+    assert np.isclose(float(th["k_cross"].grad), float(dp[k]), rtol=1e-9)
