@@ -37,8 +37,14 @@ namespace mb {
 constexpr int kLB = MB_LIST_THREADS;  // threads per CTA
 constexpr int kLWarps = kLB / 32;
 constexpr int kLQCap = 2 * kLB;
+#ifndef MB_DEBYE_MINBLOCKS
+#define MB_DEBYE_MINBLOCKS 1
+#endif
+#ifndef MB_DEBYE_UNROLL
+#define MB_DEBYE_UNROLL 2
+#endif
 constexpr int kDB = 256;            // threads per CTA of the Debye / filter pass
-constexpr int kDU = 2;              // list entries per thread and step (independent chains)
+constexpr int kDU = MB_DEBYE_UNROLL;  // list entries per thread and step (independent chains)
 
 typedef unsigned long long pk_t;
 __device__ __forceinline__ pk_t pk_make(int i, int j) { return (pk_t)(unsigned)i | ((pk_t)(unsigned)j << 32); }
@@ -178,7 +184,7 @@ __device__ __forceinline__ T list_sr_cut2(const EnergyDev<T>& a, const T* P, boo
 // ------------------------------------------------------------------------------------------------------------
 // Streaming pass: Debye-Hueckel + short-range filter.  grid = (CTAs, frames), grid-stride over list tiles.
 template <class T, bool WF, bool WP, bool MULTI>
-__global__ void __launch_bounds__(kDB) k_list_debye(const EnergyDev<T> a) {
+__global__ void __launch_bounds__(kDB, MB_DEBYE_MINBLOCKS) k_list_debye(const EnergyDev<T> a) {
   constexpr int NB = MULTI ? MB_MAX_BANKS : 1;
   __shared__ T sD[NB][6];  // kappa, prefactor, smoothing, r_cut, r_high of each bank; [5] = short-range cutoff^2
   __shared__ T sRed[kDB / 32][1 + (WP ? 5 * NB : 0)];
