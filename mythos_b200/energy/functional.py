@@ -303,22 +303,29 @@ class CellListPairs:
         """True if every list built since the last call fitted its capacity; otherwise grows the capacity."""
         if not self._pending:
             return True
-        if self._extents:
-            too_far = float(torch.stack(self._extents).max().item()) > 1500.0
-            self._extents.clear()
-            if too_far:  # float32 cannot resolve the 1e-3 margin out there: redo the pass with float64 builds
-                self.tag_float32 = False
-                self._pending.clear()
-                return False
-        worst = int(torch.stack([c.max() for c, _ in self._pending]).max().item())
-        flags = int(torch.stack([o[0] for _, o in self._pending]).max().item())
+        # one host read for everything this pass recorded (extent, longest list, overflow flags, slot statistics)
+        dev = self._pending[0][1].device
+        parts = [torch.stack(self._extents).max().double().reshape(1) if self._extents else torch.zeros(1, dtype=torch.float64, device=dev),
+                 torch.stack([c.max() for c, _ in self._pending]).max().double().reshape(1),
+                 torch.stack([o[0] for _, o in self._pending]).max().double().reshape(1)]
+        stats, self._slot_stats = self._slot_stats, []
+        if stats:
+            parts.append(torch.stack([m.max(0).values for m, _ in stats]).max(0).values.double())
+            if stats[0][1] is not None:
+                parts.append(torch.stack([m.max(0).values for _, m in stats]).max(0).values.double())
+        host = torch.cat(parts).tolist()
+        had_extents = bool(self._extents)
+        self._extents.clear()
         self._pending.clear()
-        if self._slot_stats:  # warp-slot builds: bit 0 = a slot was too narrow, bit 2 = a lane row was too short
-            stats, self._slot_stats = self._slot_stats, []
+        if had_extents and host[0] > 1500.0:  # float32 cannot resolve the 1e-3 margin out there: redo the pass with float64 builds
+            self.tag_float32 = False
+            return False
+        worst, flags = int(host[1]), int(host[2])
+        if stats:  # warp-slot builds: bit 0 = a slot was too narrow, bit 2 = a lane row was too short
             if flags & 2:
                 raise _lib.MythosB200Error("neighbour build: a nucleotide has more than 4 bonded partners")
-            a = torch.stack([m.max(0).values for m, _ in stats]).max(0).values.tolist()
-            b = torch.stack([m.max(0).values for _, m in stats if m is not None]).max(0).values.tolist() if stats[0][1] is not None else [0, 0]
+            a = host[3:5]
+            b = host[5:7] if len(host) > 5 else [0, 0]
             (ka, wa), (kb, wb) = self.slot_geometry
 
             def fit(lane, warp, k, w, grow_only):
