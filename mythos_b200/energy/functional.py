@@ -439,10 +439,29 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
 
 
 _COPY_STREAMS: dict = {}
+_PREFETCHED: dict = {}  # at most one entry: the first chunk of a pinned trajectory, copied ahead of its pass
+
+
+def prefetch_frames(center: torch.Tensor, quat: torch.Tensor) -> None:
+    """Start the host -> device copy of the first chunk of pinned host frames NOW, before the caller's host-side work
+    (the theta -> parameter-bank chain of a DiffTRe step), so the first kernels do not wait for PCIe.  A no-op for
+    device tensors; the copy is picked up by the next streamed pass over the same buffers."""
+    _PREFETCHED.clear()
+    if center.is_cuda or not (center.is_pinned() and quat.is_pinned() and torch.cuda.is_available()) or center.dim() != 3:
+        return
+    dev = torch.device("cuda", torch.cuda.current_device())
+    sl = slice(0, min(FRAME_CHUNK, center.shape[0]))
+    key = (center.data_ptr(), quat.data_ptr(), center.shape[0], sl.start, sl.stop, dev)
+    _PREFETCHED[key] = _fetch(center, quat, sl, dev)
 
 
 def _fetch(center: torch.Tensor, quat: torch.Tensor, sl: slice, dev):
     """Enqueue the host -> device copy of one chunk of frames on the device's copy stream; -> (center, quat, event)."""
+    if _PREFETCHED:
+        hit = _PREFETCHED.pop((center.data_ptr(), quat.data_ptr(), center.shape[0], sl.start, sl.stop, dev), None)
+        _PREFETCHED.clear()
+        if hit is not None:
+            return hit
     stream = _COPY_STREAMS.get(dev)
     if stream is None:
         stream = _COPY_STREAMS[dev] = torch.cuda.Stream(device=dev)

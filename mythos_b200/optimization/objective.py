@@ -208,6 +208,12 @@ def allreduce_grads(grads: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
 # ------------------------------------------------------------------------------------------- loss
 def compute_loss(opt_params, energy_fn: EnergyFunction, beta, loss_fn, ref_states, ref_energies, observables):
     """loss, (n_eff, measured value, new energies) (``objective.py:198-232``)."""
+    if (isinstance(getattr(ref_states, "center", None), torch.Tensor) and not ref_states.center.is_cuda
+            and (_world()[1] == 1 or getattr(ref_states, "shard", None) is not None)):
+        # pinned host frames: their first chunk crosses PCIe while the host evaluates theta -> parameter bank below
+        from mythos_b200.energy import functional
+
+        functional.prefetch_frames(ref_states.center, ref_states.orientation.vec)
     energy_fn = energy_fn.with_params(opt_params)
     new_energies = sharded_map(energy_fn, ref_states)
     weights, neff = compute_weights_and_neff(beta, new_energies, ref_energies)

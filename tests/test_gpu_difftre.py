@@ -229,6 +229,52 @@ def test_pinned_host_frames_are_streamed_and_give_identical_results(workload):
         functional.FRAME_CHUNK = old
 
 
+def test_loss_and_grad_with_prefetched_pinned_frames_equals_device_frames(workload):
+    """``compute_loss_and_grad`` starts the copy of the first chunk of pinned host frames before the theta chain
+    (``functional.prefetch_frames``); loss and gradients must be those of device-resident frames, also when the pass
+    that follows uses other buffers than the prefetched ones (the stale copy is dropped)."""
+    from mythos_b200.energy import functional
+    from mythos_b200.optimization import objective
+
+    s, c, q = workload
+    efn = dna2.create_default_energy_fn(s.topology)
+    base = efn.params_dict(include_dependent=False)
+    theta = {k: torch.tensor(float(base[k]), dtype=torch.float64) for k in ("eps_hb", "a_stack", "q_eff")}
+    F = c.shape[0]
+    beta = torch.full((F,), 10.0, dtype=torch.float64, device=DEV)
+    obs = torch.linspace(-1.0, 1.0, F, dtype=torch.float64, device=DEV)
+
+    def loss_fn(ref_states, weights, energy_fn, opt_params, observables):
+        m = (weights * obs).sum()
+        return m, (("obs", m), None)
+
+    old = functional.FRAME_CHUNK
+    functional.FRAME_CHUNK = 4  # two chunks for the six test frames
+    try:
+        res = []
+        for host in (False, True):
+            cc, qq = torch.tensor(c), torch.tensor(q)
+            cc, qq = (cc.pin_memory(), qq.pin_memory()) if host else (cc.to(DEV), qq.to(DEV))
+            states = RigidBody(cc, Quaternion(qq))
+            with torch.no_grad():
+                e_ref = efn.map(states) + obs * 0.01
+            (l, _), g = objective.compute_loss_and_grad(theta, efn, beta, loss_fn, states, e_ref, [])
+            res.append((float(l), {k: float(v) for k, v in g.items()}))
+            if host:
+                assert not functional._PREFETCHED  # consumed by the pass
+                functional.prefetch_frames(cc.clone().pin_memory(), qq)  # a copy nobody picks up ...
+                assert functional._PREFETCHED
+                e_again = efn.map(states)  # ... is dropped by the next streamed pass over other buffers
+                assert not functional._PREFETCHED
+                np.testing.assert_allclose(e_again.cpu().numpy(), (e_ref - obs * 0.01).cpu().numpy(), rtol=1e-13)
+        # beta * E ~ 1e4 amplifies the last-bit summation-order noise of the energies in the weights: 1e-9, not bit-equal
+        np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-9)
+        for k in res[0][1]:
+            np.testing.assert_allclose(res[0][1][k], res[1][1][k], rtol=1e-8, atol=1e-12)
+    finally:
+        functional.FRAME_CHUNK = old
+
+
 def test_tagged_float32_builds_are_safe_far_from_the_origin_and_for_extended_systems():
     """The support-tagged builds run in float32 on recentred coordinates: a trajectory far from the origin must give the
     energies of the same trajectory at the origin, and a system too extended for float32 (two duplexes 4000 length units
