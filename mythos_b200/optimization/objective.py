@@ -236,13 +236,33 @@ def compute_loss_and_grad(opt_params: dict[str, torch.Tensor], energy_fn, beta, 
     return (loss.detach(), tuple(a.detach() if isinstance(a, torch.Tensor) else a for a in aux)), grads
 
 
+class _LazyWithParams:
+    """``energy_fn.with_params(params)`` evaluated on first use: the frames-free pass below hands it to ``loss_fn``, and
+    most loss functions never touch it -- the theta -> parameter chain (milliseconds of host time) is then not rebuilt."""
+
+    def __init__(self, energy_fn, params):
+        object.__setattr__(self, "_make", lambda: energy_fn.with_params(params))
+        object.__setattr__(self, "_built", None)
+
+    def _get(self):
+        if self._built is None:
+            object.__setattr__(self, "_built", self._make())
+        return self._built
+
+    def __getattr__(self, name):
+        return getattr(self._get(), name)
+
+    def __call__(self, *args, **kwargs):
+        return self._get()(*args, **kwargs)
+
+
 def _combine_sharded_grads(grads, leaves, loss_fn, ref_states, energy_fn, beta, ref_energies, observables, aux):
     rank, world = _world()
     # frames-free pass: weights held constant -> gradient of the loss through loss_fn's direct theta dependence only
     neff, _, new_e = aux
     w_const, _ = compute_weights_and_neff(beta, new_e.detach(), ref_energies)
     l2 = {k: v.detach().clone().requires_grad_(True) for k, v in leaves.items()}
-    loss2, _ = loss_fn(ref_states, w_const.detach(), energy_fn.with_params(l2), l2, observables)
+    loss2, _ = loss_fn(ref_states, w_const.detach(), _LazyWithParams(energy_fn, l2), l2, observables)
     direct = {k: torch.zeros_like(v) for k, v in l2.items()}
     if isinstance(loss2, torch.Tensor) and loss2.requires_grad:
         gd = torch.autograd.grad(loss2, list(l2.values()), allow_unused=True)

@@ -40,7 +40,8 @@ def _cpu_weights(beta, new_e, ref_e):
 def _loss_fn(ref_states, weights, energy_fn, opt_params, observables):
     obs = observables[0]
     m = (weights * obs).sum()
-    return (m - 0.3) ** 2 + 0.01 * opt_params["a"] ** 2, (("obs", m), None)  # direct theta dependence too
+    # direct theta dependence too: through opt_params and through the re-parameterised energy function
+    return (m - 0.3) ** 2 + 0.01 * opt_params["a"] ** 2 + 0.005 * energy_fn.theta["b"] ** 2, (("obs", m), None)
 
 
 def _worker(rank, world, port, out):
@@ -91,9 +92,10 @@ def test_two_rank_gradient_equals_single_process():
     efn = FakeEnergy()
     theta = {"a": torch.tensor(0.75, dtype=torch.float64, requires_grad=True), "b": torch.tensor(-0.1, dtype=torch.float64, requires_grad=True)}
     ref = efn.map(states).detach()
-    e = efn.with_params(theta).map(states)
+    efn_theta = efn.with_params(theta)
+    e = efn_theta.map(states)
     w, _ = _cpu_weights(torch.tensor(2.0, dtype=torch.float64), e, ref)
-    loss, _ = _loss_fn(states, w, efn, theta, [obs])
+    loss, _ = _loss_fn(states, w, efn_theta, theta, [obs])
     ga, gb = torch.autograd.grad(loss, [theta["a"], theta["b"]])
     for rank in (0, 1):
         l, grads, bounds, e_full = res[rank]
