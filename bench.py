@@ -484,6 +484,17 @@ def main():
 
     for _ in range(max(1, args.warmup - 1)):
         e2e_step()
+    if os.environ.get("MB_PROFILE_E2E") and rank == 0:  # development hook: host-side profile of one end-to-end step
+        import cProfile
+        import pstats
+
+        prof = cProfile.Profile()
+        prof.enable()
+        e2e_step()
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
+    elif os.environ.get("MB_PROFILE_E2E"):
+        e2e_step()
     ms_e2e, _ = timed(e2e_step, args.steps)
     ms_e2e /= args.steps
     clocks = sampler.stop() if sampler else None

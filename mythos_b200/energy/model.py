@@ -264,9 +264,20 @@ def support_cutoffs(plan: "Plan") -> tuple[float, float]:
     return r * (1.0 + 2e-6) + 1e-9, r_db
 
 
+def _kw_key(v):
+    # value identity of a transform_fn keyword (geometry constants are tensors: their bytes, not their repr -- formatting 40
+    # tensors cost 4 ms per DiffTRe step)
+    if isinstance(v, torch.Tensor):
+        t = v.detach()
+        return ("t", tuple(t.shape), str(t.dtype), (t if not t.is_cuda else t.cpu()).contiguous().numpy().tobytes())
+    return repr(v)
+
+
 def _prop_key(fn) -> tuple:
     box = space.box_of(fn.displacement_fn)
-    return (id(getattr(fn.transform_fn, "func", fn.transform_fn)), tuple(sorted((getattr(fn.transform_fn, "keywords", {}) or {}).items(), key=lambda kv: kv[0])).__repr__(), box, id(fn.seq), id(fn.bonded_neighbors), id(fn.unbonded_neighbors), fn.HYBRID)
+    kw = getattr(fn.transform_fn, "keywords", {}) or {}
+    return (id(getattr(fn.transform_fn, "func", fn.transform_fn)), tuple((k, _kw_key(kw[k])) for k in sorted(kw)), box, id(fn.seq),
+            id(fn.bonded_neighbors), id(fn.unbonded_neighbors), fn.HYBRID)
 
 
 def fusable_groups(fns: list) -> list[list[int]]:

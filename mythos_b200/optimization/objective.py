@@ -202,7 +202,14 @@ def allreduce_grads(grads: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
     dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
     flat = torch.stack([grads[k].reshape(()).to(torch.float64) for k in keys]).to(dev)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    return {k: flat[i].to(grads[k].device, grads[k].dtype) for i, k in enumerate(keys)}
+    back: dict = {}  # one copy per destination device, not one per parameter
+    out = {}
+    for i, k in enumerate(keys):
+        d = grads[k].device
+        if d not in back:
+            back[d] = flat.to(d)
+        out[k] = back[d][i].to(grads[k].dtype)
+    return out
 
 
 # ------------------------------------------------------------------------------------------- loss
