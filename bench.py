@@ -403,17 +403,21 @@ def main():
         return e_local if world == 1 else objective.gather_frames(e_local, F)
 
     def device_pass(e_ref):
-        terms, _, _, J = functional.energy_and_gradients(
-            plan.model, topo, c_dev, q_dev, params_dev, source, cot=ones, want_pos_grad=False, want_param_grad=True,
-            per_frame_param_grad=True)
-        e = gather(terms.sum(1)).requires_grad_(True)
-        w, neff = objective.compute_weights_and_neff(beta, e, e_ref)
-        loss = (w * obs).sum()
-        (g,) = torch.autograd.grad(loss, e)
-        dp = g[lo:hi] @ J
-        if world > 1:
-            dist.all_reduce(dp)
-        return loss, neff, dp, e.detach()
+        while True:
+            # the overflow flags of the pair lists are read once, AFTER the reweighting and the collectives are enqueued
+            with functional.deferred_verification() as checks:
+                terms, _, _, J = functional.energy_and_gradients(
+                    plan.model, topo, c_dev, q_dev, params_dev, source, cot=ones, want_pos_grad=False, want_param_grad=True,
+                    per_frame_param_grad=True)
+                e = gather(terms.sum(1)).requires_grad_(True)
+                w, neff = objective.compute_weights_and_neff(beta, e, e_ref)
+                loss = (w * obs).sum()
+                (g,) = torch.autograd.grad(loss, e)
+                dp = g[lo:hi] @ J
+                if world > 1:
+                    dist.all_reduce(dp)
+            if objective.all_ranks_ok(checks.ok()):  # the ranks agree: a repeat re-enters the collectives
+                return loss, neff, dp, e.detach()
 
     with torch.no_grad():
         t0, _, _, _ = functional.energy_and_gradients(plan.model, topo, c_dev, q_dev, params_dev, source, want_pos_grad=False)

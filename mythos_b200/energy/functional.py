@@ -431,11 +431,47 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
             source._extents.clear()
             source._slot_stats.clear()
             continue
+        if isinstance(source, CellListPairs) and _DEFERRED:
+            _DEFERRED[-1].sources.append(source)  # the caller reads the overflow flags after ITS launches (deferred_verification)
+            break
         if not isinstance(source, CellListPairs) or source.verify():
             break
         if os.environ.get("MYTHOS_B200_DEBUG"):
             print("[mythos_b200] pair-list pass repeated:", source.slot_geometry, source.capacity, source.tagged_capacity, flush=True)
     return _merge(outs, want_terms, want_pos, want_par, per_frame_par)
+
+
+_DEFERRED: list = []
+
+
+class deferred_verification:  # noqa: N801 - used as a context manager
+    """Inside this context the per-pass host read of the pair-list overflow flags is NOT done by the evaluation itself:
+    the caller enqueues everything that consumes the result (weights, loss, collectives) first and then calls ``ok()``
+    -- one host sync at the end instead of one in the middle that leaves the GPU idle while the rest is launched.
+    ``ok()`` False means a list overflowed (capacities have been grown): the results are invalid, redo the pass."""
+
+    def __init__(self):
+        self.sources: list = []
+
+    def __enter__(self):
+        _DEFERRED.append(self)
+        return self
+
+    def __exit__(self, *exc):
+        _DEFERRED.remove(self)
+        if exc[0] is not None:
+            for src in self.sources:
+                src._pending.clear()
+                src._extents.clear()
+                src._slot_stats.clear()
+        return False
+
+    def ok(self) -> bool:
+        good = True
+        for src in self.sources:
+            good = src.verify() and good
+        self.sources = []
+        return good
 
 
 _COPY_STREAMS: dict = {}

@@ -137,6 +137,17 @@ def _world() -> tuple[int, int]:
     return 0, 1
 
 
+def all_ranks_ok(good: bool) -> bool:
+    """Logical AND of a per-rank flag over the ranks (a repeated pass re-enters the collectives, so the ranks must agree)."""
+    rank, world = _world()
+    if world == 1:
+        return good
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([1 if good else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
 def shard_bounds(n_frames: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous block of frames owned by ``rank`` (remainder spread over the first ranks)."""
     base, rem = divmod(n_frames, world)
@@ -230,9 +241,16 @@ def compute_loss(opt_params, energy_fn: EnergyFunction, beta, loss_fn, ref_state
 
 def compute_loss_and_grad(opt_params: dict[str, torch.Tensor], energy_fn, beta, loss_fn, ref_states, ref_energies, observables):
     """``jax.value_and_grad(compute_loss, has_aux=True)`` (``objective.py:235``) for a dict of scalar tensors."""
-    leaves = {k: torch.as_tensor(v, dtype=torch.float64).detach().clone().requires_grad_(True) for k, v in opt_params.items()}
-    loss, aux = compute_loss(leaves, energy_fn, beta, loss_fn, ref_states, ref_energies, observables)
-    gl = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
+    from mythos_b200.energy import functional
+
+    while True:
+        leaves = {k: torch.as_tensor(v, dtype=torch.float64).detach().clone().requires_grad_(True) for k, v in opt_params.items()}
+        # the pair-list overflow flags are read after the backward (which syncs anyway), not in the middle of the pass
+        with functional.deferred_verification() as checks:
+            loss, aux = compute_loss(leaves, energy_fn, beta, loss_fn, ref_states, ref_energies, observables)
+            gl = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
+        if all_ranks_ok(checks.ok()):
+            break
     grads = {k: (torch.zeros_like(leaves[k]) if g is None else g) for k, g in zip(leaves, gl)}
     rank, world = _world()
     if world > 1:

@@ -275,6 +275,51 @@ def test_loss_and_grad_with_prefetched_pinned_frames_equals_device_frames(worklo
         functional.FRAME_CHUNK = old
 
 
+def test_deferred_verification_reports_an_overflowed_pass_and_the_repeat_is_right(workload):
+    """``functional.deferred_verification``: the evaluation does not read the overflow flags itself; the caller does after
+    its own launches.  Slots that are too narrow must be reported (``ok()`` False, geometry re-fitted), and the repeated
+    pass must give the energies and dE/dparams rows of an ordinary pass."""
+    from mythos_b200 import _lib
+    from mythos_b200.energy import functional
+    from mythos_b200.energy import model as kmodel
+
+    s, c, q = workload
+    efn = dna2.create_default_energy_fn(s.topology)
+    plan = kmodel.plan_for(efn.energy_fns)
+    cd, qd = torch.tensor(c, device=DEV), torch.tensor(q, device=DEV)
+    topo = plan.topology(cd.shape[1], DEV)
+    params = plan.device_params(DEV, torch.float64)
+    ones = torch.ones((cd.shape[0], _lib.N_TERMS), dtype=torch.float64, device=DEV)
+
+    def run(src):
+        t, _, _, J = functional.energy_and_gradients(plan.model, topo, cd, qd, params, src, cot=ones, want_pos_grad=False,
+                                                     want_param_grad=True, per_frame_param_grad=True)
+        return t, J
+
+    t_ref, j_ref = run(plan.pairs(DEV, topo))
+    src = plan.pairs(DEV, topo)
+    saved = dict(functional._SLOT_GEOMETRY)
+    try:
+        src.slot_geometry = ((8, 32), (8, 32))  # far too narrow
+        with functional.deferred_verification() as checks:
+            run(src)
+            assert src._pending  # nothing was read yet
+        assert not checks.ok()
+        assert src.slot_geometry != ((8, 32), (8, 32))
+        for _ in range(8):  # statistics of an overflowed pass can be truncated: the re-fit may take more than one repeat
+            with functional.deferred_verification() as checks:
+                t2, j2 = run(src)
+            if checks.ok():
+                break
+        else:
+            raise AssertionError("slot geometry did not converge")
+        np.testing.assert_allclose(t2.cpu().numpy(), t_ref.cpu().numpy(), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(j2.cpu().numpy(), j_ref.cpu().numpy(), rtol=1e-10, atol=1e-10)
+    finally:
+        functional._SLOT_GEOMETRY.clear()
+        functional._SLOT_GEOMETRY.update(saved)
+
+
 def test_tagged_float32_builds_are_safe_far_from_the_origin_and_for_extended_systems():
     """The support-tagged builds run in float32 on recentred coordinates: a trajectory far from the origin must give the
     energies of the same trajectory at the origin, and a system too extended for float32 (two duplexes 4000 length units
