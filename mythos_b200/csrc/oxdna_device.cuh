@@ -329,21 +329,25 @@ MB_HD void f3_par(T r, const T* p, T eps, T coef, int bank, int base, int eps_id
 }
 
 // f4 block layout: [theta0, delta_star, delta_c, a, b]
+// Branch tests are written on theta itself with the breakpoints theta0 -+ delta, exactly as the reference forms them
+// (dna1/base_functions.py:82-107): a value that sits ON a breakpoint must fall into the same branch as there.
 template <class T>
 MB_HD T f4_val(T th, const T* p, T& df) {
   df = T(0);
-  const T t = th - p[0];
-  if (-p[1] < t && t < p[1]) {
+  const T lo_s = p[0] - p[1], hi_s = p[0] + p[1];
+  if (lo_s < th && th < hi_s) {
+    const T t = th - p[0];
     df = T(-2) * p[3] * t;
     return T(1) - p[3] * t * t;
   }
-  if (-p[2] < t && t < -p[1]) {
-    const T u = -p[2] - t;
+  const T lo_c = p[0] - p[2], hi_c = p[0] + p[2];
+  if (lo_c < th && th < lo_s) {
+    const T u = lo_c - th;
     df = T(-2) * p[4] * u;
     return p[4] * u * u;
   }
-  if (p[1] < t && t < p[2]) {
-    const T u = p[2] - t;
+  if (hi_s < th && th < hi_c) {
+    const T u = hi_c - th;
     df = T(-2) * p[4] * u;
     return p[4] * u * u;
   }
@@ -354,17 +358,19 @@ MB_HD T f4_val(T th, const T* p, T& df) {
 template <class T>
 MB_HD void f4_par_add(T th, const T* p, T coef, T g[4]) {
   if (coef == T(0)) return;
-  const T t = th - p[0];
-  if (-p[1] < t && t < p[1]) {
+  const T lo_s = p[0] - p[1], hi_s = p[0] + p[1];
+  const T lo_c = p[0] - p[2], hi_c = p[0] + p[2];
+  if (lo_s < th && th < hi_s) {
+    const T t = th - p[0];
     g[0] += coef * T(2) * p[3] * t;
     g[2] += coef * (-t * t);
-  } else if (-p[2] < t && t < -p[1]) {
-    const T u = -p[2] - t;
+  } else if (lo_c < th && th < lo_s) {
+    const T u = lo_c - th;
     g[0] += coef * T(2) * p[4] * u;
     g[1] += coef * T(-2) * p[4] * u;
     g[3] += coef * u * u;
-  } else if (p[1] < t && t < p[2]) {
-    const T u = p[2] - t;
+  } else if (hi_s < th && th < hi_c) {
+    const T u = hi_c - th;
     g[0] += coef * T(2) * p[4] * u;
     g[1] += coef * T(2) * p[4] * u;
     g[3] += coef * u * u;

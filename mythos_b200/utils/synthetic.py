@@ -103,8 +103,11 @@ def jitter(center, quat, rng, sigma_pos=0.02, sigma_rot=0.05):
 
 
 def assembly(n_dup: int, pitch: float = 2.6, seed: int = 0, gap: float = 1.0, margin: float = 5.0,
-             nt_pattern: tuple[tuple[int, int], ...] | None = None, max_columns: int | None = None) -> SyntheticSystem:
-    """``n_dup`` jittered copies of the duplex on a lattice.  ``nt_pattern`` cycles (strand1 type, strand2 type)."""
+             nt_pattern: tuple[tuple[int, int], ...] | None = None, max_columns: int | None = None,
+             nicked: bool = False) -> SyntheticSystem:
+    """``n_dup`` jittered copies of the duplex on a lattice.  ``nt_pattern`` cycles (strand1 type, strand2 type).
+    ``nicked``: the second strand of every duplex is cut in the middle (two strands of 30), so the two nucleotides
+    either side of the nick interact through the UNBONDED terms -- coaxial stacking is then active at scale."""
     rng = np.random.default_rng(seed)
     c0, q0, _, counts = duplex60()
     length = c0[:, 2].max() - c0[:, 2].min() + gap
@@ -127,7 +130,8 @@ def assembly(n_dup: int, pitch: float = 2.6, seed: int = 0, gap: float = 1.0, ma
         seqs += [s1, s2]
         t1, t2 = (1, 1) if nt_pattern is None else nt_pattern[d % len(nt_pattern)]
         nts += [np.full(n1, t1, np.int32), np.full(int(counts[1]), t2, np.int32)]
-        strands += [n1, int(counts[1])]
+        n2 = int(counts[1])
+        strands += [n1, n2 // 2, n2 - n2 // 2] if nicked else [n1, n2]
     center = np.concatenate(centers)
     center -= center.min(0) - margin
     box = tuple(float(x) for x in (center.max(0) + margin))

@@ -102,3 +102,34 @@ extern "C" const char* host_check_param_name(int i) {
   };
   return (i >= 0 && i < MB_P_COUNT_RAW) ? names[i] : nullptr;
 }
+
+// scalar primitives f1..f6 of the device header (value and d/dx), for the reference's scalar known-answer tests
+// (tests/test_scalar_kats.py).  Block layouts as documented in oxdna_device.cuh; f1 has eps == 1 by construction.
+extern "C" double host_check_scalar(int use_f32, int kind, double x, const double* p, double eps, double* df_out) {
+  using namespace mb;
+  double val = 0, df = 0;
+  if (use_f32) {
+    float pf[16], d = 0;
+    for (int k = 0; k < 16; ++k) pf[k] = float(p[k]);
+    switch (kind) {
+      case 1: val = f1_val<float>(float(x), pf, d); break;
+      case 2: val = f2_val<float>(float(x), pf, d); break;
+      case 3: val = f3_val<float>(float(x), pf, float(eps), d); break;
+      case 4: val = f4_val<float>(float(x), pf, d); break;
+      case 5: val = f5_val<float>(float(x), pf, d); break;
+      case 6: val = f6_val<float>(float(x), pf, d); break;
+    }
+    df = d;
+  } else {
+    switch (kind) {
+      case 1: val = f1_val<double>(x, p, df); break;
+      case 2: val = f2_val<double>(x, p, df); break;
+      case 3: val = f3_val<double>(x, p, eps, df); break;
+      case 4: val = f4_val<double>(x, p, df); break;
+      case 5: val = f5_val<double>(x, p, df); break;
+      case 6: val = f6_val<double>(x, p, df); break;
+    }
+  }
+  if (df_out) *df_out = df;
+  return val;
+}

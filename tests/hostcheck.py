@@ -56,3 +56,14 @@ def evaluate(model: _lib.Model, center, quat, seq, bonded, pairs, params, cot=No
         _p(dq, C.c_double), _p(dp, C.c_double),
     )
     return terms, dc_, dq, dp
+
+
+def scalar(kind: int, x: float, block, eps: float = 1.0, use_f32: bool = False) -> tuple[float, float]:
+    """(value, d/dx) of the device header's f<kind>_val at x for a parameter block in the header's layout."""
+    h = lib()
+    h.host_check_scalar.restype = C.c_double
+    p = np.zeros(16)
+    p[: len(block)] = block
+    df = C.c_double(0.0)
+    v = h.host_check_scalar(C.c_int(1 if use_f32 else 0), C.c_int(kind), C.c_double(x), _p(p, C.c_double), C.c_double(eps), C.byref(df))
+    return float(v), float(df.value)
