@@ -497,6 +497,12 @@ int mythos_b200_weights_neff_f32(void* cuda_stream, const mb_weights_args* a);
  * CUDA events on `cuda_stream`; flops = blocks*256*iters*16.  scratch: blocks*256 reals. */
 int mythos_b200_fma_peak_f64(void* cuda_stream, void* scratch, int blocks, int iters);
 int mythos_b200_fma_peak_f32(void* cuda_stream, void* scratch, int blocks, int iters);
+/* issue cost of the special functions the kernels call, same scheme: blocks x 256 threads x iters x 8 evaluations of
+ * special(x)*a+b (one FMA per evaluation keeps the argument in range; subtract it).  kind: 0 div, 1 sqrt, 2 exp, 3 log,
+ * 4 acos, 5 1/sqrt, 6 1/x, 7 cos, 8 fmod.  ops = blocks*256*iters*8.  These are the measured special-function weights of
+ * the roofline work model. */
+int mythos_b200_special_rate_f64(void* cuda_stream, void* scratch, int blocks, int iters, int kind);
+int mythos_b200_special_rate_f32(void* cuda_stream, void* scratch, int blocks, int iters, int kind);
 
 /* ---- introspection ------------------------------------------------------------------------------------------- */
 int mythos_b200_abi_version(void);

@@ -194,6 +194,8 @@ _SIGNATURES = {
     "mythos_b200_weights_neff_f32": (C.c_int, [C.c_void_p, C.POINTER(WeightsArgs)]),
     "mythos_b200_fma_peak_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mythos_b200_fma_peak_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "mythos_b200_special_rate_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "mythos_b200_special_rate_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "mythos_b200_abi_version": (C.c_int, []),
     "mythos_b200_param_count": (C.c_int, []),
     "mythos_b200_param_name": (C.c_char_p, [C.c_int]),

@@ -147,6 +147,11 @@ class StaticPairs:
 
     pairs: torch.Tensor | None
 
+    def __post_init__(self):
+        if self.pairs is not None and self.pairs.numel() > 0 and (self.pairs.dim() not in (2, 3) or self.pairs.shape[-2] != 2):
+            raise _lib.MythosB200Error(f"pair list must have shape (2,U) or (F,2,U), got {tuple(self.pairs.shape)} "
+                                       "(a (U,2) `topology.unbonded_neighbors` must be transposed first)")
+
     def chunk(self, sl: slice, center: torch.Tensor):
         if self.pairs is None or self.pairs.numel() == 0:
             return None, 0, None
@@ -155,7 +160,36 @@ class StaticPairs:
         return self.pairs, 0, None
 
 
-_SLOT_GEOMETRY: dict = {}  # (n, r_sr, r_db, box) -> ((lane_slots, slot_width) x 2) of the warp-slot tagged builds
+class _SizingMemo:
+    """What the pair sources learn about a system -- list capacities, warp-slot geometry, whether float32 tagged builds are
+    safe -- remembered per (device, system size, cutoffs, box).  Energy functions are rebuilt by every ``with_params()``
+    and each rebuild makes a fresh ``CellListPairs``: without this memo a source that had to grow its capacity (a later
+    frame holds more pairs than frame 0) would be discarded together with what it learnt, and the next pass would
+    overflow on the same frame again, forever.  Lock-guarded: XLA / user threads may evaluate concurrently."""
+
+    def __init__(self):
+        import threading
+
+        self._lock = threading.Lock()
+        self._data: dict = {}
+
+    def get(self, key) -> dict:
+        with self._lock:
+            return dict(self._data.get(key, ()))
+
+    def update(self, key, **values) -> None:
+        with self._lock:
+            if len(self._data) > 256 and key not in self._data:
+                self._data.pop(next(iter(self._data)))
+            self._data.setdefault(key, {}).update(values)
+
+    def clear(self) -> None:
+        with self._lock:
+            self._data.clear()
+
+
+_SIZING = _SizingMemo()
+MAX_PASS_REPEATS = 6  # a pass is repeated when a pair list overflowed; capacities grow geometrically, so this is generous
 
 
 @dc.dataclass
@@ -189,6 +223,29 @@ class CellListPairs:
     _last_tagged: bool = False
     _pending: list = dc.field(default_factory=list)
 
+    _memo_key: tuple | None = None
+
+    def _load_memo(self, device, n: int) -> None:
+        """Seed this (fresh) source from what earlier sources of the same system learnt."""
+        if self._memo_key is not None:
+            return
+        tag = None if self.tag is None else (round(float(self.tag[1]), 5), round(float(self.tag[2]), 5))
+        self._memo_key = (str(device), int(n), round(float(self.r_cutoff), 5), tag, tuple(float(b) for b in self.box))
+        m = _SIZING.get(self._memo_key)
+        if self.capacity <= 0:
+            self.capacity = int(m.get("capacity", 0))
+        if self.tagged_capacity <= 0:
+            self.tagged_capacity = int(m.get("tagged_capacity", 0))
+        if self.slot_geometry is None:
+            self.slot_geometry = m.get("slot_geometry")
+        if m.get("tag_float32") is False:
+            self.tag_float32 = False
+
+    def _store_memo(self) -> None:
+        if self._memo_key is not None:
+            _SIZING.update(self._memo_key, capacity=self.capacity, tagged_capacity=self.tagged_capacity,
+                           slot_geometry=self.slot_geometry, tag_float32=self.tag_float32)
+
     def _slot_chunk(self, c, sites, r_sr, r_db):
         """The two tagged builds in the one-pass warp-slot layout (``MB_NL_WARP_SLOTS``): every warp of 32 cell-ordered
         nucleotides writes its pairs into its own fixed-width slot of the list and pads the rest with N.  No count pass, no
@@ -219,16 +276,14 @@ class CellListPairs:
         def sized(lane_max, warp_max):
             return min(max(int(lane_max * 1.5) + 4, 8), 256), (max(int(warp_max * 1.35) + 16, 32) + 3) // 4 * 4
 
-        # slot sizes are remembered per (system size, cutoffs, box): energy functions are rebuilt by every with_params(),
-        # and a fresh pair source must not pay a probe -- or worse, an overflow and a repeated pass -- on every step
-        self._geometry_key = (n, round(r_sr, 5), round(r_db, 5), tuple(self.box))
-        if self.slot_geometry is None:
-            self.slot_geometry = _SLOT_GEOMETRY.get(self._geometry_key)
+        # slot sizes are remembered per system (_SizingMemo): a fresh pair source must not pay a probe -- or worse, an
+        # overflow and a repeated pass -- on every step
         if self.slot_geometry is None:  # probe the first frame with generous slots, size from what it needed
             _, _, _, mra, mrb = run(c[:1], None if sites is None else sites[:1], ((256, 32 * 128), (256, 32 * 128)))
             a_l, a_w = (int(v) for v in mra.max(0).values.tolist())
             b_l, b_w = (int(v) for v in mrb.max(0).values.tolist()) if mrb is not None else (0, 0)
-            self.slot_geometry = _SLOT_GEOMETRY[self._geometry_key] = (sized(a_l, a_w), sized(b_l, b_w))
+            self.slot_geometry = (sized(a_l, a_w), sized(b_l, b_w))
+            self._store_memo()
         pairs, cap, overflow, mra, mrb = run(c, sites, self.slot_geometry)
         self._pending.append((torch.zeros((1,), dtype=torch.int32, device=c.device), overflow))
         self._slot_stats.append((mra, mrb))
@@ -245,10 +300,12 @@ class CellListPairs:
         c = center.detach()
         tagged = bool(tagged and self.tag is not None and quat is not None)
         self._last_tagged = tagged
+        self._load_memo(c.device, c.shape[1])
         if not tagged:
             if self.capacity <= 0:
                 _, count, _, self.workspace = neighbors.build_pairs(c[:1], self.bonded, self.box, self.r_cutoff, 0.0, 1, self.workspace)
                 self.capacity = (max(int(int(count.max().item()) * 1.06) + 64, 64) + 3) // 4 * 4  # multiple of 4: 128-bit pair stores
+                self._store_memo()
             pairs, count, overflow, self.workspace = neighbors.build_pairs(
                 c, self.bonded, self.box, self.r_cutoff, 0.0, self.capacity, self.workspace
             )
@@ -293,6 +350,7 @@ class CellListPairs:
         if self.tagged_capacity <= 0:
             _, count, _, _ = both(c[:1], None if sites is None else sites[:1], 4)
             self.tagged_capacity = (max(int(int(count.max().item()) * 1.06) + 64, 64) + 3) // 4 * 4
+            self._store_memo()
         pairs, count, overflow, self.last_split = both(c, sites, self.tagged_capacity)
         self._pending.append((count, overflow))
         if extent is not None:
@@ -319,6 +377,7 @@ class CellListPairs:
         self._pending.clear()
         if had_extents and host[0] > 1500.0:  # float32 cannot resolve the 1e-3 margin out there: redo the pass with float64 builds
             self.tag_float32 = False
+            self._store_memo()
             return False
         worst, flags = int(host[1]), int(host[2])
         if stats:  # warp-slot builds: bit 0 = a slot was too narrow, bit 2 = a lane row was too short
@@ -338,8 +397,7 @@ class CellListPairs:
 
             over = bool(flags & 5)
             self.slot_geometry = (fit(a[0], a[1], ka, wa, over), fit(b[0], b[1], kb, wb, over))
-            if getattr(self, "_geometry_key", None) is not None:
-                _SLOT_GEOMETRY[self._geometry_key] = self.slot_geometry
+            self._store_memo()
             return not over
         if flags & 2:
             raise _lib.MythosB200Error("neighbour build: a nucleotide has more than 4 bonded partners")
@@ -348,6 +406,7 @@ class CellListPairs:
         if worst <= getattr(self, cap_attr):
             return True
         setattr(self, cap_attr, (int(worst * 1.06) + 64 + 3) // 4 * 4)  # jax_md would report did_buffer_overflow; here the pass re-runs
+        self._store_memo()
         return False
 
 
@@ -400,8 +459,14 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
     if streamed and want_pos:
         raise _lib.MythosB200Error("position gradients need device-resident frames")
     dev = params.device
+    repeats = 0
     while True:
         outs = []
+        repeats += 1
+        if repeats > MAX_PASS_REPEATS:
+            raise _lib.MythosB200Error(f"pair lists still overflow after {MAX_PASS_REPEATS} passes "
+                                       f"(capacity {getattr(source, 'capacity', None)}, tagged {getattr(source, 'tagged_capacity', None)}, "
+                                       f"slots {getattr(source, 'slot_geometry', None)})")
         try:
             chunks = _chunks(center.shape[0], source)
             nxt = _fetch(center, quat, chunks[0], dev) if streamed else None

@@ -91,10 +91,21 @@ def _cached(key: tuple, keep: tuple, make):
     return val
 
 
+def check_pair_layout(shape) -> None:
+    """The kernels take the OrderedSparse layout (2,U) / (F,2,U) -- what the reference hands its energy functions after
+    transposing ``topology.unbonded_neighbors (U,2)`` (``energy/base.py:138``, ``jaxmd.py:78,86``).  A (U,2) array would be
+    read as a two-entry list, silently: refuse it."""
+    shape = tuple(shape)
+    if len(shape) not in (2, 3) or shape[-2] != 2:
+        hint = " -- this looks like (U,2) `topology.unbonded_neighbors`: pass its transpose" if len(shape) == 2 and shape[-1] == 2 else ""
+        raise _lib.MythosB200Error(f"unbonded_neighbors must have shape (2,U) or (F,2,U), got {shape}{hint}")
+
+
 def device_pairs(pairs, device) -> torch.Tensor | None:
-    """(2,U) or (F,2,U) int32 on the device; accepts numpy / lists / tensors, (U,2) is NOT transposed here."""
+    """(2,U) or (F,2,U) int32 on the device; accepts numpy / lists / tensors; a (U,2) array is refused, not transposed."""
     if pairs is None:
         return None
+    check_pair_layout(getattr(pairs, "shape", None) if hasattr(pairs, "shape") else torch.as_tensor(pairs).shape)
     if isinstance(pairs, torch.Tensor) and pairs.device == device and pairs.dtype == torch.int32 and pairs.is_contiguous():
         return pairs
     return _cached(("pairs", id(pairs), str(device)), (pairs,), lambda: functional._as_i32(pairs, device))

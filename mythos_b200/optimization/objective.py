@@ -98,17 +98,18 @@ class _Weights(torch.autograd.Function):
         w, neff = _weights_kernel(beta, new_e.detach(), ref_e.detach())
         b = torch.as_tensor(beta, dtype=new_e.dtype, device=new_e.device).expand_as(new_e)
         ctx.save_for_backward(w, neff, b)
+        ctx.set_materialize_grads(False)  # an unused output arrives as None, not as a zero tensor
         return w, neff
 
     @staticmethod
     def backward(ctx, g_w, g_neff):
         w, neff, beta = ctx.saved_tensors
         # x_k = -beta_k (E_k - Eref_k);  dw_j/dx_k = w_j (delta_jk - w_k);  S = -sum w ln w, dS/dx_k = -w_k (ln w_k + S)
-        lw = torch.log(w)
-        gx = w * (g_w - (g_w * w).sum())
+        gx = torch.zeros_like(w) if g_w is None else w * (g_w - (g_w * w).sum())
         if g_neff is not None:
-            S = -(w * lw).sum()
-            gx = gx + g_neff * neff * (-w * (lw + S))
+            wlw = torch.xlogy(w, w)  # 0 * log 0 = 0: a weight that underflowed must not poison the gradient with NaN
+            S = -wlw.sum()
+            gx = gx + g_neff * neff * (-(wlw + w * S))
         g_e = -beta * gx
         return None, g_e, -g_e
 
@@ -211,15 +212,19 @@ def allreduce_grads(grads: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
         return grads
     keys = sorted(grads)
     dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-    flat = torch.stack([grads[k].reshape(()).to(torch.float64) for k in keys]).to(dev)
+    # parameters may be scalars or tables (ss_stack_weights (4,4), ...): flattened into one buffer, one collective
+    sizes = [grads[k].numel() for k in keys]
+    flat = torch.cat([grads[k].reshape(-1).to(torch.float64) for k in keys]).to(dev)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     back: dict = {}  # one copy per destination device, not one per parameter
     out = {}
-    for i, k in enumerate(keys):
+    off = 0
+    for k, sz in zip(keys, sizes):
         d = grads[k].device
         if d not in back:
             back[d] = flat.to(d)
-        out[k] = back[d][i].to(grads[k].dtype)
+        out[k] = back[d][off:off + sz].reshape(grads[k].shape).to(grads[k].dtype)
+        off += sz
     return out
 
 
@@ -243,7 +248,9 @@ def compute_loss_and_grad(opt_params: dict[str, torch.Tensor], energy_fn, beta, 
     """``jax.value_and_grad(compute_loss, has_aux=True)`` (``objective.py:235``) for a dict of scalar tensors."""
     from mythos_b200.energy import functional
 
-    while True:
+    for attempt in range(functional.MAX_PASS_REPEATS + 1):
+        if attempt == functional.MAX_PASS_REPEATS:
+            raise _lib.MythosB200Error(f"pair lists still overflow after {attempt} passes over the reference states")
         leaves = {k: torch.as_tensor(v, dtype=torch.float64).detach().clone().requires_grad_(True) for k, v in opt_params.items()}
         # the pair-list overflow flags are read after the backward (which syncs anyway), not in the middle of the pass
         with functional.deferred_verification() as checks:

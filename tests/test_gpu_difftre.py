@@ -298,7 +298,6 @@ def test_deferred_verification_reports_an_overflowed_pass_and_the_repeat_is_righ
 
     t_ref, j_ref = run(plan.pairs(DEV, topo))
     src = plan.pairs(DEV, topo)
-    saved = dict(functional._SLOT_GEOMETRY)
     try:
         src.slot_geometry = ((8, 32), (8, 32))  # far too narrow
         with functional.deferred_verification() as checks:
@@ -316,8 +315,61 @@ def test_deferred_verification_reports_an_overflowed_pass_and_the_repeat_is_righ
         np.testing.assert_allclose(t2.cpu().numpy(), t_ref.cpu().numpy(), rtol=1e-12, atol=1e-12)
         np.testing.assert_allclose(j2.cpu().numpy(), j_ref.cpu().numpy(), rtol=1e-10, atol=1e-10)
     finally:
-        functional._SLOT_GEOMETRY.clear()
-        functional._SLOT_GEOMETRY.update(saved)
+        functional._SIZING.clear()
+
+
+def test_loss_and_grad_recovers_when_fresh_sources_start_from_capacities_that_overflow(workload):
+    """``compute_loss_and_grad`` rebuilds the energy function -- and with it the pair source -- on every repeat.  What a
+    source learns when a list overflows (capacities, slot geometry, float64 fallback) must survive in the sizing memo, or
+    the repeat overflows on the same frame forever (round-1 advisor finding).  Poison the memo with sizes that are far too
+    small, and with a system too extended for the float32 tagged builds, and require the public call to converge to the
+    result of a clean run."""
+    from mythos_b200.energy import functional
+    from mythos_b200.energy import model as kmodel
+    from mythos_b200.input.topology import AllPairs
+
+    s, c, q = workload
+    n = s.center.shape[0]
+    efn = dna2.create_default_energy_fn(s.topology).with_props(unbonded_neighbors=AllPairs(n))
+    names = ["eps_hb", "k_cross", "q_eff"]
+    base = efn.params_dict(include_dependent=False)
+    theta = {k: torch.tensor(float(base[k]), dtype=torch.float64) for k in names}
+    F = len(c)
+    kT = 0.0987
+    beta = torch.full((F,), 1.0 / kT, dtype=torch.float64, device=DEV)
+    obs = torch.tensor(np.random.default_rng(3).standard_normal(F), device=DEV)
+
+    def loss_fn(ref_states, weights, energy_fn, opt_params, observables):
+        m = (weights * obs).sum()
+        return m, (("obs", m), None)
+
+    def run(cc):
+        states = SimulatorTrajectory(center=torch.tensor(cc, device=DEV), orientation=Quaternion(torch.tensor(q, device=DEV)),
+                                     temperature=torch.full((F,), kT, dtype=torch.float64, device=DEV))
+        with torch.no_grad():
+            e_ref = efn.map(states)
+        return objective.compute_loss_and_grad(theta, efn, beta, loss_fn, states, e_ref + 0.01 * obs, [])
+
+    try:
+        functional._SIZING.clear()
+        (l0, _), g0 = run(c)
+        # (a) poisoned sizes: every fresh source starts from them
+        probe = kmodel.plan_for(efn.energy_fns).pairs(torch.device(DEV), kmodel.plan_for(efn.energy_fns).topology(n, torch.device(DEV)))
+        probe._load_memo(torch.device(DEV), n)
+        functional._SIZING.update(probe._memo_key, slot_geometry=((8, 32), (8, 32)), capacity=64, tagged_capacity=64)
+        (l1, _), g1 = run(c)
+        assert np.isclose(float(l1), float(l0), rtol=1e-10)
+        for k in names:
+            assert np.isclose(float(g1[k]), float(g0[k]), rtol=1e-8, atol=1e-12), k
+        assert functional._SIZING.get(probe._memo_key)["slot_geometry"] != ((8, 32), (8, 32))
+        # (b) extent beyond 1500 length units: the float64 fallback must be remembered across the rebuilt sources
+        functional._SIZING.clear()
+        c2 = c.copy()
+        c2[:, n // 2:, 0] += 4000.0
+        (l2, _), g2 = run(c2)
+        assert np.isfinite(float(l2)) and functional._SIZING.get(probe._memo_key).get("tag_float32") is False
+    finally:
+        functional._SIZING.clear()
 
 
 def test_tagged_float32_builds_are_safe_far_from_the_origin_and_for_extended_systems():
