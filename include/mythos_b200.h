@@ -504,6 +504,31 @@ int mythos_b200_fma_peak_f32(void* cuda_stream, void* scratch, int blocks, int i
 int mythos_b200_special_rate_f64(void* cuda_stream, void* scratch, int blocks, int iters, int kind);
 int mythos_b200_special_rate_f32(void* cuda_stream, void* scratch, int blocks, int iters, int kind);
 
+/* ---- theta -> parameter-bank chain (host side; no device work) ------------------------------------------------
+ * Stands in for `BaseConfiguration.init_params` of every term (mythos/energy/configuration.py:110-113, e.g.
+ * mythos/energy/dna1/stacking.py:120-183, hydrogen_bonding.py:148-223) and the smoothing solvers
+ * (mythos/energy/dna1/base_smoothing_functions.py:48-142) as they run on every parameter update of a DiffTRe step
+ * (optimization/objective.py:224 `energy_fn.with_params(opt_params)`), together with their reverse-mode derivative.
+ * The chain is a straight-line scalar program (no data-dependent branches): node k computes op[k](node arg0[k],
+ * node arg1[k]) with operands that precede it; `imm` holds constants (MB_TAPE_CONST) and exponents (MB_TAPE_POW);
+ * MB_TAPE_INPUT reads inputs[arg0[k]].  out[o] = node whose value is parameter-bank slot o (-1: slot stays 0).
+ * `values` / `adjoint` are caller-owned scratch of n_nodes doubles; forward fills `values`, the VJP reads them. */
+enum mb_tape_op {
+  MB_TAPE_CONST = 0, MB_TAPE_INPUT = 1, MB_TAPE_ADD = 2, MB_TAPE_SUB = 3, MB_TAPE_MUL = 4, MB_TAPE_DIV = 5,
+  MB_TAPE_NEG = 6, MB_TAPE_RECIP = 7, MB_TAPE_EXP = 8, MB_TAPE_LOG = 9, MB_TAPE_SQRT = 10, MB_TAPE_POW = 11
+};
+typedef struct mb_theta_tape {
+  int32_t n_nodes, n_inputs, n_outputs, _pad;
+  const int32_t* op;    /* (n_nodes) mb_tape_op */
+  const int32_t* arg0;  /* (n_nodes) */
+  const int32_t* arg1;  /* (n_nodes) */
+  const double* imm;    /* (n_nodes) */
+  const int32_t* out;   /* (n_outputs) */
+} mb_theta_tape;
+int mythos_b200_theta_tape_forward(const mb_theta_tape* tape, const double* inputs, double* values, double* outputs);
+int mythos_b200_theta_tape_vjp(const mb_theta_tape* tape, const double* values, const double* out_cot, double* adjoint,
+                               double* in_grad);
+
 /* ---- introspection ------------------------------------------------------------------------------------------- */
 int mythos_b200_abi_version(void);
 int mythos_b200_param_count(void);                 /* MB_P_COUNT                              */

@@ -196,6 +196,8 @@ _SIGNATURES = {
     "mythos_b200_fma_peak_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mythos_b200_special_rate_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "mythos_b200_special_rate_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "mythos_b200_theta_tape_forward": (C.c_int, [C.c_void_p] * 4),
+    "mythos_b200_theta_tape_vjp": (C.c_int, [C.c_void_p] * 5),
     "mythos_b200_abi_version": (C.c_int, []),
     "mythos_b200_param_count": (C.c_int, []),
     "mythos_b200_param_name": (C.c_char_p, [C.c_int]),

@@ -63,6 +63,17 @@ def pack_bank(configs: list[Any]) -> torch.Tensor:
     return torch.stack(vals)
 
 
+def bank_vector(fns: list, hybrid: bool) -> torch.Tensor:
+    """(n_banks*P,) float64 host vector of a fusable group of terms (NA1: the DNA, RNA and hybrid banks in that order)."""
+    if not hybrid:
+        return pack_bank([fn.params for fn in fns])
+    banks = []
+    for b in BANKS:
+        cfgs = [getattr(fn.params, f"{b}_config") for fn in fns if f"{b}_config" in fn.params]
+        banks.append(pack_bank([c for c in cfgs if c is not None]))
+    return torch.cat(banks)
+
+
 # --------------------------------------------------------------------------------------------- geometry
 def geometry_of(transform_fn) -> tuple[str, list[_lib.FlavourGeom]]:
     """(kind, flavour geometries) of a ``functools.partial(Nucleotide.from_rigid_body, **constants)``."""
@@ -119,19 +130,19 @@ class Plan:
     term_mask: int
     hybrid: bool
 
+    # the packed bank(s) when they were produced outside the configurations (mythos_b200.energy.theta_tape replays the
+    # theta -> bank chain in C++); None: pack from fn.params
+    bank: torch.Tensor | None = None
+
     def params_vector(self) -> torch.Tensor:
         """(n_banks*P,) float64 host vector, differentiable w.r.t. any tensor inside the configurations."""
-        if not self.hybrid:
-            return pack_bank([fn.params for fn in self.fns])
-        banks = []
-        for b in BANKS:
-            cfgs = [getattr(fn.params, f"{b}_config") for fn in self.fns if f"{b}_config" in fn.params]
-            banks.append(pack_bank([c for c in cfgs if c is not None]))
-        return torch.cat(banks)
+        if self.bank is not None:
+            return self.bank
+        return bank_vector(self.fns, self.hybrid)
 
     def device_params(self, device, dtype) -> torch.Tensor:
         vec = self.params_vector()
-        if vec.requires_grad:
+        if vec.requires_grad or self.bank is not None:
             return vec.to(device=device, dtype=dtype)
         key = ("params", tuple(id(fn.params) for fn in self.fns), str(device), str(dtype))
         return _cached(key, tuple(fn.params for fn in self.fns), lambda: vec.to(device=device, dtype=dtype))

@@ -23,6 +23,7 @@ import torch
 import torch.distributed as dist
 
 from mythos_b200 import _lib
+from mythos_b200.energy import theta_tape
 from mythos_b200.energy.base import EnergyFunction
 from mythos_b200.rigid_body import Quaternion, RigidBody
 from mythos_b200.simulators.io import SimulatorTrajectory
@@ -237,7 +238,9 @@ def compute_loss(opt_params, energy_fn: EnergyFunction, beta, loss_fn, ref_state
         from mythos_b200.energy import functional
 
         functional.prefetch_frames(ref_states.center, ref_states.orientation.vec)
-    energy_fn = energy_fn.with_params(opt_params)
+    # = energy_fn.with_params(opt_params); the theta -> parameter-bank chain is replayed from a tape recorded once per
+    # energy function (what jit does for the reference) instead of ~700 eager autograd nodes per step
+    energy_fn = theta_tape.bind(energy_fn, opt_params)
     new_energies = sharded_map(energy_fn, ref_states)
     weights, neff = compute_weights_and_neff(beta, new_energies, ref_energies)
     loss, (measured_value, _) = loss_fn(ref_states, weights, energy_fn, opt_params, observables)
@@ -245,26 +248,31 @@ def compute_loss(opt_params, energy_fn: EnergyFunction, beta, loss_fn, ref_state
 
 
 def compute_loss_and_grad(opt_params: dict[str, torch.Tensor], energy_fn, beta, loss_fn, ref_states, ref_energies, observables):
-    """``jax.value_and_grad(compute_loss, has_aux=True)`` (``objective.py:235``) for a dict of scalar tensors."""
+    """``jax.value_and_grad(compute_loss, has_aux=True)`` (``objective.py:235``) for a dict of float tensors (scalars or
+    tables).  The parameters are differentiated as ONE flat leaf (``theta_tape.FlatParams``): ``loss_fn`` still sees a
+    mapping name -> tensor, the autograd engine sees one leaf instead of a hundred."""
     from mythos_b200.energy import functional
 
     for attempt in range(functional.MAX_PASS_REPEATS + 1):
         if attempt == functional.MAX_PASS_REPEATS:
             raise _lib.MythosB200Error(f"pair lists still overflow after {attempt} passes over the reference states")
-        leaves = {k: torch.as_tensor(v, dtype=torch.float64).detach().clone().requires_grad_(True) for k, v in opt_params.items()}
+        leaves = theta_tape.FlatParams(opt_params)
+        leaves.flat.requires_grad_(True)
         # the pair-list overflow flags are read after the backward (which syncs anyway), not in the middle of the pass
         with functional.deferred_verification() as checks:
             loss, aux = compute_loss(leaves, energy_fn, beta, loss_fn, ref_states, ref_energies, observables)
-            gl = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
+            (g,) = torch.autograd.grad(loss, [leaves.flat], allow_unused=True)
         if all_ranks_ok(checks.ok()):
             break
-    grads = {k: (torch.zeros_like(leaves[k]) if g is None else g) for k, g in zip(leaves, gl)}
+    g = torch.zeros_like(leaves.flat) if g is None else g
     rank, world = _world()
     if world > 1:
         # direct dependence of the loss on theta (through loss_fn) is identical on every rank; only the part that
         # flows through this rank's frames differs.  Each rank's autograd result = direct + own-frames part, so
         # sum over ranks = world*direct + total frames part; the direct part is recovered from a frames-free pass.
-        grads = _combine_sharded_grads(grads, leaves, loss_fn, ref_states, energy_fn, beta, ref_energies, observables, aux)
+        g = _combine_sharded_grads(g, leaves, loss_fn, ref_states, energy_fn, beta, ref_energies, observables, aux)
+    grads = {k: v.to(torch.as_tensor(opt_params[k]).dtype) if torch.as_tensor(opt_params[k]).is_floating_point() else v
+             for k, v in leaves.unflatten(g).items()}
     return (loss.detach(), tuple(a.detach() if isinstance(a, torch.Tensor) else a for a in aux)), grads
 
 
@@ -288,20 +296,18 @@ class _LazyWithParams:
         return self._get()(*args, **kwargs)
 
 
-def _combine_sharded_grads(grads, leaves, loss_fn, ref_states, energy_fn, beta, ref_energies, observables, aux):
-    rank, world = _world()
+def _combine_sharded_grads(g, leaves, loss_fn, ref_states, energy_fn, beta, ref_energies, observables, aux):
     # frames-free pass: weights held constant -> gradient of the loss through loss_fn's direct theta dependence only
     neff, _, new_e = aux
     w_const, _ = compute_weights_and_neff(beta, new_e.detach(), ref_energies)
-    l2 = {k: v.detach().clone().requires_grad_(True) for k, v in leaves.items()}
+    l2 = leaves.like(leaves.flat.detach().clone().requires_grad_(True))
     loss2, _ = loss_fn(ref_states, w_const.detach(), _LazyWithParams(energy_fn, l2), l2, observables)
-    direct = {k: torch.zeros_like(v) for k, v in l2.items()}
+    direct = torch.zeros_like(g)
     if isinstance(loss2, torch.Tensor) and loss2.requires_grad:
-        gd = torch.autograd.grad(loss2, list(l2.values()), allow_unused=True)
-        direct = {k: (torch.zeros_like(l2[k]) if g is None else g) for k, g in zip(l2, gd)}
-    via_frames = {k: grads[k] - direct[k] for k in grads}
-    total = allreduce_grads(via_frames)
-    return {k: total[k] + direct[k] for k in grads}
+        (gd,) = torch.autograd.grad(loss2, [l2.flat], allow_unused=True)
+        if gd is not None:
+            direct = gd
+    return allreduce_grads({"flat": g - direct})["flat"] + direct
 
 
 @dc.dataclass(frozen=True, kw_only=True)
@@ -346,9 +352,9 @@ class DiffTReObjective(Objective):
         beta = 1.0 / reference_states.temperature
         reference_opt_params = reference_opt_params or opt_params
         with torch.no_grad():
-            reference_energies = sharded_map(self.energy_fn.with_params(reference_opt_params), reference_states)
+            reference_energies = sharded_map(theta_tape.bind(self.energy_fn, reference_opt_params), reference_states)
             same = reference_opt_params is opt_params
-            new_energies = reference_energies if same else sharded_map(self.energy_fn.with_params(opt_params), reference_states)
+            new_energies = reference_energies if same else sharded_map(theta_tape.bind(self.energy_fn, opt_params), reference_states)
         neff = compute_min_segment_neff(reference_states.temperature, new_energies, reference_energies)
         if neff < self.min_n_eff_factor:
             return ObjectiveOutput(

@@ -449,3 +449,43 @@ def test_map_of_a_system_too_large_for_the_frame_kernel_falls_back_to_the_list_k
     np.testing.assert_allclose(e.detach().cpu().numpy(), terms.sum(1).cpu().numpy(), rtol=1e-11)
     k = _lib.param_names().index("cross_stacking.k_cross")
     assert np.isclose(float(th["k_cross"].grad), float(dp[k]), rtol=1e-9)
+
+
+def test_loss_and_grad_through_the_replayed_theta_chain_equals_the_eager_chain(workload):
+    """``compute_loss`` binds theta through the recorded tape (``theta_tape.bind``); with the replay switched off it runs
+    the eager ``with_params`` chain.  Loss, n_eff and every gradient (all default optimisable parameters, plus a direct
+    theta term in the loss) must agree; a loss function that calls the bound energy function gets the real object."""
+    from mythos_b200.energy import theta_tape
+    from mythos_b200.optimization import objective
+
+    s, c, q = workload
+    efn = dna2.create_default_energy_fn(s.topology)
+    theta = {k: torch.as_tensor(v, dtype=torch.float64) * 1.01 for k, v in efn.opt_params().items()}
+    F = c.shape[0]
+    beta = torch.full((F,), 10.0, dtype=torch.float64, device=DEV)
+    obs = torch.linspace(-1.0, 1.0, F, dtype=torch.float64, device=DEV)
+    states = RigidBody(torch.tensor(c, device=DEV), Quaternion(torch.tensor(q, device=DEV)))
+    seen = []
+
+    def loss_fn(ref_states, weights, energy_fn, opt_params, observables):
+        seen.append(float(energy_fn.params_dict()["eps_hb"]))  # answered by the materialised with_params result
+        m = (weights * obs).sum() + 1e-3 * opt_params["eps_hb"] ** 2
+        return m, (("obs", m), None)
+
+    with torch.no_grad():
+        e_ref = efn.map(states) + obs * 0.01
+    res = []
+    for enabled in (True, False):
+        theta_tape.ENABLED = enabled
+        try:
+            (l, (neff, _, e_new)), g = objective.compute_loss_and_grad(theta, efn, beta, loss_fn, states, e_ref, [])
+        finally:
+            theta_tape.ENABLED = True
+        res.append((float(l), float(neff), e_new.cpu().numpy(), {k: v.detach().cpu().numpy() for k, v in g.items()}))
+    assert seen[0] == seen[1] == float(theta["eps_hb"])
+    np.testing.assert_allclose(res[0][2], res[1][2], rtol=1e-13)
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-10)
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-10)
+    scale = max(float(np.abs(v).max()) for v in res[1][3].values())
+    for k in theta:
+        np.testing.assert_allclose(res[0][3][k], res[1][3][k], rtol=1e-8, atol=1e-10 * scale, err_msg=k)
