@@ -224,6 +224,13 @@ class CellListPairs:
     _pending: list = dc.field(default_factory=list)
 
     _memo_key: tuple | None = None
+    _cache_candidates: list = dc.field(default_factory=list)  # lists built this pass, remembered once verify() passes
+
+    def _settle_cache(self, good: bool) -> None:
+        cands, self._cache_candidates = self._cache_candidates, []
+        if good:
+            for args in cands:
+                _PAIR_LISTS.commit(*args)
 
     def _load_memo(self, device, n: int) -> None:
         """Seed this (fresh) source from what earlier sources of the same system learnt."""
@@ -359,6 +366,11 @@ class CellListPairs:
 
     def verify(self) -> bool:
         """True if every list built since the last call fitted its capacity; otherwise grows the capacity."""
+        good = self._verify()
+        self._settle_cache(good)
+        return good
+
+    def _verify(self) -> bool:
         if not self._pending:
             return True
         # one host read for everything this pass recorded (extent, longest list, overflow flags, slot statistics)
@@ -422,12 +434,105 @@ def backbone_sites(model, center: torch.Tensor, quat: torch.Tensor, nt_type: tor
     return out
 
 
+class _PairListCache:
+    """Per-frame pair lists of stored trajectory frames, kept between passes.
+
+    DiffTRe evaluates the SAME stored frames again and again -- reference energies, new energies and the loss pass of
+    every optimiser step until the trajectory is resampled (``mythos/optimization/objective.py:298-303,345-361``) -- and
+    a pair list depends on the parameters only through the cutoffs it was built with.  Lists are therefore built with
+    the cutoffs widened by ``PAIR_LIST_MARGIN`` and remembered per (frames tensor, chunk): a later pass over the same
+    tensor objects whose cutoffs still fit inside the built ones streams the remembered lists and launches no
+    neighbour kernels at all (the energy kernels re-apply every term's exact support, so a superset list changes nothing
+    -- tests compare cached and rebuilt passes).  Keyed by the identity of the ``center`` / ``quat`` tensor objects
+    (weak references: an entry dies with its frames) and their version counters (an in-place update invalidates it);
+    bounded by ``PAIR_LIST_CACHE_GB``.  Entries are committed only after the pass that built them verified its lists."""
+
+    def __init__(self):
+        import threading
+
+        self._lock = threading.Lock()
+        self._entries: dict = {}  # id(center) -> dict(ref_c, ref_q, version, sig, chunks={(lo,hi): value}, bytes)
+
+    def _alive(self, e, center, quat) -> bool:
+        return (e is not None and e["ref_c"]() is center and e["ref_q"]() is quat
+                and e["version"] == (center._version, quat._version))
+
+    def lookup(self, center, quat, sig, cutoffs, lo, hi):
+        """The remembered lists of frames [lo, hi) if they were built for the same system with cutoffs >= `cutoffs`."""
+        with self._lock:
+            e = self._entries.get(id(center))
+            if not self._alive(e, center, quat):
+                self._entries.pop(id(center), None)
+                return None
+            if e["sig"] != sig or any(need > have for need, have in zip(cutoffs, e["cutoffs"])):
+                return None
+            return e["chunks"].get((lo, hi))
+
+    def built_cutoffs(self, center, quat, sig):
+        with self._lock:
+            e = self._entries.get(id(center))
+            return e["cutoffs"] if self._alive(e, center, quat) and e["sig"] == sig else None
+
+    def commit(self, center, quat, sig, cutoffs, lo, hi, value, nbytes) -> None:
+        import weakref
+
+        budget = PAIR_LIST_CACHE_GB * 2**30
+        with self._lock:
+            e = self._entries.get(id(center))
+            if not self._alive(e, center, quat) or e["sig"] != sig or e["cutoffs"] != cutoffs:
+                key = id(center)
+                e = {"ref_c": weakref.ref(center, lambda _r, k=key: self._drop(k)), "ref_q": weakref.ref(quat),
+                     "version": (center._version, quat._version), "sig": sig, "cutoffs": cutoffs, "chunks": {}, "bytes": 0}
+                self._entries[key] = e
+            total = sum(x["bytes"] for x in self._entries.values())
+            while total + nbytes > budget and len(self._entries) > 1:  # oldest trajectories go first
+                k = next(k for k in self._entries if k != id(center))
+                total -= self._entries.pop(k)["bytes"]
+            if total + nbytes > budget:
+                return
+            e["chunks"][(lo, hi)] = value
+            e["bytes"] += nbytes
+
+    def _drop(self, key) -> None:
+        with self._lock:
+            self._entries.pop(key, None)
+
+    def clear(self) -> None:
+        with self._lock:
+            self._entries.clear()
+
+    def nbytes(self) -> int:
+        with self._lock:
+            return sum(x["bytes"] for x in self._entries.values())
+
+
+PAIR_LIST_CACHE_GB = float(os.environ.get("MYTHOS_B200_PAIR_LIST_CACHE_GB", "24"))  # 0 disables the cache
+PAIR_LIST_MARGIN = 0.01  # cutoffs of cached lists are widened by this fraction, so small parameter updates keep them valid
+_PAIR_LISTS = _PairListCache()
+
+
 FRAME_CHUNK = int(os.environ.get("MYTHOS_B200_FRAME_CHUNK", "1184"))  # frames per launch group (8 waves of one CTA per SM); bounds the pair-list buffer (~1.2 GB at N=2k)
 
 
-def _chunks(n_frames: int, source) -> list[slice]:
-    step = FRAME_CHUNK if isinstance(source, CellListPairs) else 65535
-    return [slice(lo, min(lo + step, n_frames)) for lo in range(0, n_frames, step)]
+STREAM_FIRST_CHUNK = 148  # frames of the first chunk of a pass over pinned HOST frames (one wave of one CTA per SM)
+
+
+def _chunks(n_frames: int, source, streamed: bool = False) -> list[slice]:
+    """Frame ranges of one pass.  Frames streamed from pinned host memory start with a one-wave chunk and double from
+    there up to the regular chunk size: the copy of a frame takes about half the time of its evaluation, so after the
+    first small chunk (the only copy the kernels ever wait for) every later chunk is on the device before it is needed --
+    also when a rank's whole block is smaller than one regular chunk (8 GPUs: 1024 frames each)."""
+    step = FRAME_CHUNK if (isinstance(source, CellListPairs) or source is CellListPairs) else 65535
+    if not streamed:
+        return [slice(lo, min(lo + step, n_frames)) for lo in range(0, n_frames, step)]
+    out, lo, size = [], 0, min(STREAM_FIRST_CHUNK, step)
+    while lo < n_frames:
+        hi = min(lo + size, n_frames)
+        if n_frames - hi < size // 2:  # do not leave a sliver for a chunk of its own
+            hi = n_frames if n_frames - lo <= step else hi
+        out.append(slice(lo, hi))
+        lo, size = hi, min(2 * size, step)
+    return out
 
 
 def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, want_pos, want_par, per_frame_par, flags=0):
@@ -459,6 +564,12 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
     if streamed and want_pos:
         raise _lib.MythosB200Error("position gradients need device-resident frames")
     dev = params.device
+    # stored frames that are evaluated again and again (DiffTRe) keep their pair lists between passes (_PairListCache)
+    cacheable = (isinstance(source, CellListPairs) and PAIR_LIST_CACHE_GB > 0 and center.dim() == 3 and center.shape[0] > 1
+                 and not center.requires_grad and not quat.requires_grad)
+    # (today's cutoffs, read once: a repeated pass must not widen the already widened ones again)
+    need_tagged = (float(source.tag[1]), float(source.tag[2])) if cacheable and source.tag is not None else None
+    need_plain = (float(source.r_cutoff),) if cacheable else None
     repeats = 0
     while True:
         outs = []
@@ -468,7 +579,20 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
                                        f"(capacity {getattr(source, 'capacity', None)}, tagged {getattr(source, 'tagged_capacity', None)}, "
                                        f"slots {getattr(source, 'slot_geometry', None)})")
         try:
-            chunks = _chunks(center.shape[0], source)
+            chunks = _chunks(center.shape[0], source, streamed)
+            sig = need = built = None
+            if cacheable:
+                # what a remembered list must have been built for: same system, same route, cutoffs at least today's
+                need = need_tagged if tagged else need_plain
+                sig = (str(dev), center.shape[1], tuple(float(b) for b in source.box), id(source.bonded), bool(tagged), bool(frame_route),
+                       None if not tagged or source.tag[3] is None else id(source.tag[3]))
+                built = _PAIR_LISTS.built_cutoffs(center, quat, sig)
+                if built is None or any(n_ > b_ for n_, b_ in zip(need, built)):
+                    built = tuple(x * (1.0 + PAIR_LIST_MARGIN) for x in need)  # (re)build with room for parameter updates
+                if tagged:
+                    source.tag = (source.tag[0], built[0], built[1], *source.tag[3:])
+                else:
+                    source.r_cutoff = built[0]
             nxt = _fetch(center, quat, chunks[0], dev) if streamed else None
             for k, sl in enumerate(chunks):
                 if streamed:
@@ -479,19 +603,28 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
                     q_sl.record_stream(torch.cuda.current_stream(dev))
                 else:
                     c_sl, q_sl = center[sl], quat[sl]
-                if tagged:
-                    pairs, stride, count = source.chunk(sl, c_sl, q_sl, tagged=True, slots=frame_route)
+                hit = _PAIR_LISTS.lookup(center, quat, sig, need, sl.start, sl.stop) if cacheable else None
+                if hit is not None:
+                    pairs, stride, count, split = hit
                 else:
-                    pairs, stride, count = source.chunk(sl, c_sl)
+                    if tagged:
+                        pairs, stride, count = source.chunk(sl, c_sl, q_sl, tagged=True, slots=frame_route)
+                    else:
+                        pairs, stride, count = source.chunk(sl, c_sl)
+                    split = source.last_split if tagged else None
+                    if cacheable and pairs is not None:
+                        nbytes = pairs.numel() * 4 + (0 if count is None else count.numel() * 4)
+                        source._cache_candidates.append((center, quat, sig, built, sl.start, sl.stop, (pairs, stride, count, split), nbytes))
                 outs.append(
                     _launch(model, topo, c_sl, q_sl, params, pairs, stride, term_mask,
                             None if cot is None else cot[sl], want_terms, want_pos, want_par, per_frame_par, count,
-                            flags | (_lib.FLAG_TAGGED_PAIRS if tagged else 0), 0.0, None, source.last_split if tagged else None)
+                            flags | (_lib.FLAG_TAGGED_PAIRS if tagged else 0), 0.0, None, split)
                 )
         except _lib.MythosB200Error as err:
             if not tagged or getattr(err, "status", None) != 3:  # MB_ECAPACITY: the frame-resident kernel does not apply
                 raise
             tagged, source.tag = False, None
+            source._cache_candidates.clear()
             source._pending.clear()
             source._extents.clear()
             source._slot_stats.clear()
@@ -526,6 +659,7 @@ class deferred_verification:  # noqa: N801 - used as a context manager
         _DEFERRED.remove(self)
         if exc[0] is not None:
             for src in self.sources:
+                src._cache_candidates.clear()
                 src._pending.clear()
                 src._extents.clear()
                 src._slot_stats.clear()
@@ -551,7 +685,7 @@ def prefetch_frames(center: torch.Tensor, quat: torch.Tensor) -> None:
     if center.is_cuda or not (center.is_pinned() and quat.is_pinned() and torch.cuda.is_available()) or center.dim() != 3:
         return
     dev = torch.device("cuda", torch.cuda.current_device())
-    sl = slice(0, min(FRAME_CHUNK, center.shape[0]))
+    sl = _chunks(center.shape[0], CellListPairs, True)[0]  # as a pass with per-frame device lists (the DiffTRe route) cuts it
     key = (center.data_ptr(), quat.data_ptr(), center.shape[0], sl.start, sl.stop, dev)
     _PREFETCHED[key] = _fetch(center, quat, sl, dev)
 

@@ -310,6 +310,33 @@ def _combine_sharded_grads(g, leaves, loss_fn, ref_states, energy_fn, beta, ref_
     return allreduce_grads({"flat": g - direct})["flat"] + direct
 
 
+_REFERENCE_STATES: dict = {}  # (ids of the trajectories' frame tensors, n_equilibration) -> (weak refs, sliced + concatenated states)
+
+
+def _reference_states(trajectories: list, n_equilibration_steps: int) -> SimulatorTrajectory:
+    """Equilibration slicing + concatenation of ``calculate`` (``objective.py:322-326``), remembered per set of input
+    trajectories: an optimiser calls ``calculate`` many times on the SAME stored trajectories before it resamples, and
+    handing the same tensor objects down each time is what lets the evaluation keep its per-frame pair lists
+    (``functional._PairListCache``) instead of rebuilding them on every call."""
+    import weakref
+
+    key = (tuple(id(t.center) for t in trajectories), int(n_equilibration_steps))
+    hit = _REFERENCE_STATES.get(key)
+    if hit is not None and all(r() is t.center and v == t.center._version for (r, v), t in zip(hit[0], trajectories)):
+        return hit[1]
+    if n_equilibration_steps > 0:
+        sliced = [obs.slice(slice(n_equilibration_steps, obs.length(), None)) for obs in trajectories]
+    else:
+        sliced = list(trajectories)
+    states = SimulatorTrajectory.concat(sliced)
+    for k in [k for k, (refs, _) in _REFERENCE_STATES.items() if any(r() is None for r, _ in refs)]:
+        del _REFERENCE_STATES[k]
+    if len(_REFERENCE_STATES) > 8:
+        _REFERENCE_STATES.pop(next(iter(_REFERENCE_STATES)))
+    _REFERENCE_STATES[key] = ([(weakref.ref(t.center), t.center._version) for t in trajectories], states)
+    return states
+
+
 @dc.dataclass(frozen=True, kw_only=True)
 class DiffTReObjective(Objective):
     """DiffTRe gradient computation with the reference's state machine (``objective.py:239-389``)."""
@@ -340,9 +367,7 @@ class DiffTReObjective(Objective):
         trajectories = [obs for obs in sorted_obs if isinstance(obs, SimulatorTrajectory)]
         if not trajectories:
             raise ValueError("No SimulatorTrajectory observables found in observables.")
-        if self.n_equilibration_steps > 0:
-            trajectories = [obs.slice(slice(self.n_equilibration_steps, obs.length(), None)) for obs in trajectories]
-        reference_states = SimulatorTrajectory.concat(trajectories)
+        reference_states = _reference_states(trajectories, self.n_equilibration_steps)
         if reference_states.length() == 0:
             raise ValueError("Equilibration slicing yields no states! Note slicing is in number of snapshots, not timesteps.")
         if reference_states.temperature is None:

@@ -489,3 +489,88 @@ def test_loss_and_grad_through_the_replayed_theta_chain_equals_the_eager_chain(w
     scale = max(float(np.abs(v).max()) for v in res[1][3].values())
     for k in theta:
         np.testing.assert_allclose(res[0][3][k], res[1][3][k], rtol=1e-8, atol=1e-10 * scale, err_msg=k)
+
+
+def test_remembered_pair_lists_give_the_same_pass_and_are_invalidated_correctly(workload):
+    """``functional._PairListCache``: a second pass over the same frame tensors launches no neighbour kernels and returns
+    the energies / gradients of a rebuilt pass (1e-12: the lists are supersets built with a margin, the kernels apply the
+    exact supports); parameters that push a cutoff beyond the remembered one, an in-place update of the frames, and new
+    tensor objects all trigger a rebuild; ``DiffTReObjective.calculate`` reaches the cache across calls."""
+    from mythos_b200.energy import functional
+    from mythos_b200.optimization import objective
+
+    s, c, q = workload
+    efn = dna2.create_default_energy_fn(s.topology)
+    F = c.shape[0]
+    cc, qq = torch.tensor(c, device=DEV), torch.tensor(q, device=DEV)
+    states = RigidBody(cc, Quaternion(qq))
+    theta = {k: torch.tensor(float(v), dtype=torch.float64) for k, v in efn.opt_params().items() if k in ("eps_hb", "a_stack", "q_eff", "lambda_factor")}
+    beta = torch.full((F,), 10.0, dtype=torch.float64, device=DEV)
+    obs = torch.linspace(-1.0, 1.0, F, dtype=torch.float64, device=DEV)
+
+    def loss_fn(ref_states, weights, energy_fn, opt_params, observables):
+        m = (weights * obs).sum()
+        return m, (("obs", m), None)
+
+    builds = []
+    real_chunk = functional.CellListPairs.chunk
+
+    def counting_chunk(self, *a, **k):
+        builds.append(1)
+        return real_chunk(self, *a, **k)
+
+    functional.CellListPairs.chunk = counting_chunk
+    old_gb = functional.PAIR_LIST_CACHE_GB
+    try:
+        functional._PAIR_LISTS.clear()
+        with torch.no_grad():
+            e_ref = efn.map(states) + obs * 0.01
+        n_cold = len(builds)
+        assert n_cold >= 1 and functional._PAIR_LISTS.nbytes() > 0
+        warm = objective.compute_loss_and_grad(theta, efn, beta, loss_fn, states, e_ref, [])
+        assert len(builds) == n_cold, "the second pass must reuse the remembered lists"
+        functional.PAIR_LIST_CACHE_GB = 0.0
+        cold = objective.compute_loss_and_grad(theta, efn, beta, loss_fn, states, e_ref, [])
+        functional.PAIR_LIST_CACHE_GB = old_gb
+        assert len(builds) > n_cold
+        np.testing.assert_allclose(warm[0][1][2].cpu().numpy(), cold[0][1][2].cpu().numpy(), rtol=1e-12)
+        for k in theta:
+            np.testing.assert_allclose(float(warm[1][k]), float(cold[1][k]), rtol=1e-9, atol=1e-12)
+
+        # a wider Debye cutoff than the remembered one (lambda_factor +5 % > the 1 % margin) -> rebuilt, and still right
+        wide = dict(theta, lambda_factor=theta["lambda_factor"] * 1.05)
+        n0 = len(builds)
+        with torch.no_grad():
+            e_wide = efn.with_params(wide).map(states)
+        assert len(builds) > n0
+        functional.PAIR_LIST_CACHE_GB = 0.0
+        with torch.no_grad():
+            e_wide_cold = efn.with_params(wide).map(states)
+        functional.PAIR_LIST_CACHE_GB = old_gb
+        np.testing.assert_allclose(e_wide.cpu().numpy(), e_wide_cold.cpu().numpy(), rtol=1e-12)
+        n0 = len(builds)
+        with torch.no_grad():
+            efn.map(states)  # narrower cutoffs fit inside the wider remembered lists
+        assert len(builds) == n0
+
+        # in-place update of the frames -> version counter moves -> rebuilt
+        cc.add_(0.0)
+        with torch.no_grad():
+            efn.map(states)
+        assert len(builds) > n0
+
+        # calculate(): the same trajectory object across calls reaches the remembered lists
+        kT = float(dna2.default_configs()[0]["kT"])
+        traj = SimulatorTrajectory(center=cc, orientation=Quaternion(qq), temperature=torch.full((F,), kT, dtype=torch.float64, device=DEV))
+        objv = objective.DiffTReObjective(name="t", required_observables=("traj",), grad_or_loss_fn=loss_fn, energy_fn=efn,
+                                          min_n_eff_factor=0.5, n_equilibration_steps=1)
+        out1 = objv.calculate({"traj": traj}, theta)
+        n1 = len(builds)
+        out2 = objv.calculate({"traj": traj}, theta, opt_steps=1, reference_opt_params=theta)
+        assert out1.is_ready and out2.is_ready and len(builds) == n1
+        for k in theta:
+            np.testing.assert_allclose(float(out1.grads[k]), float(out2.grads[k]), rtol=1e-12, atol=1e-14)
+    finally:
+        functional.CellListPairs.chunk = real_chunk
+        functional.PAIR_LIST_CACHE_GB = old_gb
+        functional._PAIR_LISTS.clear()
