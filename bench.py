@@ -40,11 +40,28 @@ sys.path.insert(0, str(ROOT))
 
 N_DUPLEX, PITCH, SEED = 17, 2.6, 1
 METRIC, UNIT = "DiffTRe frames/s (E+dE/dtheta)", "frames/s"
-# SURVEY 8d provisional per-unit work (flops, FMA-equivalent special slots) for float64
-W_SPECIAL = {"div": 16, "sqrt": 16, "exp": 40, "log": 50, "acos": 70}
-S_BONDED = 3 * 70 + 40 + 2 * 50 + 7 * 16 + 3 * 16
-S_LR = 40 + 16 + 16
-S_SR = 8 * 70 + 2 * 40 + 5 * 16 + 7 * 16
+# hardware counters of k_frame_energy<double,1,1,0> at 1184 frames x 2040 nt from the committed `ncu --set full` capture
+NCU_COUNTERS = {"source": "profiles/r01_v7_k_frame_energy_details.csv", "sm__inst_executed_pipe_fp64_pct": 21.06,
+                "smsp__issue_active_pct": 34.7, "sm__warps_active_pct": 25.0, "dram_bytes": 0.7834e9, "duration_ms": 3.83}
+# Issue cost of the special functions in FP64 FMA slots.  MEASURED (csrc/peaks.cu micro-kernels: a dependent chain of
+# f(x)*a+b against a chain of FMAs, profiles/r02_special_weights.json); bench re-measures them in every run and uses the
+# live numbers -- these are only the fallback.  (SURVEY 8d's provisional guesses were div 16 sqrt 16 exp 40 log 50 acos 70.)
+W_SPECIAL = {"div": 11.5, "sqrt": 12.2, "exp": 16.1, "log": 43.9, "acos": 27.5}
+# SURVEY 8d per-unit work: (flops, specials) of one unit of each kind, a term counted only inside its radial support
+WORK = {
+    "nucleotide": (60, {}),
+    "bonded": (290, {"acos": 3, "exp": 1, "log": 2, "sqrt": 7, "div": 3}),
+    "screen": (30, {}),                                                   # centre-distance test of a listed pair
+    "debye": (65, {"exp": 1, "div": 1, "sqrt": 1}),                      # backbone sites inside r_cut
+    "exc": (200, {"div": 4, "sqrt": 2}),                                 # centres inside the short-range cutoff
+    "hbcr": (330, {"acos": 6, "exp": 1, "sqrt": 1, "div": 1}),           # base-site window: hydrogen bonding + cross stacking
+    "coax": (225, {"acos": 2, "sqrt": 1, "div": 1}),                     # stacking-site window
+}
+
+
+def slot_cost(kind: str) -> float:
+    flop, specials = WORK[kind]
+    return flop / 2 + sum(n * W_SPECIAL[k] for k, n in specials.items())
 
 
 def parse():
@@ -110,7 +127,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sample / v, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.frames), "l2": "inputs larger than L2"},
+        "config": {"workload": workload_name(args.frames), "l2": "inputs larger than L2",
+                   "sample": f"{sample} frames of the workload per step, rate extrapolated (a full 8192-frame pass of the CPU port would take ~15 min)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{sample} frames of the same workload per step (oracle: torch-f64 restatement of the reference; JAX is not installable here)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -157,9 +175,73 @@ def md_benchmark(dev, n_steps: int = 10000):
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
     e_last = float(efn(RigidBody(traj.center[-1], Quaternion(traj.orientation.vec[-1]))))
+    us_step = 1e3 * ms / n_steps
+
+    # Roofline of this leg: N = 120 is LAUNCH / DEPENDENCY bound, not FP or HBM bound (each step is two dependent kernels of
+    # one wave: 280 B x 120 of state, ~1e5 flop).  The floor measured here is the same replay structure with empty work:
+    # CUDA graphs of 16 steps x 2 dependent one-thread kernels, i.e. what the device needs just to sequence the step's two
+    # launches.  frac = floor / achieved.
+    x = torch.zeros(1, device=dev)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        x.add_(1.0)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(32):
+                x.add_(1.0)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    g.replay()
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(256):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    floor_us = 1e3 * e0.elapsed_time(e1) / (256 * 16)
+    n_pairs = 7021
+    flops_step = 2 * 3.0 * (slot_cost("nucleotide") * 120 + slot_cost("bonded") * 118 + slot_cost("screen") * n_pairs) + 150 * 120
+    roofline = {"bound": "launch latency (two dependent kernels per step, one wave each)",
+                "achieved": us_step, "peak": floor_us, "unit": "us/step", "frac": floor_us / us_step,
+                "floor": "CUDA-graph replay of 2 dependent empty kernels per step, measured in this run",
+                "fp64_tflops_equiv": flops_step / (us_step * 1e-6) / 1e12,
+                "hbm_gbs": (35 * 8 * 120 + 8 * n_pairs) / (us_step * 1e-6) / 1e9}
+
+    # CPU baseline of this leg: the oracle's BAOAB step (oracle/langevin_oracle.py) with forces from torch autograd over the
+    # oracle energy, same system, a bounded number of steps on the host cores
+    cpu = None
+    try:
+        from oracle import langevin_oracle as lo
+        from oracle import oxdna_oracle as orc
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        params_o = orc.init_all("dna1", orc.default_theta("dna1"))
+        pairs_o = orc.all_unbonded_pairs(120, top.bonded_neighbors)
+        cc, qq = np.array(c), np.array(q)
+        pc, pq = np.zeros_like(cc), np.zeros_like(qq)
+        rng_o = np.random.default_rng(0)
+
+        def forces(cc, qq):
+            ct, qt = torch.tensor(cc, requires_grad=True), torch.tensor(qq, requires_grad=True)
+            e = orc.energy_terms("dna1", ct, qt, top.seq, top.bonded_neighbors, pairs_o, params_o).sum()
+            gc, gq = torch.autograd.grad(e, [ct, qt])
+            return gc.numpy(), gq.numpy()
+
+        dcen, dquat = forces(cc, qq)
+        n_cpu = 10
+        t0 = time.perf_counter()
+        for _ in range(n_cpu):
+            noise = rng_o.standard_normal((120, 6))
+            cc, qq, pc, pq = lo.step(cc, qq, pc, pq, dcen, dquat, noise, 5e-3, kT, kT / 2.5, kT / 7.5, 1.0, np.ones(3))[:4]
+            dcen, dquat = forces(cc, qq)
+        dt_cpu = time.perf_counter() - t0
+        cpu = {"value": 120 * n_cpu / dt_cpu, "unit": "nucleotide-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{n_cpu} steps of the same system (oracle BAOAB step + torch-autograd forces of the oracle energy)"}
+    except Exception as err:  # noqa: BLE001  (the baseline is a report, never a reason to lose the measurement)
+        cpu = {"unavailable": repr(err)[:200]}
     return {"metric": "MD nucleotide-steps/s", "value": 120 * n_steps / (ms * 1e-3), "unit": "nucleotide-steps/s",
             "workload": "configs[1]: oxDNA1 Langevin MD, 60-bp duplex (N=120), 10^4 steps, all-pairs list (U=7021), float64",
-            "ms_total": ms, "us_per_step": 1e3 * ms / n_steps, "final_energy_per_nt": e_last / 120}
+            "ms_total": ms, "us_per_step": us_step, "final_energy_per_nt": e_last / 120, "roofline": roofline, "cpu_baseline": cpu}
 
 
 # Work model: SURVEY 8d's per-pair counts, split per term so that a term counts for a pair only
@@ -170,11 +252,6 @@ def md_benchmark(dev, n_steps: int = 10000):
 #   hydrogen bonding + cross stacking (base-site window)     330 flop + 6 acos + exp + sqrt + div
 #   coaxial stacking (stacking-site window)                  225 flop + 2 acos + sqrt + div
 # (sum over a pair inside every support = SURVEY's 820 flop + 8 acos + 2 exp + 5 sqrt + 7 div)
-SLOT_SCREEN = 30 / 2
-SLOT_DEBYE = 65 / 2 + 40 + 16 + 16
-SLOT_EXC = 200 / 2 + 4 * 16 + 2 * 16
-SLOT_HBCR = 330 / 2 + 6 * 70 + 40 + 16 + 16
-SLOT_COAX = 225 / 2 + 2 * 70 + 16 + 16
 
 
 def pair_support_counts(plan, center, quat, pairs, count):
@@ -221,10 +298,13 @@ def pair_support_counts(plan, center, quat, pairs, count):
             "coax_window": mean(in_cx)}
 
 
-def slots_forward(n, n_b, u):
-    """Forward work of one configuration in FMA-issue slots (float64) from the measured support counts `u`."""
-    return (60 / 2 * n + (290 / 2 + S_BONDED) * n_b + SLOT_SCREEN * u["listed"] + SLOT_DEBYE * u["debye_support"] +
-            SLOT_EXC * u["short_range"] + SLOT_HBCR * u["hb_cross_window"] + SLOT_COAX * u["coax_window"])
+def slots_forward(n, n_b, u, screen: bool = True):
+    """Forward work of one configuration in FMA-issue slots (float64) from the measured support counts `u`.  `screen`:
+    charge the centre-distance test of every listed pair (done by the neighbour walk on the support-tagged route, so NOT
+    credited to the frame kernel there)."""
+    return (slot_cost("nucleotide") * n + slot_cost("bonded") * n_b + (slot_cost("screen") * u["listed"] if screen else 0.0) +
+            slot_cost("debye") * u["debye_support"] + slot_cost("exc") * u["short_range"] +
+            slot_cost("hbcr") * u["hb_cross_window"] + slot_cost("coax") * u["coax_window"])
 
 
 def force_benchmark(dev, n_dup: int, model: str, seed: int, peak_tflops: float, label: str, reps: int = 7):
@@ -396,32 +476,7 @@ def main():
     plan = kmodel.plan_for(efn.energy_fns)
     topo = plan.topology(n, dev)
     params_dev = plan.device_params(dev, torch.float64)
-    source = plan.pairs(dev, topo)
     ones = torch.ones((hi - lo, _lib.N_TERMS), dtype=torch.float64, device=dev)
-
-    def gather(e_local):
-        return e_local if world == 1 else objective.gather_frames(e_local, F)
-
-    def device_pass(e_ref):
-        while True:
-            # the overflow flags of the pair lists are read once, AFTER the reweighting and the collectives are enqueued
-            with functional.deferred_verification() as checks:
-                terms, _, _, J = functional.energy_and_gradients(
-                    plan.model, topo, c_dev, q_dev, params_dev, source, cot=ones, want_pos_grad=False, want_param_grad=True,
-                    per_frame_param_grad=True)
-                e = gather(terms.sum(1)).requires_grad_(True)
-                w, neff = objective.compute_weights_and_neff(beta, e, e_ref)
-                loss = (w * obs).sum()
-                (g,) = torch.autograd.grad(loss, e)
-                dp = g[lo:hi] @ J
-                if world > 1:
-                    dist.all_reduce(dp)
-            if objective.all_ranks_ok(checks.ok()):  # the ranks agree: a repeat re-enters the collectives
-                return loss, neff, dp, e.detach()
-
-    with torch.no_grad():
-        t0, _, _, _ = functional.energy_and_gradients(plan.model, topo, c_dev, q_dev, params_dev, source, want_pos_grad=False)
-        e_ref = gather(t0.sum(1))
 
     def barrier():
         if world > 1:
@@ -443,17 +498,12 @@ def main():
             ms = float(t.item())
         return ms, out
 
-    # FP64 FMA issue peak, measured
-    scratch = torch.empty(148 * 32 * 256, dtype=torch.float64, device=dev)
-    lib = _lib.lib()
-    best = 0.0
-    for _ in range(4):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _lib.check(lib.mythos_b200_fma_peak_f64(_lib.current_stream(dev), scratch.data_ptr(), 148 * 32, 4096), "fma_peak")
-        e1.record()
-        torch.cuda.synchronize(dev)
-        best = max(best, 148 * 32 * 256 * 4096 * 16 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    # FP64 FMA issue peak and the special-function weights of the work model, measured now
+    from mythos_b200.utils import peaks as peaks_mod
+
+    best = max(peaks_mod.fma_peak_tflops(dev, torch.float64) for _ in range(2))
+    measured_w = peaks_mod.special_weights(dev, torch.float64)["weights"]
+    W_SPECIAL.update({k: float(measured_w[k]) for k in W_SPECIAL})
     # The single-GPU legs of the other configurations run FIRST, on a quiet process: MD at N = 120 is bound by launch and
     # dependency latency, and measured 4x slower after the big passes (allocator state of the 936 MB streaming buffers) or
     # after the CPU oracle (its OpenMP workers keep spinning and slow the launch thread).
@@ -464,44 +514,67 @@ def main():
                                     "configs[2]: oxDNA2 + Debye, synthetic 68-duplex assembly (N=8160), neighbour list, float64")
         forces_100k = force_benchmark(dev, 834, "na1", 2, best,
                                       "configs[4]: NA1 hybrid DNA/RNA, synthetic 834-duplex assembly (N=100080), neighbour rebuild + forces, float64")
-
     torch.cuda.empty_cache()
-    for _ in range(args.warmup):
-        device_pass(e_ref)
-    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("MB_NO_CLOCK_SAMPLER")) else None
-    ms_total, (loss, neff, dp, _) = timed(lambda: device_pass(e_ref), args.steps)
-    ms_step = ms_total / args.steps
-    value = F / (ms_step * 1e-3)
 
-    # ---- end to end through the public API, host buffers ----
+    # ---- one DiffTRe step = compute_loss_and_grad (the public API): theta -> parameter bank, E and dE/dparams rows of this
+    # rank's frames, all-gather, weights / n_eff, loss, dL/dE, g @ J, theta chain backward, all-reduce -> loss + dL/dtheta
     def loss_fn(ref_states, weights, energy_fn, opt_params, observables):
         measured = (weights * obs).sum()
         return measured, (("obs", measured), None)
 
-    def e2e_step():
-        # the frames stay in pinned host memory: the public API streams them to the device chunk by chunk (copy stream),
-        # overlapped with the kernels of the previous chunk; every byte crosses PCIe inside the timed region
-        states = SimulatorTrajectory(center=c_host, orientation=Quaternion(q_host), temperature=temperature, shard=(lo, hi, F))
-        (l, aux), grads = objective.compute_loss_and_grad(theta, efn, beta, loss_fn, states, e_ref, [])
-        host = torch.stack([grads[k] for k in sorted(grads)]).cpu()
-        return float(l), host
+    states_dev = SimulatorTrajectory(center=c_dev, orientation=Quaternion(q_dev), temperature=temperature, shard=(lo, hi, F))
+    states_host = SimulatorTrajectory(center=c_host, orientation=Quaternion(q_host), temperature=temperature, shard=(lo, hi, F))
+    with torch.no_grad():
+        functional.PAIR_LIST_CACHE_GB = 0.0
+        e_ref = objective.sharded_map(efn, states_dev).detach()
 
-    for _ in range(max(1, args.warmup - 1)):
-        e2e_step()
+    def step(states):
+        (l, aux), grads = objective.compute_loss_and_grad(theta, efn, beta, loss_fn, states, e_ref, [])
+        host = torch.stack([grads[k] for k in sorted(grads)]).cpu()  # D2H of the gradients (loss below): the step's result
+        return float(l), host, aux
+
+    def measure(states, cache_gb):
+        functional.PAIR_LIST_CACHE_GB = cache_gb
+        functional._PAIR_LISTS.clear()
+        for _ in range(args.warmup):
+            step(states)
+        # warm-up is over when a pass no longer grows the caching allocator (a cudaMalloc of one more 0.7 GB pair-list
+        # block costs ~90 ms once, measured; it can still happen in the third pass): at most 4 extra untimed passes
+        for _ in range(4):
+            before = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+            step(states)
+            if torch.cuda.memory_stats(dev).get("num_device_alloc", 0) == before:
+                break
+        ms, out = timed(lambda: step(states), args.steps)
+        return ms / args.steps, out
+
+    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("MB_NO_CLOCK_SAMPLER")) else None
+    # headline numbers: COLD passes -- every pass rebuilds the per-frame pair lists (the pair-list cache is switched off)
+    ms_step, (loss, grad_host, aux) = measure(states_dev, 0.0)
+    value = F / (ms_step * 1e-3)
     if os.environ.get("MB_PROFILE_E2E") and rank == 0:  # development hook: host-side profile of one end-to-end step
         import cProfile
         import pstats
 
         prof = cProfile.Profile()
         prof.enable()
-        e2e_step()
+        step(states_host)
         prof.disable()
         pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
     elif os.environ.get("MB_PROFILE_E2E"):
-        e2e_step()
-    ms_e2e, _ = timed(e2e_step, args.steps)
-    ms_e2e /= args.steps
+        step(states_host)
+    # end to end: the frames stay in pinned host memory; the public API streams them to the device chunk by chunk (copy
+    # stream), overlapped with the kernels of the previous chunk; every byte crosses PCIe inside the timed region
+    ms_e2e, _ = measure(states_host, 0.0)
     clocks = sampler.stop() if sampler else None
+    # WARM passes: what every pass after the first costs while an optimiser keeps reweighting the same stored frames
+    # (the lists are remembered per frame tensor, functional._PairListCache; reached through DiffTReObjective.calculate)
+    ms_warm, _ = measure(states_dev, 24.0)
+    ms_warm_e2e, _ = measure(states_host, 24.0)
+    cache_bytes = functional._PAIR_LISTS.nbytes()
+    functional._PAIR_LISTS.clear()
+    functional.PAIR_LIST_CACHE_GB = 0.0
+    neff = aux[0]
     h2d = (c_host.numel() + q_host.numel()) * 8
     d2h = (len(theta) + 1) * 8
 
@@ -540,29 +613,46 @@ def main():
     src.verify()
     k_ms = float(np.median(launches[1:]))
     n_b = int(topo.bonded.shape[0])
-    slots_fwd = chunk * slots_forward(n, n_b, u)
     nl_ms = float(np.median(nl_launches[1:]))
-    flop_eq = 2 * 2.5 * slots_fwd  # E + params-only backward = 2.5 x forward; 1 FMA slot = 2 flop
-    achieved = flop_eq / (k_ms * 1e-3) / 1e12
+    # E + params-only backward = 2.5 x forward; 1 FMA slot = 2 flop.  The kernel is credited with what IT
+    # computes: on the support-tagged route the centre-distance screen of the listed pairs is the neighbour walk's work.
+    kernel_flop_eq = 2 * 2.5 * chunk * slots_forward(n, n_b, u, screen=False)
+    kernel_achieved = kernel_flop_eq / (k_ms * 1e-3) / 1e12
+    # the headline fraction is the whole step's: all algorithmic work of the pass (screen included) over the time of the
+    # COLD timed step (neighbour builds, frame kernel, reweighting, theta chain, collectives), all ranks' frames
+    step_flop_eq = 2 * 2.5 * F * slots_forward(n, n_b, u, screen=True)
+    step_achieved = step_flop_eq / (ms_step * 1e-3) / 1e12 / world
 
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     alg_bytes = chunk * (n * 7 * 8 + 8 * u["kept_by_tagged_build"] + 232 * 8 + 64)  # frame + tagged pairs in, J row + terms row out (slot padding not counted)
+    ncu = NCU_COUNTERS if (chunk == 1184 and n == 2040) else None
     roofline = {
-        "bound": "fp64", "kernel": "k_frame_energy<double,WP=1> (all terms of a frame; support-tagged pair lists from the device neighbour build)", "achieved": achieved, "peak": best, "unit": "TFLOP/s",
-        "frac": achieved / best if best else None,
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed ncu capture
-        # (profiles/r01_v7_k_frame_energy_details.csv: 754.9 MB + 28.5 MB), in bytes; other shapes have no capture.  It
-        # exceeds the algorithmic bytes by the padding entries of the one-pass warp-slot lists (64 000 entries per frame
-        # for 42 600 pairs): read once, skipped, never re-read.
-        "traffic": 0.7834e9 if (chunk == 1184 and n == 2040) else None,
+        "bound": "fp64", "kernel": "k_frame_energy<double,WP=1> (all terms of a frame; support-tagged pair lists from the device neighbour build)",
+        "achieved": step_achieved, "peak": best, "unit": "TFLOP/s", "frac": step_achieved / best if best else None,
+        "scope": "whole cold step per GPU (neighbour builds + frame kernel + reweighting + theta chain); frac_kernel is the dominant kernel alone",
+        "achieved_kernel": kernel_achieved, "frac_kernel": kernel_achieved / best if best else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of the kernel at this shape from the committed ncu capture, in bytes;
+        # other shapes have no capture.  It exceeds the algorithmic bytes by the padding entries of the one-pass warp-slot
+        # lists (64 000 entries per frame for 42 600 pairs): read once, skipped, never re-read.
+        "traffic": ncu["dram_bytes"] if ncu else None,
+        "ncu": ncu,
+        "model_vs_counter": (None if not ncu else
+                             f"frac_kernel / FP64-pipe counter = {kernel_achieved / best / (ncu['sm__inst_executed_pipe_fp64_pct'] / 100):.2f}: the model "
+                             "charges a special function its measured ISSUE cost in FMA slots (most of which are integer / FP32-seed / "
+                             "conversion instructions outside the FP64 pipe), the counter sees only DFMA/DMUL/DADD; compare with "
+                             "smsp__issue_active instead"),
         "peak_source": "measured in this run (library FMA micro-benchmark, 148x32 blocks x 256 threads)",
+        "special_weights": {k: round(v, 2) for k, v in W_SPECIAL.items()},
+        "special_weights_source": "measured in this run (csrc/peaks.cu: dependent chain of f(x)*a+b vs chain of FMA)",
         "kernel_ms_per_launch": k_ms, "frames_per_launch": chunk, "neighbour_build_ms_per_chunk": nl_ms,
         "share_of_step": k_ms / (k_ms + nl_ms),
         "pairs_per_frame": u,
+        "slots_forward_per_frame": {"kernel": slots_forward(n, n_b, u, screen=False), "step": slots_forward(n, n_b, u, screen=True)},
         "hbm": {"algorithmic_gb_per_launch": alg_bytes / 1e9, "achieved_gbs": alg_bytes / 1e9 / (k_ms * 1e-3), "peak_gbs": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-        "work_model": "SURVEY 8d per-pair counts split per term, each term counted only inside its radial support (supports measured on 16 frames); x2.5 for E + dE/dparams; fp64 special weights div16 sqrt16 exp40 log50 acos70",
+        "work_model": "SURVEY 8d per-pair flop + special counts split per term, each term counted only inside its radial support "
+                      "(supports measured on 16 frames); slots = flop/2 + sum(special x measured weight); x2.5 for E + dE/dparams",
     }
 
     cpu_baseline = None
@@ -580,8 +670,14 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload_name(F), "frames_per_gpu": hi - lo, "n_nucleotides": n,
                    "l2": "inputs larger than L2 (frames 936 MB + 0.8 GB of pair lists per 1184-frame chunk)", "n_theta": len(theta),
-                   "loss": float(loss.detach()), "n_eff": float(neff.detach()), "grad_norm": float(dp.norm())},
+                   "loss": loss, "n_eff": float(neff.detach()), "grad_norm": float(grad_host.norm()),
+                   "pass": "cold: the per-frame pair lists are rebuilt in every timed step (pair-list cache off)",
+                   "step": "objective.compute_loss_and_grad (theta -> bank, E + dE/dparams rows, gather, weights/n_eff, loss, g @ J, theta VJP, all-reduce)"},
         "e2e": {"value": F / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        # every pass after the first while an optimiser reweights the same stored frames (DiffTReObjective.calculate)
+        "warm": {"value": F / (ms_warm * 1e-3), "ms_per_step": ms_warm, "e2e_value": F / (ms_warm_e2e * 1e-3), "e2e_ms_per_step": ms_warm_e2e,
+                 "unit": UNIT, "pair_list_cache_bytes_per_gpu": cache_bytes,
+                 "what": "pair lists remembered per frame tensor (built once with a 1% cutoff margin); no neighbour kernels in the timed step"},
         "gpu_launches": args.steps * (n_chunks * 24 + 1),  # k_nl_* + k_frame_energy per chunk, k_weights per step (torch glue not counted)
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "md": md_line, "forces_8k": forces_8k,
         "forces_100k": forces_100k,

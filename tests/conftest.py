@@ -17,3 +17,18 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return ROOT / "tests" / "golden"
+
+
+@pytest.fixture
+def no_pair_list_cache():
+    """Tests of the pair-list SIZING logic (capacities, slot geometry, repeats) need every pass to build its lists."""
+    from mythos_b200.energy import functional
+
+    old = functional.PAIR_LIST_CACHE_GB
+    functional.PAIR_LIST_CACHE_GB = 0.0
+    functional._PAIR_LISTS.clear()
+    try:
+        yield
+    finally:
+        functional.PAIR_LIST_CACHE_GB = old
+        functional._PAIR_LISTS.clear()

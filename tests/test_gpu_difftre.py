@@ -200,9 +200,9 @@ def test_all_pairs_sentinel_equals_explicit_all_pairs_list(box, in_kernel):
     np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-10, atol=1e-10)
 
 
-def test_pinned_host_frames_are_streamed_and_give_identical_results(workload):
+def test_pinned_host_frames_are_streamed_and_give_identical_results(workload, no_pair_list_cache):
     """``map`` over frames that live in pinned host memory (streamed to the device chunk by chunk on a copy stream) must
-    reproduce the device-resident result bit for bit, energies and theta-gradients; pageable host memory is refused."""
+    reproduce the device-resident result (1e-13), energies and theta-gradients; pageable host memory is refused."""
     from mythos_b200 import _lib
     from mythos_b200.energy import functional
 
@@ -221,15 +221,17 @@ def test_pinned_host_frames_are_streamed_and_give_identical_results(workload):
             assert e.is_cuda
             (e * torch.arange(1, e.shape[0] + 1, device=e.device, dtype=e.dtype)).sum().backward()
             outs.append((e.detach().cpu().numpy(), float(th["eps_hb"].grad)))
-        np.testing.assert_array_equal(outs[0][0], outs[1][0])
-        assert outs[0][1] == outs[1][1]
+        # (streamed passes cut their chunks differently -- ramping up from one wave -- so the per-chunk list layout and with
+        # it the summation order inside a frame may differ in the last bit)
+        np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-13)
+        np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=1e-12)
         with pytest.raises(_lib.MythosB200Error):
             efn.map(RigidBody(torch.tensor(c), Quaternion(torch.tensor(q))))
     finally:
         functional.FRAME_CHUNK = old
 
 
-def test_loss_and_grad_with_prefetched_pinned_frames_equals_device_frames(workload):
+def test_loss_and_grad_with_prefetched_pinned_frames_equals_device_frames(workload, no_pair_list_cache):
     """``compute_loss_and_grad`` starts the copy of the first chunk of pinned host frames before the theta chain
     (``functional.prefetch_frames``); loss and gradients must be those of device-resident frames, also when the pass
     that follows uses other buffers than the prefetched ones (the stale copy is dropped)."""
@@ -275,7 +277,7 @@ def test_loss_and_grad_with_prefetched_pinned_frames_equals_device_frames(worklo
         functional.FRAME_CHUNK = old
 
 
-def test_deferred_verification_reports_an_overflowed_pass_and_the_repeat_is_right(workload):
+def test_deferred_verification_reports_an_overflowed_pass_and_the_repeat_is_right(workload, no_pair_list_cache):
     """``functional.deferred_verification``: the evaluation does not read the overflow flags itself; the caller does after
     its own launches.  Slots that are too narrow must be reported (``ok()`` False, geometry re-fitted), and the repeated
     pass must give the energies and dE/dparams rows of an ordinary pass."""
@@ -318,7 +320,7 @@ def test_deferred_verification_reports_an_overflowed_pass_and_the_repeat_is_righ
         functional._SIZING.clear()
 
 
-def test_loss_and_grad_recovers_when_fresh_sources_start_from_capacities_that_overflow(workload):
+def test_loss_and_grad_recovers_when_fresh_sources_start_from_capacities_that_overflow(workload, no_pair_list_cache):
     """``compute_loss_and_grad`` rebuilds the energy function -- and with it the pair source -- on every repeat.  What a
     source learns when a list overflows (capacities, slot geometry, float64 fallback) must survive in the sizing memo, or
     the repeat overflows on the same frame forever (round-1 advisor finding).  Poison the memo with sizes that are far too
@@ -372,7 +374,7 @@ def test_loss_and_grad_recovers_when_fresh_sources_start_from_capacities_that_ov
         functional._SIZING.clear()
 
 
-def test_tagged_float32_builds_are_safe_far_from_the_origin_and_for_extended_systems():
+def test_tagged_float32_builds_are_safe_far_from_the_origin_and_for_extended_systems(no_pair_list_cache):
     """The support-tagged builds run in float32 on recentred coordinates: a trajectory far from the origin must give the
     energies of the same trajectory at the origin, and a system too extended for float32 (two duplexes 4000 length units
     apart) must fall back to float64 builds and still agree with plain lists."""
@@ -509,7 +511,7 @@ def test_remembered_pair_lists_give_the_same_pass_and_are_invalidated_correctly(
     obs = torch.linspace(-1.0, 1.0, F, dtype=torch.float64, device=DEV)
 
     def loss_fn(ref_states, weights, energy_fn, opt_params, observables):
-        m = (weights * obs).sum()
+        m = (weights * obs[-weights.shape[0]:]).sum()
         return m, (("obs", m), None)
 
     builds = []
