@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MB_ABI_VERSION 2
+#define MB_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------------------------------------- */
 enum mb_status {
@@ -339,6 +339,32 @@ typedef struct mb_model {
 } mb_model;
 
 /* ---- energy / forces / parameter gradient ----------------------------------------------------------------- */
+/* ---- per-frame structural observables -------------------------------------------------------
+ * Stand in for mythos/observables/propeller.py:18-71 (PropellerTwist), rise.py:19-70 (Rise), pitch.py:32-88
+ * (PitchAngle), diameter.py:21-76 (Diameter) and base.py:24-44 (local_helical_axis): per frame, the MEAN over the listed
+ * base pairs / quartets of
+ *   MB_OBS_PROPELLER    180 - acos(clamp(a3_i . a3_j)) * 180/pi            [degrees]       (base pairs)
+ *   MB_OBS_DIAMETER     (|disp(back_i, back_j)| + sigma_backbone) * 8.518   [Angstrom]      (base pairs)
+ *   MB_OBS_RISE         dot(dr, dr/|dr|) * 8.518, dr = disp(midp2, midp1)   [Angstrom]      (quartets)
+ *   MB_OBS_PITCH_ANGLE  acos(clamp(p1 . p2)), p = backbone-backbone vector of a base pair with its component along the
+ *                       local helical axis removed, normalised              [radians]       (quartets)
+ * with midp = midpoint of the two base sites of a base pair; sites from the model's flavour geometry (nt_type picks the
+ * flavour for the 3-bank model).  An empty list gives NaN in its columns (mean of nothing), as jnp.mean does. */
+enum mb_observable { MB_OBS_PROPELLER = 0, MB_OBS_RISE = 1, MB_OBS_PITCH_ANGLE = 2, MB_OBS_DIAMETER = 3, MB_N_OBS = 4 };
+typedef struct mb_observable_spec {
+  const int32_t* base_pairs; /* (P,2) hydrogen-bonded nucleotide pairs, device pointer */
+  int32_t n_base_pairs;
+  int32_t n_quartets;
+  const int32_t* quartets;   /* (Q,4) = (a1, b1, a2, b2): two adjacent base pairs (a1-b1), (a2-b2), device pointer */
+  double sigma_backbone;     /* excluded-volume distance added to the diameter (diameter.py:40) */
+} mb_observable_spec;
+/* standalone: center (F,N,3), quat (F,N,4) -> out (F, MB_N_OBS); one block per frame, HBM-bound (reads only the listed
+ * nucleotides) */
+int mythos_b200_observables_f64(void* cuda_stream, const mb_model* model, int32_t n, int32_t n_frames, const void* center,
+                                const void* quat, const int32_t* nt_type, const mb_observable_spec* spec, void* out);
+int mythos_b200_observables_f32(void* cuda_stream, const mb_model* model, int32_t n, int32_t n_frames, const void* center,
+                                const void* quat, const int32_t* nt_type, const mb_observable_spec* spec, void* out);
+
 typedef struct mb_energy_args {
   const mb_model* model;
   int32_t n;              /* nucleotides per frame                                                           */
@@ -375,6 +401,10 @@ typedef struct mb_energy_args {
   size_t workspace_bytes;
   const int32_t* pair_split; /* MB_FLAG_TAGGED_PAIRS with the list kernels: (F) entries of each list before this index are
                               * the short-range pairs, the rest (up to pair_count) the Debye pairs; else NULL              */
+  const mb_observable_spec* observables; /* optional: also evaluate the per-frame observables of these frames in this call.
+                              * On the frame-resident route they are an epilogue of the SAME kernel (the frame is already in
+                              * shared memory); on the other routes the standalone kernel is enqueued behind the energy kernels */
+  void* observables_out;     /* out (F, MB_N_OBS) when `observables` is set */
 } mb_energy_args;
 #define MB_FLAG_ACCUMULATE 0x1u /* add into the outputs instead of zeroing them first */
 #define MB_FLAG_GENERIC_KERNEL 0x2u /* force the one-thread-per-pair kernels even where the frame-resident kernel applies */

@@ -103,7 +103,18 @@ class EnergyArgs(C.Structure):
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
         ("pair_split", C.c_void_p),
+        ("observables", C.c_void_p),
+        ("observables_out", C.c_void_p),
     ]
+
+
+class ObservableSpec(C.Structure):
+    _fields_ = [("base_pairs", C.c_void_p), ("n_base_pairs", C.c_int32), ("n_quartets", C.c_int32), ("quartets", C.c_void_p),
+                ("sigma_backbone", C.c_double)]
+
+
+N_OBS = 4
+OBS_PROPELLER, OBS_RISE, OBS_PITCH_ANGLE, OBS_DIAMETER = range(4)
 
 
 class NlArgs(C.Structure):
@@ -196,6 +207,8 @@ _SIGNATURES = {
     "mythos_b200_fma_peak_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mythos_b200_special_rate_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "mythos_b200_special_rate_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "mythos_b200_observables_f64": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ObservableSpec), C.c_void_p]),
+    "mythos_b200_observables_f32": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ObservableSpec), C.c_void_p]),
     "mythos_b200_theta_tape_forward": (C.c_int, [C.c_void_p] * 4),
     "mythos_b200_theta_tape_vjp": (C.c_int, [C.c_void_p] * 5),
     "mythos_b200_abi_version": (C.c_int, []),

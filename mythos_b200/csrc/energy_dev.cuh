@@ -8,6 +8,15 @@ namespace mb {
 
 constexpr unsigned kFull = 0xffffffffu;
 
+// per-frame structural observables (observables_dev.cuh): device-side copy of mb_observable_spec
+struct ObsDev {
+  const int32_t* base_pairs;
+  const int32_t* quartets;
+  int n_base_pairs, n_quartets;
+  double sigma_backbone;
+};
+int check_observable_spec(const mb_observable_spec* spec, ObsDev* o);
+
 template <class T>
 struct EnergyDev {
   ModelT<T> M;
@@ -38,6 +47,8 @@ struct EnergyDev {
   long long sr_capacity;
   int tagged;  // `pairs` carries support tags (MB_NL_TAG_SUPPORTS)
   const int32_t* pair_split;  // tagged lists: (F) entries before it are short-range pairs, after it Debye pairs (list kernels)
+  ObsDev obs;                 // fused observables epilogue of the frame-resident kernel (obs_out != nullptr)
+  T* obs_out;                 // (F, MB_N_OBS) or nullptr
 };
 
 // Parameter-gradient accumulator: warp-reduce, then one shared-memory atomic per warp and parameter.

@@ -8,6 +8,7 @@
 // warp-reduced into a shared-memory bank image and flushed once per block.
 #include "common.cuh"
 #include "energy_dev.cuh"
+#include "observables_dev.cuh"
 
 namespace mb {
 
@@ -210,6 +211,15 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
   a.sr_capacity = 0;
   a.tagged = (x->flags & MB_FLAG_TAGGED_PAIRS) ? 1 : 0;
   a.pair_split = x->pair_split;
+  a.obs_out = nullptr;
+  ObsDev obs{};
+  T* obs_out = nullptr;
+  if (x->observables) {
+    MB_REQUIRE(x->observables_out, MB_EINVAL_SHAPE, "energy: observables requested without observables_out");
+    const int st = check_observable_spec(x->observables, &obs);
+    if (st != MB_OK) return st;
+    obs_out = static_cast<T*>(x->observables_out);
+  }
 
   const size_t np = (size_t)m.n_banks * MB_P_COUNT;
   if (!(x->flags & MB_FLAG_ACCUMULATE)) {
@@ -225,7 +235,15 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
   }
   const bool wf = a.d_center || a.d_quat, wp = a.d_params != nullptr;
   // frame-resident path: one block per frame with the frame staged in shared memory (energies and dE/dparams only)
-  if (!wf && !(x->flags & MB_FLAG_GENERIC_KERNEL) && frame_kernel_eligible<T>(a)) return launch_frame_kernel<T>(s, a, wp);
+  if (!wf && !(x->flags & MB_FLAG_GENERIC_KERNEL) && frame_kernel_eligible<T>(a)) {
+    a.obs = obs;
+    a.obs_out = obs_out;  // epilogue of the same kernel: the frame is already in shared memory
+    return launch_frame_kernel<T>(s, a, wp);
+  }
+  if (obs_out) {  // every other route: the standalone kernel, enqueued on the same stream
+    const int st = launch_observables<T>(s, a.M, a.n, a.n_frames, a.center, a.quat, m.n_banks == 1 ? nullptr : a.nt_type, obs, obs_out);
+    if (st != MB_OK) return st;
+  }
   MB_REQUIRE(!a.tagged || (x->pair_split && x->pair_count && x->workspace), MB_ECAPACITY,
              "energy: tagged pair lists need the frame-resident kernel (single bank, no position gradients, frame fits in "
              "shared memory, n < 16384) or the list kernels (workspace, pair_count and pair_split)");

@@ -27,6 +27,7 @@
 //
 // Every queue append is ordered (block prefix over warp counts), so results are bitwise repeatable run to run.
 #include "energy_dev.cuh"
+#include "observables_dev.cuh"
 
 namespace mb {
 
@@ -264,6 +265,23 @@ __device__ __forceinline__ void cell_of(const CellGrid<T>* grid, const T* box, b
     ci = ci < 0 ? 0 : (ci >= grid->n[d] ? grid->n[d] - 1 : ci);
     cc[d] = ci;
   }
+}
+
+// the observables epilogue as a real call with scalar arguments: its registers are allocated on their own and nothing of the
+// energy phases' state has its address taken (which would push it into local memory)
+template <class T>
+__device__ __noinline__ void frame_observables_smem(const int32_t* base_pairs, const int32_t* quartets, int n_bp, int n_q, double sigma,
+                                                    T box0, T box1, T box2, T back0, T back1, T back2, T base, const T* sC, const T* sQ,
+                                                    T* red, T* out) {
+  ObsDev o{base_pairs, quartets, n_bp, n_q, sigma};
+  const T box[3] = {box0, box1, box2};
+  Geom<T> g{};
+  g.back[0] = back0;
+  g.back[1] = back1;
+  g.back[2] = back2;
+  g.base = base;
+  frame_observables<T>(
+      o, box, [&](int i) { return smem_nuc(sC, sQ, i); }, [&](int) -> const Geom<T>& { return g; }, red, out);
 }
 
 #ifdef MB_FRAME_PROFILE
@@ -917,6 +935,15 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
       for (int r = 0; r < L.acc_rows; ++r) v += sAcc[r * MB_P_COUNT + p];
       if (v != T(0)) atomicAdd(&out[p], v);
     }
+  }
+  // ---------------------------------------------------------------- fused observables
+  // propeller twist / rise / pitch angle / diameter of this frame from the nucleotides already staged in shared memory
+  // (the reference re-derives every site of every frame in a second vmap pass inside the loss function)
+  if (a.obs_out) {
+    __syncthreads();  // sE (the per-warp energy rows) becomes the reduction scratch
+    frame_observables_smem<T>(a.obs.base_pairs, a.obs.quartets, a.obs.n_base_pairs, a.obs.n_quartets, a.obs.sigma_backbone, M.box[0],
+                              M.box[1], M.box[2], g.back[0], g.back[1], g.back[2], g.base, sC, sQ, sE,
+                              a.obs_out + (long long)frame * MB_N_OBS);
   }
 }
 

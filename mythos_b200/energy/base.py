@@ -263,9 +263,12 @@ class ComposedEnergyFunction(EnergyFunction):
     def __call__(self, body: RigidBody) -> torch.Tensor:
         return self._combine(self.compute_terms(body))
 
-    def map(self, body_sequence: RigidBody) -> torch.Tensor:
+    def map(self, body_sequence: RigidBody, observables=None) -> torch.Tensor:
         """(F,) energies.  When the whole composition fuses into one launch group the weighted sum and the
-        parameter-gradient rows come out of a single pass (``functional._FrameEnergy``, the DiffTRe shape)."""
+        parameter-gradient rows come out of a single pass (``functional._FrameEnergy``, the DiffTRe shape).
+
+        ``observables``: a ``mythos_b200.observables.ObservableSet`` evaluated in the SAME pass (epilogue of the
+        frame-resident kernel); its members then answer ``observable(body_sequence)`` from that result."""
         c, q, _ = _frames(body_sequence)
         groups = kmodel.fusable_groups(self.energy_fns)
         if len(groups) == 1:
@@ -273,7 +276,7 @@ class ComposedEnergyFunction(EnergyFunction):
             wt = torch.ones(len(self.energy_fns), dtype=torch.float64) if self.weights is None else torch.as_tensor(self.weights, dtype=torch.float64).cpu()
             for k, fn in enumerate(self.energy_fns):
                 w[fn.TERM] = wt[k]
-            return kmodel.plan_for(self.energy_fns).evaluate_total(c, q, w)
+            return kmodel.evaluate_with_observables(kmodel.plan_for(self.energy_fns), c, q, w, observables)
         return self._combine(self.compute_terms_frames(body_sequence))
 
     def without_terms(self, *terms: list[str | type]) -> "ComposedEnergyFunction":

@@ -71,6 +71,7 @@ def _launch(
     all_pairs_cutoff: float = 0.0,
     out: tuple | None = None,
     pair_split: torch.Tensor | None = None,
+    observables=None,
 ):
     _lib.require_cuda(center, "center")
     F, N = center.shape[0], center.shape[1]
@@ -129,6 +130,11 @@ def _launch(
     a.d_params_frame_stride = stride
     ws = None
     a.pair_split = _lib.ptr(pair_split) if cap else None
+    obs_spec = None
+    if observables is not None:  # (ObservableRequest, out (F,4)): fused epilogue of the frame-resident kernel, else a launch behind it
+        obs_spec = observables[0].struct()
+        a.observables = C.addressof(obs_spec)
+        a.observables_out = observables[1].data_ptr()
     if cap and (cap * F >= 65536 or (flags & (_lib.FLAG_LIST_KERNEL | _lib.FLAG_TAGGED_PAIRS))) and not (flags & _lib.FLAG_GENERIC_KERNEL):
         # scratch of the phase-queued list kernel (caller-owned, as everywhere in the C-ABI); the caching allocator
         # makes this a pointer bump, and it is graph-capture safe
@@ -535,14 +541,19 @@ def _chunks(n_frames: int, source, streamed: bool = False) -> list[slice]:
     return out
 
 
-def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, want_pos, want_par, per_frame_par, flags=0):
-    """Chunked launch over frames; concatenates / sums the per-chunk outputs."""
+def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, want_pos, want_par, per_frame_par, flags=0,
+         observables=None):
+    """Chunked launch over frames; concatenates / sums the per-chunk outputs.  ``observables``: an ``ObservableRequest``
+    whose ``out`` receives the (F,4) per-frame observables evaluated in the same pass."""
+    if observables is not None:
+        observables.out = torch.empty((center.shape[0], _lib.N_OBS), dtype=center.dtype, device=params.device)
     if isinstance(source, CellListPairs) and not want_pos and model.n_banks == 1 and source.in_kernel and not (flags & _lib.FLAG_GENERIC_KERNEL):
         # all-pairs mode inside the frame-resident kernel: the CTA finds its own pairs, no list in HBM
         try:
             outs = [
                 _launch(model, topo, center[sl], quat[sl], params, None, 0, term_mask, None if cot is None else cot[sl],
-                        want_terms, False, want_par, per_frame_par, None, flags, source.r_cutoff)
+                        want_terms, False, want_par, per_frame_par, None, flags, source.r_cutoff,
+                        observables=None if observables is None else (observables, observables.out[sl]))
                 for sl in _chunks(center.shape[0], None)
             ]
             return _merge(outs, want_terms, False, want_par, per_frame_par)
@@ -618,7 +629,8 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
                 outs.append(
                     _launch(model, topo, c_sl, q_sl, params, pairs, stride, term_mask,
                             None if cot is None else cot[sl], want_terms, want_pos, want_par, per_frame_par, count,
-                            flags | (_lib.FLAG_TAGGED_PAIRS if tagged else 0), 0.0, None, split)
+                            flags | (_lib.FLAG_TAGGED_PAIRS if tagged else 0), 0.0, None, split,
+                            observables=None if observables is None else (observables, observables.out[sl]))
                 )
         except _lib.MythosB200Error as err:
             if not tagged or getattr(err, "status", None) != 3:  # MB_ECAPACITY: the frame-resident kernel does not apply
@@ -754,11 +766,12 @@ class _FrameEnergy(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, center, quat, params, weights, model, topo, source, term_mask):
+    def forward(ctx, center, quat, params, weights, model, topo, source, term_mask, observables=None):
         F = center.shape[0]
         cot = weights.to(device=params.device, dtype=center.dtype).reshape(1, -1).expand(F, -1).contiguous()
         jac_now = ctx.needs_input_grad[2] and not (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
-        terms, _, _, J = _run(model, topo, center, quat, params, source, term_mask, cot, True, False, jac_now, True)
+        terms, _, _, J = _run(model, topo, center, quat, params, source, term_mask, cot, True, False, jac_now, True,
+                              observables=observables)
         ctx.jac_now = jac_now
         if jac_now:
             ctx.save_for_backward(J)
@@ -772,7 +785,7 @@ class _FrameEnergy(torch.autograd.Function):
         model, topo, source, mask, pdev, pdtype = ctx.static
         if ctx.jac_now:
             (J,) = ctx.saved_tensors
-            return None, None, (g.to(J.dtype) @ J).to(device=pdev, dtype=pdtype), None, None, None, None, None
+            return None, None, (g.to(J.dtype) @ J).to(device=pdev, dtype=pdtype), None, None, None, None, None, None
         center, quat, params, cot = ctx.saved_tensors
         need_pos = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         _, d_center, d_quat, d_params = _run(
@@ -782,7 +795,7 @@ class _FrameEnergy(torch.autograd.Function):
         if d_params is not None:
             d_params = d_params.to(device=pdev, dtype=pdtype)
         return (d_center if ctx.needs_input_grad[0] else None, d_quat if ctx.needs_input_grad[1] else None, d_params,
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
 def _source_of(pairs) -> StaticPairs | CellListPairs:
@@ -798,11 +811,13 @@ def energy_terms(model, topo, center, quat, params, pairs, term_mask: int = _lib
     return _EnergyTerms.apply(center, quat, params, model, topo, _source_of(pairs), term_mask)
 
 
-def frame_energies(model, topo, center, quat, params, pairs, weights: torch.Tensor, term_mask: int = _lib.ALL_TERMS) -> torch.Tensor:
-    """``sum_t weights[t] * E_t`` per frame, ``(F,)``; see ``_FrameEnergy`` for the fused parameter-gradient pass."""
+def frame_energies(model, topo, center, quat, params, pairs, weights: torch.Tensor, term_mask: int = _lib.ALL_TERMS,
+                   observables=None) -> torch.Tensor:
+    """``sum_t weights[t] * E_t`` per frame, ``(F,)``; see ``_FrameEnergy`` for the fused parameter-gradient pass.
+    ``observables``: an ``ObservableRequest`` (mythos_b200.observables.base) filled in the same pass."""
     if center.dim() != 3 or quat.dim() != 3:
         raise _lib.MythosB200Error("center must be (F,N,3) and quat (F,N,4)")
-    return _FrameEnergy.apply(center, quat, params, weights, model, topo, _source_of(pairs), term_mask)
+    return _FrameEnergy.apply(center, quat, params, weights, model, topo, _source_of(pairs), term_mask, observables)
 
 
 def energy_and_gradients(model, topo, center, quat, params, pairs, cot=None, term_mask: int = _lib.ALL_TERMS,

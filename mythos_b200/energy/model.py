@@ -198,7 +198,7 @@ class Plan:
             self.model, topo, center, quat, self.device_params(dev, dtype), self.pairs(dev, topo), self.term_mask
         )
 
-    def evaluate_total(self, center: torch.Tensor, quat: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    def evaluate_total(self, center: torch.Tensor, quat: torch.Tensor, weights: torch.Tensor, observables=None) -> torch.Tensor:
         """(F,) weighted total energies with the parameter-gradient rows produced in the same pass (DiffTRe shape).
 
         ``center`` / ``quat`` may also be PINNED HOST tensors (stored trajectory frames): they are then streamed to the
@@ -212,8 +212,20 @@ class Plan:
         dtype = center.dtype
         topo = self.topology(center.shape[1], dev)
         return functional.frame_energies(
-            self.model, topo, center, quat, self.device_params(dev, dtype), self.pairs(dev, topo), weights, self.term_mask
+            self.model, topo, center, quat, self.device_params(dev, dtype), self.pairs(dev, topo), weights, self.term_mask,
+            observables,
         )
+
+
+def evaluate_with_observables(plan: "Plan", center: torch.Tensor, quat: torch.Tensor, weights: torch.Tensor, observables=None) -> torch.Tensor:
+    """``plan.evaluate_total`` with an optional ``ObservableSet`` evaluated in the same pass and published to its members
+    (device-resident frames only: the result is remembered per frames tensor)."""
+    if observables is None or not center.is_cuda:
+        return plan.evaluate_total(center, quat, weights)
+    req = observables.request(center.device)
+    e = plan.evaluate_total(center, quat, weights, req)
+    observables.publish(center, req)
+    return e
 
 
 def interaction_range(plan: "Plan") -> float:

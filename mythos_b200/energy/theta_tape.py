@@ -472,12 +472,13 @@ class BoundEnergyFunction:
             object.__setattr__(self, "_real", self._base.with_params(self._opt))
         return self._real
 
-    def map(self, body_sequence):
+    def map(self, body_sequence, observables=None):
+        from mythos_b200.energy import model as kmodel
         from mythos_b200.energy.base import _frames
 
         c, q, _ = _frames(body_sequence)
         plan = dc.replace(self._entry.plan, bank=self._bank)
-        return plan.evaluate_total(c, q, self._entry.weights)
+        return kmodel.evaluate_with_observables(plan, c, q, self._entry.weights, observables)
 
     def with_params(self, *repl_dicts, **repl_kwargs):
         return self._materialise().with_params(*repl_dicts, **repl_kwargs)

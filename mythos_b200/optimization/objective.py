@@ -185,7 +185,7 @@ class _GatherFrames(torch.autograd.Function):
         return g[lo:hi].contiguous(), None
 
 
-def sharded_map(energy_fn: EnergyFunction, states: RigidBody, sharded: bool | None = None) -> torch.Tensor:
+def sharded_map(energy_fn: EnergyFunction, states: RigidBody, sharded: bool | None = None, observables=None) -> torch.Tensor:
     """``energy_fn.map(states)`` -> (F,) with the frames split over the ranks when torch.distributed is up.
 
     ``states`` holds ALL frames on every rank (they are a few hundred MB and arrive by the same route on each rank);
@@ -194,7 +194,7 @@ def sharded_map(energy_fn: EnergyFunction, states: RigidBody, sharded: bool | No
     if sharded is None:
         sharded = world > 1
     if not sharded or world == 1:
-        return energy_fn.map(states)
+        return energy_fn.map(states, observables=observables) if observables is not None else energy_fn.map(states)
     shard = getattr(states, "shard", None)
     if shard is not None:  # the caller already holds only this rank's block (lo, hi, total)
         lo, hi, total = shard
@@ -241,7 +241,9 @@ def compute_loss(opt_params, energy_fn: EnergyFunction, beta, loss_fn, ref_state
     # = energy_fn.with_params(opt_params); the theta -> parameter-bank chain is replayed from a tape recorded once per
     # energy function (what jit does for the reference) instead of ~700 eager autograd nodes per step
     energy_fn = theta_tape.bind(energy_fn, opt_params)
-    new_energies = sharded_map(energy_fn, ref_states)
+    # observables the loss function declares (loss_fn.fused_observables = ObservableSet([...])) are evaluated by the epilogue of
+    # the same kernel that computes the energies; loss_fn's own observable(ref_states) calls then find them ready
+    new_energies = sharded_map(energy_fn, ref_states, observables=getattr(loss_fn, "fused_observables", None))
     weights, neff = compute_weights_and_neff(beta, new_energies, ref_energies)
     loss, (measured_value, _) = loss_fn(ref_states, weights, energy_fn, opt_params, observables)
     return loss, (neff, measured_value, new_energies)

@@ -46,7 +46,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert not missing, missing
     assert set(_lib.EXPORTED_SYMBOLS) <= declared
     lib = _lib.lib()
-    assert lib.mythos_b200_abi_version() == 2
+    assert lib.mythos_b200_abi_version() == 3
     assert lib.mythos_b200_param_count() == 232
     names = _lib.param_names()
     assert len(names) == 231 and len(set(names)) == 231
