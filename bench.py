@@ -528,9 +528,17 @@ def main():
         functional.PAIR_LIST_CACHE_GB = 0.0
         e_ref = objective.sharded_map(efn, states_dev).detach()
 
+    debug_steps = bool(os.environ.get("MB_DEBUG_STEPS"))
+
     def step(states):
+        t0 = time.perf_counter() if debug_steps else 0.0
         (l, aux), grads = objective.compute_loss_and_grad(theta, efn, beta, loss_fn, states, e_ref, [])
         host = torch.stack([grads[k] for k in sorted(grads)]).cpu()  # D2H of the gradients (loss below): the step's result
+        if debug_steps and rank == 0:
+            st = torch.cuda.memory_stats(dev)
+            print(f"[step] {'dev' if states.center.is_cuda else 'host'} cache={functional.PAIR_LIST_CACHE_GB} {1e3 * (time.perf_counter() - t0):.2f} ms "
+                  f"cudaMalloc {st['num_device_alloc']} cudaFree {st['num_device_free']} reserved {st['reserved_bytes.all.current'] / 2**30:.2f} GB",
+                  file=sys.stderr, flush=True)
         return float(l), host, aux
 
     def measure(states, cache_gb):

@@ -195,6 +195,17 @@ class _SizingMemo:
 
 
 _SIZING = _SizingMemo()
+_PAIR_SCRATCH: dict = {}
+
+
+def _scratch_pairs(device, n_frames: int, cap: int) -> torch.Tensor:
+    """(F,2,cap) int32 view of the per-(device, stream) scratch buffer for pair lists that live for one launch."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    need = n_frames * 2 * cap
+    buf = _PAIR_SCRATCH.get(key)
+    if buf is None or buf.numel() < need:
+        _PAIR_SCRATCH[key] = buf = torch.empty(int(need * 1.1) + 1024, dtype=torch.int32, device=device)
+    return buf[:need].view(n_frames, 2, cap)
 MAX_PASS_REPEATS = 6  # a pass is repeated when a pair list overflowed; capacities grow geometrically, so this is generous
 
 
@@ -230,6 +241,7 @@ class CellListPairs:
     _pending: list = dc.field(default_factory=list)
 
     _memo_key: tuple | None = None
+    keep_lists: bool = False  # the lists of this pass will be remembered: they must not share the reused scratch buffer
     _cache_candidates: list = dc.field(default_factory=list)  # lists built this pass, remembered once verify() passes
 
     def _settle_cache(self, good: bool) -> None:
@@ -272,7 +284,11 @@ class CellListPairs:
             (ka, wa), (kb, wb) = geo
             cap = wpf * (wa + (wb if ss is not None else 0))
             F = cc.shape[0]
-            pairs = torch.empty((F, 2, cap), dtype=torch.int32, device=cc.device)
+            # lists that are consumed by the very next launch and then dropped live in one reused per-device buffer (stream
+            # order makes that safe); a fresh 0.6 GB tensor per chunk made the caching allocator cudaMalloc a new block at
+            # unpredictable passes (~100 ms each).  Lists that will be remembered (_PairListCache) own their memory.
+            pairs = (torch.empty((F, 2, cap), dtype=torch.int32, device=cc.device) if self.keep_lists
+                     else _scratch_pairs(cc.device, F, cap))
             count = torch.empty((F,), dtype=torch.int32, device=cc.device)
             overflow = torch.zeros((1,), dtype=torch.int32, device=cc.device)
             mra = torch.empty((F, 2), dtype=torch.int32, device=cc.device)
@@ -604,6 +620,8 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
                     source.tag = (source.tag[0], built[0], built[1], *source.tag[3:])
                 else:
                     source.r_cutoff = built[0]
+            if isinstance(source, CellListPairs):
+                source.keep_lists = bool(cacheable)
             nxt = _fetch(center, quat, chunks[0], dev) if streamed else None
             for k, sl in enumerate(chunks):
                 if streamed:

@@ -448,7 +448,8 @@ def _entry_for(energy_fn, opt_params) -> _Entry | None:
         hit = _CACHE.get(key)
         if hit is not None and hit.ref() is energy_fn:
             return hit
-    entry = _build_entry(energy_fn, opt_params, names, shapes)
+    with torch.enable_grad():  # (the first call may come from inside a no_grad block; the self-check differentiates)
+        entry = _build_entry(energy_fn, opt_params, names, shapes)
     with _LOCK:
         for k in [k for k, e in _CACHE.items() if e.ref() is None]:
             del _CACHE[k]
