@@ -365,6 +365,27 @@ int mythos_b200_observables_f64(void* cuda_stream, const mb_model* model, int32_
 int mythos_b200_observables_f32(void* cuda_stream, const mb_model* model, int32_t n, int32_t n_frames, const void* center,
                                 const void* quat, const int32_t* nt_type, const mb_observable_spec* spec, void* out);
 
+/* ---- probabilistic sequences ----------------------------------------------------------------
+ * Stand in for `compute_seq_dep_weight` (mythos/energy/utils.py:45-132) as used by Stacking.pseq_weights
+ * (dna1/stacking.py:261-287) and HydrogenBonding.weight (dna1/hydrogen_bonding.py:308-335): the sequence weight of a
+ * pair is the expectation of the term's 4x4 table under a distribution in which nucleotides are independent except
+ * the two members of one base pair.  The host reduces (unpaired_pseq, bp_pseq, SequenceConstraints) to per-nucleotide
+ * marginals and per-base-pair same-pair expectations (differentiable there); the kernel evaluates
+ *   w(i,j) = same_w[bp][within_i]                      if i and j are the two members of base pair bp
+ *          = sum_ab pmarg[i][a] W[a][b] pmarg[j][b]    otherwise
+ * and returns the gradients with respect to W (in d_params), pmarg and same_w.  Generic pair kernel only
+ * (MB_FLAG_GENERIC_KERNEL, explicit pair list, single-bank models); gradient outputs are ACCUMULATED into (zero them). */
+typedef struct mb_pseq {
+  const void* pmarg;          /* (N,4) reals */
+  const int32_t* bp_of;       /* (N) base-pair index, -1 = unpaired */
+  const int32_t* within;      /* (N) 0/1 position inside its base pair */
+  const void* same_w_stack;   /* (n_bp,2) reals, may be NULL if n_bp == 0 */
+  const void* same_w_hb;      /* (n_bp,2) */
+  void* d_pmarg;              /* out (N,4) or NULL */
+  void* d_same_w_stack;       /* out (n_bp,2) or NULL */
+  void* d_same_w_hb;          /* out (n_bp,2) or NULL */
+} mb_pseq;
+
 typedef struct mb_energy_args {
   const mb_model* model;
   int32_t n;              /* nucleotides per frame                                                           */
@@ -395,9 +416,11 @@ typedef struct mb_energy_args {
                               * shared-memory cell list inside the kernel.  The caller passes the interaction range of its
                               * parameters (all terms have compact support).  MB_ECAPACITY if the frame-resident kernel
                               * does not apply (3 banks, position gradients requested, frame too large for shared memory) */
-  void* workspace;           /* optional scratch of mythos_b200_energy_workspace_bytes(): lets explicit pair lists run through
-                              * the phase-queued list kernels (per-nucleotide records, backbone-site gradient buffer, short-range list);
-                              * NULL or too small = the one-thread-per-pair kernels                                        */
+  void* workspace;           /* scratch of mythos_b200_energy_workspace_bytes(): lets explicit pair lists run through the
+                              * phase-queued list kernels (per-nucleotide records, backbone-site gradient buffer, short-range list;
+                              * NULL or too small = the one-thread-per-pair kernels) and holds the frame-resident kernel's
+                              * parameter-gradient images (REQUIRED when d_params is requested on that route: MB_ECAPACITY
+                              * otherwise).  Needs no initialisation.                                                         */
   size_t workspace_bytes;
   const int32_t* pair_split; /* MB_FLAG_TAGGED_PAIRS with the list kernels: (F) entries of each list before this index are
                               * the short-range pairs, the rest (up to pair_count) the Debye pairs; else NULL              */
@@ -405,6 +428,7 @@ typedef struct mb_energy_args {
                               * On the frame-resident route they are an epilogue of the SAME kernel (the frame is already in
                               * shared memory); on the other routes the standalone kernel is enqueued behind the energy kernels */
   void* observables_out;     /* out (F, MB_N_OBS) when `observables` is set */
+  const mb_pseq* pseq;       /* optional: probabilistic sequence weights for stacking and hydrogen bonding */
 } mb_energy_args;
 #define MB_FLAG_ACCUMULATE 0x1u /* add into the outputs instead of zeroing them first */
 #define MB_FLAG_GENERIC_KERNEL 0x2u /* force the one-thread-per-pair kernels even where the frame-resident kernel applies */

@@ -105,7 +105,13 @@ class EnergyArgs(C.Structure):
         ("pair_split", C.c_void_p),
         ("observables", C.c_void_p),
         ("observables_out", C.c_void_p),
+        ("pseq", C.c_void_p),
     ]
+
+
+class Pseq(C.Structure):
+    _fields_ = [("pmarg", C.c_void_p), ("bp_of", C.c_void_p), ("within", C.c_void_p), ("same_w_stack", C.c_void_p),
+                ("same_w_hb", C.c_void_p), ("d_pmarg", C.c_void_p), ("d_same_w_stack", C.c_void_p), ("d_same_w_hb", C.c_void_p)]
 
 
 class ObservableSpec(C.Structure):

@@ -17,6 +17,72 @@ struct ObsDev {
 };
 int check_observable_spec(const mb_observable_spec* spec, ObsDev* o);
 
+// Probabilistic sequences (mythos/energy/utils.py:45-132): the sequence weight of a pair is the expectation of the 4x4
+// table under the pair's nucleotide distribution.  Nucleotides are independent except the two members of one base pair:
+//   different base pairs / unpaired:   w = sum_ab pmarg[i][a] W[a][b] pmarg[j][b]      (pmarg = per-nucleotide marginals)
+//   same base pair:                    w = same_w[bp][within_i]  (= sum_t p_bp[t] W[BP[t][within_i]][BP[t][within_j]],
+//                                          evaluated on the host where it chains to the table and to the base-pair distribution)
+template <class T>
+struct PseqDev {
+  const T* pmarg;          // (N,4) or nullptr = discrete sequence
+  const int32_t* bp_of;    // (N) base-pair index or -1
+  const int32_t* within;   // (N) 0 / 1: which member of its base pair
+  const T* same_w_stack;   // (n_bp,2) stacking table expectation of a same-base-pair pair, by within_i
+  const T* same_w_hb;      // (n_bp,2) hydrogen-bond table
+  T* d_pmarg;              // out (N,4) gradient of sum_f sum_t cot E, or nullptr
+  T* d_same_w_stack;       // out (n_bp,2)
+  T* d_same_w_hb;          // out (n_bp,2)
+};
+// weight of pair (i,j) for table W (16 reals); `same` <- flat index into the (n_bp,2) same-pair tables or -1
+template <class T>
+__device__ __forceinline__ T pseq_weight(const PseqDev<T>& ps, const T* W, const T* same_w, int i, int j, int& same) {
+  same = -1;
+  const int bi = ps.bp_of[i];
+  if (bi >= 0 && bi == ps.bp_of[j]) {
+    same = 2 * bi + ps.within[i];
+    return same_w[same];
+  }
+  T w = T(0);
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    T row = T(0);
+#pragma unroll
+    for (int y = 0; y < 4; ++y) row += W[4 * x + y] * ps.pmarg[4 * j + y];
+    w += ps.pmarg[4 * i + x] * row;
+  }
+  return w;
+}
+// gradient of coef * w(i,j) with respect to the table (-> acc), the marginals and the same-pair table (-> atomics)
+template <class T, bool WP, class Acc>
+__device__ __forceinline__ void pseq_weight_grad(const PseqDev<T>& ps, const T* W, T* d_same_w, int w00, int i, int j, int same, T coef,
+                                                 Acc& acc) {
+  // (no early exit: acc.add is warp-convergent, every lane must reach it -- a same-pair lane contributes zeros there)
+  if (same >= 0) {
+    if (d_same_w && coef != T(0)) atomicAdd(&d_same_w[same], coef);
+    coef = T(0);
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    T gi = T(0);
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const T pj = ps.pmarg[4 * j + y];
+      gi += W[4 * x + y] * pj;
+      if (WP) acc.add(0, w00 + 4 * x + y, coef * ps.pmarg[4 * i + x] * pj);
+    }
+    if (ps.d_pmarg && coef != T(0)) atomicAdd(&ps.d_pmarg[4 * i + x], coef * gi);
+  }
+  if (ps.d_pmarg && coef != T(0)) {
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      T gj = T(0);
+#pragma unroll
+      for (int x = 0; x < 4; ++x) gj += ps.pmarg[4 * i + x] * W[4 * x + y];
+      atomicAdd(&ps.d_pmarg[4 * j + y], coef * gj);
+    }
+  }
+}
+
 template <class T>
 struct EnergyDev {
   ModelT<T> M;
@@ -47,6 +113,8 @@ struct EnergyDev {
   long long sr_capacity;
   int tagged;  // `pairs` carries support tags (MB_NL_TAG_SUPPORTS)
   const int32_t* pair_split;  // tagged lists: (F) entries before it are short-range pairs, after it Debye pairs (list kernels)
+  PseqDev<T> pseq;            // probabilistic sequence weights (generic pair kernel only); pmarg == nullptr: discrete seq
+  T* acc_scratch;             // frame-resident kernel: [resident CTAs][MB_P_COUNT][32] parameter-gradient images (workspace)
   ObsDev obs;                 // fused observables epilogue of the frame-resident kernel (obs_out != nullptr)
   T* obs_out;                 // (F, MB_N_OBS) or nullptr
 };
@@ -73,6 +141,20 @@ struct SmemAcc {
   }
 };
 
+
+// Parameter-gradient accumulator in GLOBAL memory, one slot per (parameter, lane) of this CTA's scratch image: every lane
+// adds its own contribution with a fire-and-forget RED.ADD (no warp reduction, no shuffles, no dependent chain); the 32
+// lane slots of a parameter are summed once per frame.  The image is L2-resident (232 x 32 reals per resident CTA).
+template <class T>
+struct GlobAcc {
+  T* img;  // [MB_P_COUNT][32]
+  __device__ __forceinline__ void add(int, int idx, T v) {
+    if (v != T(0)) atomicAdd(img + idx * 32 + (threadIdx.x & 31), v);
+  }
+  __device__ __forceinline__ void add_scatter(int, int idx, T v, bool pred) {
+    if (pred && v != T(0)) atomicAdd(img + idx * 32 + (threadIdx.x & 31), v);
+  }
+};
 
 // Parameter-gradient accumulator held in registers: a run of COUNT parameters starting at BASE (single bank)
 template <class T, int BASE, int COUNT>
@@ -172,6 +254,7 @@ template <class T>
 bool frame_kernel_fits(int n, bool want_params);
 template <class T>
 int launch_frame_kernel(cudaStream_t s, const EnergyDev<T>& a, bool want_params);
+size_t frame_scratch_bytes(int real_bytes);  // workspace the frame-resident kernel needs for its parameter-gradient images
 // unbonded terms of explicit pair lists of any size, phase-queued (list_kernels.cu)
 template <class T>
 int launch_list_kernel(cudaStream_t s, const EnergyDev<T>& a, void* workspace, bool want_forces, bool want_params);

@@ -76,11 +76,25 @@ __device__ __forceinline__ void pairs_body(const EnergyDev<T>& a, long long k, u
   if (BONDED) {
     const int32_t* snt = a.nt_type_stack ? a.nt_type_stack : a.nt_type;
     const int si = snt ? snt[i] : 1, sj = snt ? snt[j] : 1;
-    bonded_pair<T, WF, WP>(a.M, sP, valid, ni, nj, a.seq[i], a.seq[j], nti, ntj, si, sj, mask, cot, e, Gi, Gj, acc);
+    const bool ps = a.pseq.pmarg != nullptr && (mask & (1u << MB_TERM_STACK));
+    int same = -1;
+    const T wx = (ps && valid) ? pseq_weight(a.pseq, sP + MB_P_STACK_W00, a.pseq.same_w_stack, i, j, same) : T(0);
+    bonded_pair<T, WF, WP>(a.M, sP, valid, ni, nj, a.seq[i], a.seq[j], nti, ntj, si, sj, mask, cot, e, Gi, Gj, acc, ps, wx);
+    if (ps) {  // (warp-uniform branch: acc.add is warp-convergent; invalid / zero pairs contribute coef = 0)
+      const T coef = (valid && wx != T(0)) ? cot[MB_TERM_STACK] * e[MB_TERM_STACK] / wx : T(0);
+      pseq_weight_grad<T, WP>(a.pseq, sP + MB_P_STACK_W00, a.pseq.d_same_w_stack, MB_P_STACK_W00, i, j, same, coef, acc);
+    }
   } else {
     T m = T(1);
     if (a.M.half_charged_ends && a.is_end) m = (a.is_end[i] ? T(0.5) : T(1)) * (a.is_end[j] ? T(0.5) : T(1));
-    unbonded_pair<T, WF, WP>(a.M, sP, valid, ni, nj, a.seq[i], a.seq[j], nti, ntj, m, mask, cot, e, Gi, Gj, acc);
+    const bool ps = a.pseq.pmarg != nullptr && (mask & (1u << MB_TERM_HB));
+    int same = -1;
+    const T wx = (ps && valid) ? pseq_weight(a.pseq, sP + MB_P_HB_W00, a.pseq.same_w_hb, i, j, same) : T(0);
+    unbonded_pair<T, WF, WP>(a.M, sP, valid, ni, nj, a.seq[i], a.seq[j], nti, ntj, m, mask, cot, e, Gi, Gj, acc, ps, wx);
+    if (ps) {
+      const T coef = (valid && wx != T(0)) ? cot[MB_TERM_HB] * e[MB_TERM_HB] / wx : T(0);
+      pseq_weight_grad<T, WP>(a.pseq, sP + MB_P_HB_W00, a.pseq.d_same_w_hb, MB_P_HB_W00, i, j, same, coef, acc);
+    }
   }
   if (WF && valid) {
     scatter_nuc_grad(a, fbase + i, Gi, qi);
@@ -212,6 +226,23 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
   a.tagged = (x->flags & MB_FLAG_TAGGED_PAIRS) ? 1 : 0;
   a.pair_split = x->pair_split;
   a.obs_out = nullptr;
+  a.acc_scratch = nullptr;
+  a.pseq = PseqDev<T>{};
+  if (x->pseq) {
+    const mb_pseq& q = *x->pseq;
+    MB_REQUIRE(m.n_banks == 1, MB_EINVAL_MODEL, "energy: probabilistic sequences are supported for single-bank models");
+    MB_REQUIRE(q.pmarg && q.bp_of && q.within, MB_EINVAL_SHAPE, "energy: pseq needs pmarg, bp_of and within");
+    MB_REQUIRE((x->flags & MB_FLAG_GENERIC_KERNEL) && x->all_pairs_cutoff == 0, MB_EINVAL_SHAPE,
+               "energy: probabilistic sequences run through the generic pair kernel (set MB_FLAG_GENERIC_KERNEL, explicit pair list)");
+    a.pseq.pmarg = static_cast<const T*>(q.pmarg);
+    a.pseq.bp_of = q.bp_of;
+    a.pseq.within = q.within;
+    a.pseq.same_w_stack = static_cast<const T*>(q.same_w_stack);
+    a.pseq.same_w_hb = static_cast<const T*>(q.same_w_hb);
+    a.pseq.d_pmarg = static_cast<T*>(q.d_pmarg);
+    a.pseq.d_same_w_stack = static_cast<T*>(q.d_same_w_stack);
+    a.pseq.d_same_w_hb = static_cast<T*>(q.d_same_w_hb);
+  }
   ObsDev obs{};
   T* obs_out = nullptr;
   if (x->observables) {
@@ -238,6 +269,12 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
   if (!wf && !(x->flags & MB_FLAG_GENERIC_KERNEL) && frame_kernel_eligible<T>(a)) {
     a.obs = obs;
     a.obs_out = obs_out;  // epilogue of the same kernel: the frame is already in shared memory
+    a.acc_scratch = nullptr;
+    if (wp) {
+      MB_REQUIRE(x->workspace && x->workspace_bytes >= frame_scratch_bytes(sizeof(T)), MB_ECAPACITY,
+                 "energy: dE/dparams through the frame-resident kernel needs a workspace of mythos_b200_energy_workspace_bytes() bytes");
+      a.acc_scratch = static_cast<T*>(x->workspace);
+    }
     return launch_frame_kernel<T>(s, a, wp);
   }
   if (obs_out) {  // every other route: the standalone kernel, enqueued on the same stream
@@ -379,9 +416,13 @@ extern "C" int mythos_b200_frame_kernel_fits(int32_t n, int32_t real_bytes, int3
   return (real_bytes == 4 ? mb::frame_kernel_fits<float>(n, want_params != 0) : mb::frame_kernel_fits<double>(n, want_params != 0)) ? 1 : 0;
 }
 extern "C" size_t mythos_b200_energy_workspace_bytes(int32_t n, int32_t n_frames, int64_t pair_capacity, int32_t real_bytes) {
-  if (n <= 0 || n_frames <= 0 || pair_capacity <= 0) return 0;
-  return real_bytes == 4 ? mb::list_workspace_bytes<float>(n, n_frames, pair_capacity)
-                         : mb::list_workspace_bytes<double>(n, n_frames, pair_capacity);
+  if (n <= 0 || n_frames <= 0) return 0;
+  // the larger of: the list kernels' scratch (explicit lists) and the frame-resident kernel's parameter-gradient images
+  const size_t frame_ws = mb::frame_scratch_bytes(real_bytes == 4 ? 4 : 8);
+  if (pair_capacity <= 0) return frame_ws;
+  const size_t list_ws = real_bytes == 4 ? mb::list_workspace_bytes<float>(n, n_frames, pair_capacity)
+                                         : mb::list_workspace_bytes<double>(n, n_frames, pair_capacity);
+  return list_ws > frame_ws ? list_ws : frame_ws;
 }
 extern "C" int mythos_b200_energy_f64(void* stream, const mb_energy_args* a) {
   return mb::energy_impl<double>(static_cast<cudaStream_t>(stream), a);

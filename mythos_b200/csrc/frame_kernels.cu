@@ -31,6 +31,10 @@
 
 namespace mb {
 
+#ifndef MB_FRAME_GLOBACC
+#define MB_FRAME_GLOBACC 0  // parameter gradients: lane-private RED.ADD into an L2-resident image (1) or warp reductions + shared atomics (0)
+#endif
+constexpr int kMaxResidentCtas = 148 * 4;  // scratch images are sized for this many persistent CTAs
 #ifndef MB_FRAME_THREADS
 #define MB_FRAME_THREADS 512
 #endif
@@ -320,25 +324,37 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   long long prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_last = clock64();
   int prof_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
-  const int frame = blockIdx.x;
   const int n = a.n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long fbase = (long long)frame * n;
-  for (int k = threadIdx.x; k < 3 * n; k += kFB) sC[k] = a.center[3 * fbase + k];
-  for (int k = threadIdx.x; k < 4 * n; k += kFB) sQ[k] = a.quat[4 * fbase + k];
+  // frame-independent staging: parameters, sequence / end flags, angular windows
   for (int k = threadIdx.x; k < MB_P_COUNT; k += kFB) sP[k] = a.params[k];
-  if (WP)
-    for (int k = threadIdx.x; k < MB_P_COUNT * L.acc_rows; k += kFB) sAcc[k] = T(0);
   for (int k = threadIdx.x; k < n; k += kFB)
     sF[k] = (unsigned char)((a.seq[k] & 3) | ((a.is_end && a.is_end[k]) ? 4 : 0));
-  if (threadIdx.x < 8) ctr[threadIdx.x] = 0;
+#if MB_FRAME_GLOBACC
+  // this CTA's parameter-gradient image in the workspace: zeroed here, left zeroed by every frame's flush
+  T* const gimg = WP ? a.acc_scratch + (size_t)blockIdx.x * MB_P_COUNT * 32 : nullptr;
+  if (WP)
+    for (int k = threadIdx.x; k < MB_P_COUNT * 32; k += kFB) gimg[k] = T(0);
+  GlobAcc<T> pacc{gimg};
+#endif
   __syncthreads();
-  if (threadIdx.x == 0) bp_windows(sP, sWin);  // visible after the next barrier (bonded phase / cell build / loop top)
-
+  if (threadIdx.x == 0) bp_windows(sP, sWin);  // visible after the next barrier
   const ModelT<T>& M = a.M;
   const Geom<T>& g = M.geom[0];
   const mb_bank_forms F = M.forms[0];
   const unsigned mask = a.mask;
+
+  // persistent CTA: frames blockIdx.x, blockIdx.x + gridDim.x, ...
+  for (int frame = blockIdx.x; frame < a.n_frames; frame += gridDim.x) {
+  __syncthreads();  // the previous frame is finished with shared memory
+  const long long fbase = (long long)frame * n;
+  for (int k = threadIdx.x; k < 3 * n; k += kFB) sC[k] = a.center[3 * fbase + k];
+  for (int k = threadIdx.x; k < 4 * n; k += kFB) sQ[k] = a.quat[4 * fbase + k];
+  if (WP)
+    for (int k = threadIdx.x; k < MB_P_COUNT * L.acc_rows; k += kFB) sAcc[k] = T(0);
+  if (threadIdx.x < 8) ctr[threadIdx.x] = 0;
+  __syncthreads();
+
   if (CACHE_BACK) {
     for (int i = threadIdx.x; i < n; i += kFB) {
       const Nuc<T> ni = smem_nuc(sC, sQ, i);
@@ -354,7 +370,12 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   T e[MB_N_TERMS];
 #pragma unroll
   for (int t = 0; t < MB_N_TERMS; ++t) e[t] = T(0);
+  // warp-reduced shared-memory image: the bonded phase (a burst of ~60 parameters x 4 batches from every thread at once
+  // throttles the load/store unit when it goes out as RED.ADDs: measured) -- and every phase when MB_FRAME_GLOBACC is 0
   SmemAcc<T> sacc{sAcc + ((warp * L.acc_rows) / kFWarps) * MB_P_COUNT, false};  // this warp's copy of the image
+#if !MB_FRAME_GLOBACC
+  SmemAcc<T>& pacc = sacc;
+#endif
   NullAcc nacc;
   NucGrad<T> G0, G1;  // unused (WF = false) but required by the pair drivers' signatures
 
@@ -638,13 +659,13 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         const int tab = (sF[i] & 3) * 4 + (sF[j] & 3);
         if (mask & (1u << MB_TERM_HB)) {
           if (WP)
-            e[MB_TERM_HB] += hb_term<T, false, true>(sP, 0, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, tab, cot[MB_TERM_HB], HG, sacc);
+            e[MB_TERM_HB] += hb_term<T, false, true>(sP, 0, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, tab, cot[MB_TERM_HB], HG, pacc);
           else
             e[MB_TERM_HB] += hb_term<T, false, false>(sP, 0, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, tab, cot[MB_TERM_HB], HG, nacc);
         }
         if (mask & (1u << MB_TERM_CROSS)) {
           if (WP)
-            e[MB_TERM_CROSS] += cross_term<T, false, true>(sP, 0, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, cot[MB_TERM_CROSS], HG, sacc);
+            e[MB_TERM_CROSS] += cross_term<T, false, true>(sP, 0, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, cot[MB_TERM_CROSS], HG, pacc);
           else
             e[MB_TERM_CROSS] += cross_term<T, false, false>(sP, 0, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, cot[MB_TERM_CROSS], HG, nacc);
         }
@@ -667,7 +688,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         const V3<T> db = disp(site(nj, g.back[0], g.back[1], g.back[2]), site(ni, g.back[0], g.back[1], g.back[2]), M.box);
         CoaxGrad<T> CG;
         if (WP)
-          e[MB_TERM_COAX] += coax_term<T, false, true>(sP, 0, F.coax_form, in, ds, rs, db, ni.a1, nj.a1, ni.a3, nj.a3, cot[MB_TERM_COAX], CG, sacc);
+          e[MB_TERM_COAX] += coax_term<T, false, true>(sP, 0, F.coax_form, in, ds, rs, db, ni.a1, nj.a1, ni.a3, nj.a3, cot[MB_TERM_COAX], CG, pacc);
         else
           e[MB_TERM_COAX] += coax_term<T, false, false>(sP, 0, F.coax_form, in, ds, rs, db, ni.a1, nj.a1, ni.a3, nj.a3, cot[MB_TERM_COAX], CG, nacc);
         if (threadIdx.x == 0) ctr[2] = n_cx - cnt;
@@ -920,6 +941,9 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
     if (lane == 0) sE[warp * MB_N_TERMS + t] = v;
   }
+#if MB_FRAME_GLOBACC
+  if (WP) __threadfence();  // this thread's RED.ADDs are performed before the barrier releases the readers below
+#endif
   __syncthreads();
   const bool poisoned = cells && ctr[5] != 0;
   if (threadIdx.x < MB_N_TERMS && a.terms) {
@@ -930,11 +954,24 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   }
   if (WP) {
     T* out = a.d_params + (long long)frame * a.d_params_frame_stride;
+#if MB_FRAME_GLOBACC
+    // one warp per parameter: sum its 32 lane slots (fixed tree), add to the frame's row, leave the image zeroed
+    for (int p = warp; p < MB_P_COUNT; p += kFWarps) {
+      T v = __ldcg(gimg + p * 32 + lane);
+      const bool any = __any_sync(kFull, v != T(0));
+      if (any) gimg[p * 32 + lane] = T(0);
+      if (lane < L.acc_rows) v += sAcc[lane * MB_P_COUNT + p];  // the shared-memory image (bonded phase, register accumulators)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+      if (lane == 0 && v != T(0)) atomicAdd(&out[p], v);
+    }
+#else
     for (int p = threadIdx.x; p < MB_P_COUNT; p += kFB) {
       T v = T(0);
       for (int r = 0; r < L.acc_rows; ++r) v += sAcc[r * MB_P_COUNT + p];
       if (v != T(0)) atomicAdd(&out[p], v);
     }
+#endif
   }
   // ---------------------------------------------------------------- fused observables
   // propeller twist / rise / pitch angle / diameter of this frame from the nucleotides already staged in shared memory
@@ -945,6 +982,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
                               M.box[1], M.box[2], g.back[0], g.back[1], g.back[2], g.base, sC, sQ, sE,
                               a.obs_out + (long long)frame * MB_N_OBS);
   }
+  }  // persistent loop over frames
 }
 
 template <class T>
@@ -972,10 +1010,24 @@ bool frame_kernel_eligible(const EnergyDev<T>& a) {
   return pick_layout(a, true, &cb, &L);
 }
 
+size_t frame_scratch_bytes(int real_bytes) {
+  return MB_FRAME_GLOBACC ? (size_t)kMaxResidentCtas * MB_P_COUNT * 32 * (size_t)real_bytes : 0;
+}
+
 template <class T, bool WP, bool CB, bool CELLS>
 static int launch_two(cudaStream_t s, const EnergyDev<T>& a, const FrameSmem& L) {
   MB_CUDA_CHECK(cudaFuncSetAttribute(k_frame_energy<T, WP, CB, CELLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-  k_frame_energy<T, WP, CB, CELLS><<<a.n_frames, kFB, L.total, s>>>(a, L);
+  // persistent CTAs: as many as are resident at once (one per SM at the DiffTRe size), each walks frames b, b + grid, ...
+  int dev = 0, n_sm = 0, per_sm = 0;
+  MB_CUDA_CHECK(cudaGetDevice(&dev));
+  MB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  MB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame_energy<T, WP, CB, CELLS>, kFB, L.total));
+  long long grid = (long long)n_sm * (per_sm > 0 ? per_sm : 1);
+  if (grid > kMaxResidentCtas) grid = kMaxResidentCtas;
+  if (grid > a.n_frames) grid = a.n_frames;
+  MB_REQUIRE(!(WP && MB_FRAME_GLOBACC) || a.acc_scratch, MB_ECAPACITY,
+             "frame kernel: parameter gradients need the workspace of mythos_b200_energy_workspace_bytes()");
+  k_frame_energy<T, WP, CB, CELLS><<<(unsigned)grid, kFB, L.total, s>>>(a, L);
   MB_CUDA_CHECK(cudaGetLastError());
   return MB_OK;
 }

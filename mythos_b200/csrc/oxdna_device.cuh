@@ -530,7 +530,9 @@ struct StackGrad {
 template <class T, bool WF, bool WP, class Acc>
 MB_HD T stack_term(const T* P, int bank, int form, bool act, const V3<T>& ds, const V3<T>& db, const V3<T>& a3i,
                    const V3<T>& a3j, const V3<T>& a2i, const V3<T>& a2j, const V3<T>& p3j, const V3<T>& p5i,
-                   int tab, T cot, StackGrad<T>& G, Acc& acc) {
+                   int tab, T cot, StackGrad<T>& G, Acc& acc, bool has_w_ext = false, T w_ext = T(0)) {
+  // `has_w_ext`: the pair's sequence weight comes from outside (probabilistic sequences: an expectation over the table,
+  // mythos/energy/utils.py:45-132) instead of the table entry `tab`; the table gradient is then the caller's business
   // factor slots: 0 f1(r)  1 f4(th4)|f4(th9)  2 f4(th5)  3 f4(th6)  4 f4(th10) (RNA only)  5 f5(phi1)  6 f5(phi2)
   T e = 0;
   T f[7], df[7], arg[7], dth[7];
@@ -545,7 +547,7 @@ MB_HD T stack_term(const T* P, int bank, int form, bool act, const V3<T>& ds, co
     df[k] = dth[k] = arg[k] = T(0);
   }
   if (act) {
-    w = P[MB_P_STACK_W00 + tab];
+    w = has_w_ext ? w_ext : P[MB_P_STACK_W00 + tab];
     rs = sqrt(dot(ds, ds));
     f[0] = f1_val(rs, P + MB_P_STACK_RLOW, df[0]);
     arg[0] = rs;
@@ -648,7 +650,7 @@ MB_HD T stack_term(const T* P, int bank, int form, bool act, const V3<T>& ds, co
     f4_par_flush(g, bank, b4[4], acc);
     f5_par(arg[5], P + MB_P_STACK_PHI1_XSTAR, oth[5], bank, MB_P_STACK_PHI1_XSTAR, acc);
     f5_par(arg[6], P + MB_P_STACK_PHI2_XSTAR, oth[6], bank, MB_P_STACK_PHI2_XSTAR, acc);
-    acc.add_scatter(bank, MB_P_STACK_W00 + tab, nz ? cot * e / w : T(0), nz);
+    if (!has_w_ext) acc.add_scatter(bank, MB_P_STACK_W00 + tab, nz ? cot * e / w : T(0), nz);
   }
   return e;
 }
@@ -699,7 +701,8 @@ MB_HD void hb_scatter(const T gx[6], const V3<T>& dh, T r, T gr, const V3<T>& a1
 
 template <class T, bool WF, bool WP, class Acc>
 MB_HD T hb_term(const T* P, int bank, bool act, T r, const V3<T>& dh, const V3<T>& a1i, const V3<T>& a1j,
-                const V3<T>& a3i, const V3<T>& a3j, HbAngles<T>& A, int tab, T cot, HbGrad<T>& G, Acc& acc) {
+                const V3<T>& a3i, const V3<T>& a3j, HbAngles<T>& A, int tab, T cot, HbGrad<T>& G, Acc& acc,
+                bool has_w_ext = false, T w_ext = T(0)) {
   const int b4[6] = {MB_P_HB_T1_TH0, MB_P_HB_T2_TH0, MB_P_HB_T3_TH0, MB_P_HB_T4_TH0, MB_P_HB_T7_TH0, MB_P_HB_T8_TH0};
   T e = 0, w = 0, fr = 0, dfr = 0;
   T f[6], df[6];
@@ -710,7 +713,7 @@ MB_HD T hb_term(const T* P, int bank, bool act, T r, const V3<T>& dh, const V3<T
     df[k] = T(0);
   }
   if (act) {
-    w = P[MB_P_HB_W00 + tab];
+    w = has_w_ext ? w_ext : P[MB_P_HB_W00 + tab];
     if (w != T(0)) {
       fr = f1_val(r, P + MB_P_HB_RLOW, dfr);
       if (fr != T(0)) {
@@ -758,7 +761,7 @@ MB_HD T hb_term(const T* P, int bank, bool act, T r, const V3<T>& dh, const V3<T
       if (nz) f4_par_add(A.th[k], P + b4[k], oth[k], g);
       f4_par_flush(g, bank, b4[k], acc);
     }
-    acc.add_scatter(bank, MB_P_HB_W00 + tab, nz ? cot * e / w : T(0), nz);
+    if (!has_w_ext) acc.add_scatter(bank, MB_P_HB_W00 + tab, nz ? cot * e / w : T(0), nz);
   }
   return e;
 }
@@ -1063,7 +1066,7 @@ struct ModelT {
 template <class T, bool WF, bool WP, class Acc>
 MB_HD void bonded_pair(const ModelT<T>& M, const T* Pall, bool valid, const Nuc<T>& ni, const Nuc<T>& nj, int seq_i,
                        int seq_j, int nt_i, int nt_j, int snt_i, int snt_j, unsigned mask, const T* cot, T e[MB_N_TERMS],
-                       NucGrad<T>& Gi, NucGrad<T>& Gj, Acc& acc) {
+                       NucGrad<T>& Gi, NucGrad<T>& Gj, Acc& acc, bool has_w_ext = false, T w_ext = T(0)) {
   // bank / flavour selection, mythos/energy/na1/fene.py:96, na1/stacking.py:201: RNA bank iff both RNA
   int bank = 0, fl = 0, sbank = 0, sfl = 0;
   if (M.n_banks > 1) {
@@ -1131,7 +1134,7 @@ MB_HD void bonded_pair(const ModelT<T>& M, const T* Pall, bool valid, const Nuc<
     StackGrad<T> G;
     G.ds = G.db = G.a3i = G.a3j = G.a2i = G.a2j = G.p3j = G.p5i = v3<T>(0, 0, 0);
     e[MB_TERM_STACK] += stack_term<T, WF, WP>(SP, sbank, form, valid, ds, db, ni.a3, nj.a3, ni.a2, nj.a2, p3j, p5i,
-                                              seq_i * 4 + seq_j, cot[MB_TERM_STACK], G, acc);
+                                              seq_i * 4 + seq_j, cot[MB_TERM_STACK], G, acc, has_w_ext, w_ext);
     if (WF && valid) {
       site_grad(Gi, T(1), G.ds, si1, si2, T(0));
       site_grad(Gj, T(-1), G.ds, sj1, sj2, T(0));
@@ -1156,7 +1159,7 @@ MB_HD void bonded_pair(const ModelT<T>& M, const T* Pall, bool valid, const Nuc<
 template <class T, bool WF, bool WP, class Acc>
 MB_HD void unbonded_pair(const ModelT<T>& M, const T* Pall, bool valid, const Nuc<T>& ni, const Nuc<T>& nj, int seq_i,
                          int seq_j, int nt_i, int nt_j, T end_mult, unsigned mask, const T* cot, T e[MB_N_TERMS],
-                         NucGrad<T>& Gi, NucGrad<T>& Gj, Acc& acc) {
+                         NucGrad<T>& Gi, NucGrad<T>& Gj, Acc& acc, bool has_w_ext = false, T w_ext = T(0)) {
   // bank / flavour selection, mythos/energy/na1/hydrogen_bonding.py:325-359 (same in every unbonded term)
   int bank = 0, fi = 0, fj = 0;
   if (M.n_banks > 1) {
@@ -1225,7 +1228,7 @@ MB_HD void unbonded_pair(const ModelT<T>& M, const T* Pall, bool valid, const Nu
     G.d = G.a1i = G.a1j = G.a3i = G.a3j = v3<T>(0, 0, 0);
     if (mask & (1u << MB_TERM_HB))
       e[MB_TERM_HB] += hb_term<T, WF, WP>(P, bank, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, seq_i * 4 + seq_j,
-                                          cot[MB_TERM_HB], G, acc);
+                                          cot[MB_TERM_HB], G, acc, has_w_ext, w_ext);
     if (mask & (1u << MB_TERM_CROSS))
       e[MB_TERM_CROSS] += cross_term<T, WF, WP>(P, bank, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A,
                                                 cot[MB_TERM_CROSS], G, acc);

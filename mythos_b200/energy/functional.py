@@ -135,11 +135,12 @@ def _launch(
         obs_spec = observables[0].struct()
         a.observables = C.addressof(obs_spec)
         a.observables_out = observables[1].data_ptr()
-    if cap and (cap * F >= 65536 or (flags & (_lib.FLAG_LIST_KERNEL | _lib.FLAG_TAGGED_PAIRS))) and not (flags & _lib.FLAG_GENERIC_KERNEL):
-        # scratch of the phase-queued list kernel (caller-owned, as everywhere in the C-ABI); the caching allocator
-        # makes this a pointer bump, and it is graph-capture safe
+    frame_ws = want_param_grad and not want_pos_grad and model.n_banks == 1  # the frame-resident kernel may take this call
+    if ((cap and (cap * F >= 65536 or (flags & (_lib.FLAG_LIST_KERNEL | _lib.FLAG_TAGGED_PAIRS)))) or frame_ws) and not (flags & _lib.FLAG_GENERIC_KERNEL):
+        # scratch of the phase-queued list kernel / parameter-gradient images of the frame-resident kernel (caller-owned,
+        # as everywhere in the C-ABI); the caching allocator makes this a pointer bump, and it is graph-capture safe
         need = int(_lib.lib().mythos_b200_energy_workspace_bytes(N, F, cap, 8 if dtype == torch.float64 else 4))
-        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
         a.workspace, a.workspace_bytes = ws.data_ptr(), need
     fn = getattr(_lib.lib(), f"mythos_b200_energy_{sfx}")
     with torch.cuda.device(dev):
