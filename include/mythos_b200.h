@@ -384,6 +384,8 @@ typedef struct mb_pseq {
   void* d_pmarg;              /* out (N,4) or NULL */
   void* d_same_w_stack;       /* out (n_bp,2) or NULL */
   void* d_same_w_hb;          /* out (n_bp,2) or NULL */
+  uint32_t terms;             /* which terms take their weight from the distribution: bits MB_TERM_STACK, MB_TERM_HB */
+  uint32_t _pad;
 } mb_pseq;
 
 typedef struct mb_energy_args {

@@ -111,7 +111,8 @@ class EnergyArgs(C.Structure):
 
 class Pseq(C.Structure):
     _fields_ = [("pmarg", C.c_void_p), ("bp_of", C.c_void_p), ("within", C.c_void_p), ("same_w_stack", C.c_void_p),
-                ("same_w_hb", C.c_void_p), ("d_pmarg", C.c_void_p), ("d_same_w_stack", C.c_void_p), ("d_same_w_hb", C.c_void_p)]
+                ("same_w_hb", C.c_void_p), ("d_pmarg", C.c_void_p), ("d_same_w_stack", C.c_void_p), ("d_same_w_hb", C.c_void_p),
+                ("terms", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class ObservableSpec(C.Structure):

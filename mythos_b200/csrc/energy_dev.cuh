@@ -32,6 +32,7 @@ struct PseqDev {
   T* d_pmarg;              // out (N,4) gradient of sum_f sum_t cot E, or nullptr
   T* d_same_w_stack;       // out (n_bp,2)
   T* d_same_w_hb;          // out (n_bp,2)
+  unsigned terms;          // bits MB_TERM_STACK / MB_TERM_HB: which terms use the distribution
 };
 // weight of pair (i,j) for table W (16 reals); `same` <- flat index into the (n_bp,2) same-pair tables or -1
 template <class T>

@@ -76,7 +76,7 @@ __device__ __forceinline__ void pairs_body(const EnergyDev<T>& a, long long k, u
   if (BONDED) {
     const int32_t* snt = a.nt_type_stack ? a.nt_type_stack : a.nt_type;
     const int si = snt ? snt[i] : 1, sj = snt ? snt[j] : 1;
-    const bool ps = a.pseq.pmarg != nullptr && (mask & (1u << MB_TERM_STACK));
+    const bool ps = a.pseq.pmarg != nullptr && (mask & a.pseq.terms & (1u << MB_TERM_STACK));
     int same = -1;
     const T wx = (ps && valid) ? pseq_weight(a.pseq, sP + MB_P_STACK_W00, a.pseq.same_w_stack, i, j, same) : T(0);
     bonded_pair<T, WF, WP>(a.M, sP, valid, ni, nj, a.seq[i], a.seq[j], nti, ntj, si, sj, mask, cot, e, Gi, Gj, acc, ps, wx);
@@ -87,7 +87,7 @@ __device__ __forceinline__ void pairs_body(const EnergyDev<T>& a, long long k, u
   } else {
     T m = T(1);
     if (a.M.half_charged_ends && a.is_end) m = (a.is_end[i] ? T(0.5) : T(1)) * (a.is_end[j] ? T(0.5) : T(1));
-    const bool ps = a.pseq.pmarg != nullptr && (mask & (1u << MB_TERM_HB));
+    const bool ps = a.pseq.pmarg != nullptr && (mask & a.pseq.terms & (1u << MB_TERM_HB));
     int same = -1;
     const T wx = (ps && valid) ? pseq_weight(a.pseq, sP + MB_P_HB_W00, a.pseq.same_w_hb, i, j, same) : T(0);
     unbonded_pair<T, WF, WP>(a.M, sP, valid, ni, nj, a.seq[i], a.seq[j], nti, ntj, m, mask, cot, e, Gi, Gj, acc, ps, wx);
@@ -242,6 +242,8 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
     a.pseq.d_pmarg = static_cast<T*>(q.d_pmarg);
     a.pseq.d_same_w_stack = static_cast<T*>(q.d_same_w_stack);
     a.pseq.d_same_w_hb = static_cast<T*>(q.d_same_w_hb);
+    a.pseq.terms = q.terms;
+    MB_REQUIRE(!(q.terms & (1u << MB_TERM_STACK)) || q.same_w_stack || true, MB_EINVAL_SHAPE, "energy: pseq stacking table missing");
   }
   ObsDev obs{};
   T* obs_out = nullptr;

@@ -167,13 +167,6 @@ class Stacking(je_base.BaseEnergyFunction):
     TERM = TERM_STACK
     FORM = {"stack_form": 0, "use_back_stack": 0}
 
-    def __post_init__(self, topology) -> None:
-        super().__post_init__(topology)
-        if self.params.pseq is not None:
-            raise NotImplementedError(
-                "probabilistic sequences (pseq) are not on the CUDA path yet (SURVEY 8f rank 2); use a discrete seq"
-            )
-
 
 # ------------------------------------------------------------------------------------------------ hydrogen bonding
 _HB_F4_REQ, _HB_F4_DEP = _f4_fields("hb", "123478")
@@ -205,13 +198,6 @@ class HydrogenBonding(je_base.BaseEnergyFunction):
     """dna1/hydrogen_bonding.py:226-340: f1(r_hb) prod f4(th1,2,3,4,7,8) x eps_hb_weights[seq_i, seq_j]."""
 
     TERM = TERM_HB
-
-    def __post_init__(self, topology) -> None:
-        super().__post_init__(topology)
-        if self.params.pseq is not None:
-            raise NotImplementedError(
-                "probabilistic sequences (pseq) are not on the CUDA path yet (SURVEY 8f rank 2); use a discrete seq"
-            )
 
 
 # ------------------------------------------------------------------------------------------------ cross stacking

@@ -72,6 +72,7 @@ def _launch(
     out: tuple | None = None,
     pair_split: torch.Tensor | None = None,
     observables=None,
+    pseq=None,
 ):
     _lib.require_cuda(center, "center")
     F, N = center.shape[0], center.shape[1]
@@ -130,6 +131,12 @@ def _launch(
     a.d_params_frame_stride = stride
     ws = None
     a.pair_split = _lib.ptr(pair_split) if cap else None
+    pseq_struct = None
+    if pseq is not None:  # PseqInputs: device tensors of the probabilistic-sequence weights (+ gradient buffers, accumulated into)
+        pseq_struct = pseq.struct(dtype)
+        a.pseq = C.addressof(pseq_struct)
+        flags |= _lib.FLAG_GENERIC_KERNEL
+        a.flags = flags
     obs_spec = None
     if observables is not None:  # (ObservableRequest, out (F,4)): fused epilogue of the frame-resident kernel, else a launch behind it
         obs_spec = observables[0].struct()
@@ -559,11 +566,13 @@ def _chunks(n_frames: int, source, streamed: bool = False) -> list[slice]:
 
 
 def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, want_pos, want_par, per_frame_par, flags=0,
-         observables=None):
+         observables=None, pseq=None):
     """Chunked launch over frames; concatenates / sums the per-chunk outputs.  ``observables``: an ``ObservableRequest``
     whose ``out`` receives the (F,4) per-frame observables evaluated in the same pass."""
     if observables is not None:
         observables.out = torch.empty((center.shape[0], _lib.N_OBS), dtype=center.dtype, device=params.device)
+    if pseq is not None:
+        flags |= _lib.FLAG_GENERIC_KERNEL  # probabilistic sequence weights live in the generic pair kernel
     if isinstance(source, CellListPairs) and not want_pos and model.n_banks == 1 and source.in_kernel and not (flags & _lib.FLAG_GENERIC_KERNEL):
         # all-pairs mode inside the frame-resident kernel: the CTA finds its own pairs, no list in HBM
         try:
@@ -649,7 +658,7 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
                     _launch(model, topo, c_sl, q_sl, params, pairs, stride, term_mask,
                             None if cot is None else cot[sl], want_terms, want_pos, want_par, per_frame_par, count,
                             flags | (_lib.FLAG_TAGGED_PAIRS if tagged else 0), 0.0, None, split,
-                            observables=None if observables is None else (observables, observables.out[sl]))
+                            observables=None if observables is None else (observables, observables.out[sl]), pseq=pseq)
                 )
         except _lib.MythosB200Error as err:
             if not tagged or getattr(err, "status", None) != 3:  # MB_ECAPACITY: the frame-resident kernel does not apply
@@ -815,6 +824,77 @@ class _FrameEnergy(torch.autograd.Function):
             d_params = d_params.to(device=pdev, dtype=pdtype)
         return (d_center if ctx.needs_input_grad[0] else None, d_quat if ctx.needs_input_grad[1] else None, d_params,
                 None, None, None, None, None, None)
+
+
+@dc.dataclass
+class PseqInputs:
+    """Device-side inputs of the probabilistic-sequence weights (``mb_pseq``); ``grads=True`` adds zeroed gradient buffers."""
+
+    pmarg: torch.Tensor  # (N,4)
+    bp_of: torch.Tensor  # (N) int32
+    within: torch.Tensor  # (N) int32
+    same_w_stack: torch.Tensor  # (n_bp,2)
+    same_w_hb: torch.Tensor  # (n_bp,2)
+    terms: int
+    d_pmarg: torch.Tensor | None = None
+    d_same_w_stack: torch.Tensor | None = None
+    d_same_w_hb: torch.Tensor | None = None
+
+    def with_grads(self) -> "PseqInputs":
+        return dc.replace(self, d_pmarg=torch.zeros_like(self.pmarg), d_same_w_stack=torch.zeros_like(self.same_w_stack),
+                          d_same_w_hb=torch.zeros_like(self.same_w_hb))
+
+    def struct(self, dtype) -> _lib.Pseq:
+        for t in (self.pmarg, self.same_w_stack, self.same_w_hb):
+            if t.dtype != dtype or not t.is_contiguous():
+                raise _lib.MythosB200Error("pseq inputs must be contiguous and of the frames' dtype")
+        s = _lib.Pseq()
+        s.pmarg, s.bp_of, s.within = self.pmarg.data_ptr(), self.bp_of.data_ptr(), self.within.data_ptr()
+        s.same_w_stack = self.same_w_stack.data_ptr() if self.same_w_stack.numel() else None
+        s.same_w_hb = self.same_w_hb.data_ptr() if self.same_w_hb.numel() else None
+        s.d_pmarg = _lib.ptr(self.d_pmarg)
+        s.d_same_w_stack = self.d_same_w_stack.data_ptr() if self.d_same_w_stack is not None and self.d_same_w_stack.numel() else None
+        s.d_same_w_hb = self.d_same_w_hb.data_ptr() if self.d_same_w_hb is not None and self.d_same_w_hb.numel() else None
+        s.terms = self.terms
+        return s
+
+
+class _PseqTerms(torch.autograd.Function):
+    """Per-term energies with probabilistic sequence weights: (center, quat, params, pmarg, same_w_stack, same_w_hb) ->
+    (F,8); the backward is a second launch that also returns the gradients with respect to the three weight inputs."""
+
+    @staticmethod
+    def forward(ctx, center, quat, params, pmarg, same_s, same_h, model, topo, source, term_mask, bp_of, within, terms):
+        dev, dtype = center.device, center.dtype
+        ps = PseqInputs(pmarg.to(dev, dtype).contiguous(), bp_of, within, same_s.to(dev, dtype).contiguous(),
+                        same_h.to(dev, dtype).contiguous(), terms)
+        out, _, _, _ = _run(model, topo, center, quat, params, source, term_mask, None, True, False, False, False, pseq=ps)
+        ctx.save_for_backward(center, quat, params, pmarg, same_s, same_h)
+        ctx.static = (model, topo, source, term_mask, bp_of, within, terms)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_terms):
+        center, quat, params, pmarg, same_s, same_h = ctx.saved_tensors
+        model, topo, source, mask, bp_of, within, terms = ctx.static
+        dev, dtype = center.device, center.dtype
+        ps = PseqInputs(pmarg.to(dev, dtype).contiguous(), bp_of, within, same_s.to(dev, dtype).contiguous(),
+                        same_h.to(dev, dtype).contiguous(), terms).with_grads()
+        need_pos = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        _, d_center, d_quat, d_params = _run(model, topo, center, quat, params, source, mask, g_terms.contiguous(), False, need_pos,
+                                             True, False, pseq=ps)
+        back = lambda g, like: g.to(device=like.device, dtype=like.dtype)  # noqa: E731
+        return (d_center if ctx.needs_input_grad[0] else None, d_quat if ctx.needs_input_grad[1] else None,
+                back(d_params, params), back(ps.d_pmarg, pmarg), back(ps.d_same_w_stack, same_s), back(ps.d_same_w_hb, same_h),
+                None, None, None, None, None, None, None)
+
+
+def pseq_energy_terms(model, topo, center, quat, params, pairs, term_mask, pmarg, same_w_stack, same_w_hb, bp_of, within, terms):
+    """``energy_terms`` with probabilistic sequence weights (generic pair kernel)."""
+    if center.dim() != 3 or quat.dim() != 3:
+        raise _lib.MythosB200Error("center must be (F,N,3) and quat (F,N,4)")
+    return _PseqTerms.apply(center, quat, params, pmarg, same_w_stack, same_w_hb, model, topo, _source_of(pairs), term_mask,
+                            bp_of, within, terms)
 
 
 def _source_of(pairs) -> StaticPairs | CellListPairs:

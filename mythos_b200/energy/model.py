@@ -189,11 +189,49 @@ class Plan:
             return functional.CellListPairs(bonded=topo.bonded, box=box, r_cutoff=interaction_range(self), in_kernel=in_kernel, tag=tag)
         return functional.StaticPairs(device_pairs(ub, device))
 
+    def pseq_inputs(self, n: int, device):
+        """Probabilistic-sequence inputs of the stacking / hydrogen-bonding terms, or None for discrete sequences:
+        ``(pmarg (N,4), same_w_stack (n_bp,2), same_w_hb (n_bp,2), bp_of, within, term bits)`` -- the three real arrays
+        differentiable in ``pseq`` and in the terms' weight tables (``mythos_b200.energy.pseq``)."""
+        from mythos_b200.energy import pseq as kpseq
+
+        users = [fn for fn in self.fns if fn.TERM in (2, 4) and "pseq" in fn.params and fn.params.pseq is not None]
+        if not users:
+            return None
+        if self.hybrid:
+            raise NotImplementedError("probabilistic sequences with the hybrid (NA1) model are not on the CUDA path")
+        ps, sc = users[0].params.pseq, users[0].params.pseq_constraints
+        for fn in users[1:]:
+            same = fn.params.pseq_constraints is sc and all(a is b or torch.equal(torch.as_tensor(a), torch.as_tensor(b))
+                                                            for a, b in zip(fn.params.pseq, ps))
+            if not same:
+                raise NotImplementedError("stacking and hydrogen bonding must share one probabilistic sequence")
+        if sc is None or sc.n_nucleotides != n:
+            raise ValueError("pseq_constraints must be provided when pseq is provided." if sc is None else
+                             f"pseq_constraints describe {sc.n_nucleotides} nucleotides, the body has {n}")
+        pmarg = kpseq.marginals(ps, sc)
+        zero = torch.zeros((sc.n_bp, 2), dtype=torch.float64)
+        same_s = same_h = zero
+        terms = 0
+        for fn in users:
+            if fn.TERM == 2:
+                same_s, terms = kpseq.same_pair_weights(ps, fn.params.eps_stack, sc), terms | (1 << 2)
+            else:
+                same_h, terms = kpseq.same_pair_weights(ps, fn.params.eps_hb_weights, sc), terms | (1 << 4)
+        bp_of, within = kpseq.index_arrays(sc)
+        key = ("pseq_idx", id(sc), str(device))
+        bp_dev, within_dev = _cached(key, (sc,), lambda: (functional._as_i32(bp_of, device), functional._as_i32(within, device)))
+        return pmarg, same_s, same_h, bp_dev, within_dev, terms
+
     def evaluate(self, center: torch.Tensor, quat: torch.Tensor) -> torch.Tensor:
         """(F,8) per-term energies; differentiable in center, quat and the configurations' tensors."""
         _lib.require_cuda(center, "RigidBody.center")
         dev, dtype = center.device, center.dtype
         topo = self.topology(center.shape[1], dev)
+        pq = self.pseq_inputs(center.shape[1], dev)
+        if pq is not None:
+            return functional.pseq_energy_terms(self.model, topo, center, quat, self.device_params(dev, dtype), self.pairs(dev, topo),
+                                                self.term_mask, *pq)
         return functional.energy_terms(
             self.model, topo, center, quat, self.device_params(dev, dtype), self.pairs(dev, topo), self.term_mask
         )
@@ -211,6 +249,9 @@ class Plan:
             _lib.require_cuda(center, "RigidBody.center (or pinned host memory, which is streamed)")
         dtype = center.dtype
         topo = self.topology(center.shape[1], dev)
+        if self.pseq_inputs(center.shape[1], dev) is not None:  # probabilistic sequences: generic pair kernel, per-term route
+            _lib.require_cuda(center, "RigidBody.center")
+            return self.evaluate(center, quat) @ weights.to(device=dev, dtype=dtype)
         return functional.frame_energies(
             self.model, topo, center, quat, self.device_params(dev, dtype), self.pairs(dev, topo), weights, self.term_mask,
             observables,

@@ -400,6 +400,8 @@ def _build_entry(energy_fn, opt_params, names, shapes) -> _Entry:
     fns = getattr(energy_fn, "energy_fns", None)
     if not fns or len(kmodel.fusable_groups(fns)) != 1:
         return entry
+    if any("pseq" in fn.params and fn.params.pseq is not None for fn in fns) or any(k in ("pseq", "pseq_constraints") for k in names):
+        return entry  # probabilistic sequences chain through the configurations themselves (mythos_b200.energy.pseq)
     try:
         chain = _chain_fn(energy_fn, names, shapes)
         vec = _flatten(opt_params, names, shapes).detach().cpu()

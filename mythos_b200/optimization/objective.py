@@ -255,6 +255,9 @@ def compute_loss_and_grad(opt_params: dict[str, torch.Tensor], energy_fn, beta, 
     mapping name -> tensor, the autograd engine sees one leaf instead of a hundred."""
     from mythos_b200.energy import functional
 
+    if not all(isinstance(v, (int, float, torch.Tensor)) for v in opt_params.values()):
+        # parameter PYTREES (e.g. pseq = (unpaired (n_u,4), base-paired (n_bp,4)) for sequence design): one leaf per tensor
+        return _loss_and_grad_pytree(opt_params, energy_fn, beta, loss_fn, ref_states, ref_energies, observables)
     for attempt in range(functional.MAX_PASS_REPEATS + 1):
         if attempt == functional.MAX_PASS_REPEATS:
             raise _lib.MythosB200Error(f"pair lists still overflow after {attempt} passes over the reference states")
@@ -275,6 +278,28 @@ def compute_loss_and_grad(opt_params: dict[str, torch.Tensor], energy_fn, beta, 
         g = _combine_sharded_grads(g, leaves, loss_fn, ref_states, energy_fn, beta, ref_energies, observables, aux)
     grads = {k: v.to(torch.as_tensor(opt_params[k]).dtype) if torch.as_tensor(opt_params[k]).is_floating_point() else v
              for k, v in leaves.unflatten(g).items()}
+    return (loss.detach(), tuple(a.detach() if isinstance(a, torch.Tensor) else a for a in aux)), grads
+
+
+def _loss_and_grad_pytree(opt_params, energy_fn, beta, loss_fn, ref_states, ref_energies, observables):
+    """``compute_loss_and_grad`` for parameter values that are nested containers of tensors (single process)."""
+    from torch.utils import _pytree as pytree
+
+    from mythos_b200.energy import functional
+
+    if _world()[1] > 1:
+        raise NotImplementedError("pytree-valued parameters (pseq) with frame sharding")
+    flat, spec = pytree.tree_flatten(opt_params)
+    for attempt in range(functional.MAX_PASS_REPEATS + 1):
+        if attempt == functional.MAX_PASS_REPEATS:
+            raise _lib.MythosB200Error(f"pair lists still overflow after {attempt} passes over the reference states")
+        leaves = [torch.as_tensor(v, dtype=torch.float64).detach().clone().requires_grad_(True) for v in flat]
+        with functional.deferred_verification() as checks:
+            loss, aux = compute_loss(pytree.tree_unflatten(leaves, spec), energy_fn, beta, loss_fn, ref_states, ref_energies, observables)
+            gl = torch.autograd.grad(loss, leaves, allow_unused=True)
+        if all_ranks_ok(checks.ok()):
+            break
+    grads = pytree.tree_unflatten([torch.zeros_like(x) if g is None else g for x, g in zip(leaves, gl)], spec)
     return (loss.detach(), tuple(a.detach() if isinstance(a, torch.Tensor) else a for a in aux)), grads
 
 

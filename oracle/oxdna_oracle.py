@@ -907,3 +907,29 @@ def flatten_params(params: dict, prefix: str = "") -> dict:
         elif isinstance(v, torch.Tensor) and v.dtype == DT:
             out[prefix + k] = v
     return out
+
+
+# --------------------------------------------------------------------------- probabilistic sequences
+BP_IDXS = ((0, 3), (3, 0), (2, 1), (1, 2))  # mythos/utils/constants.py:13-18: AT, TA, GC, CG over "ACGT"
+
+
+def compute_seq_dep_weight(pseq, nt1, nt2, weights_table, is_unpaired, idx_to_unpaired_idx, idx_to_bp_idx):
+    """mythos/energy/utils.py:45-132, case by case as the reference writes it (explicit sums, no marginals)."""
+    up, bp = (torch.as_tensor(x, dtype=DT) for x in pseq)
+    W = torch.as_tensor(weights_table, dtype=DT)
+    u1, u2 = bool(is_unpaired[nt1]), bool(is_unpaired[nt2])
+    if u1 and u2:  # case 1
+        return torch.kron(up[int(idx_to_unpaired_idx[nt1])], up[int(idx_to_unpaired_idx[nt2])]) @ W.reshape(-1)
+    if u1:  # case 2: nt1 unpaired, nt2 base paired
+        p1 = up[int(idx_to_unpaired_idx[nt1])]
+        k2, w2 = (int(x) for x in idx_to_bp_idx[nt2])
+        return sum(p1[a] * bp[k2][t] * W[a, BP_IDXS[t][w2]] for a in range(4) for t in range(4))
+    if u2:  # case 3
+        p2 = up[int(idx_to_unpaired_idx[nt2])]
+        k1, w1 = (int(x) for x in idx_to_bp_idx[nt1])
+        return sum(p2[b] * bp[k1][t] * W[BP_IDXS[t][w1], b] for b in range(4) for t in range(4))
+    k1, w1 = (int(x) for x in idx_to_bp_idx[nt1])
+    k2, w2 = (int(x) for x in idx_to_bp_idx[nt2])
+    if k1 == k2:  # case 4.I: the two members of one base pair
+        return sum(bp[k1][t] * W[BP_IDXS[t][w1], BP_IDXS[t][w2]] for t in range(4))
+    return sum(bp[k1][s] * bp[k2][t] * W[BP_IDXS[s][w1], BP_IDXS[t][w2]] for s in range(4) for t in range(4))  # case 4.II
