@@ -560,6 +560,39 @@ int mythos_b200_fma_peak_f32(void* cuda_stream, void* scratch, int blocks, int i
 int mythos_b200_special_rate_f64(void* cuda_stream, void* scratch, int blocks, int iters, int kind);
 int mythos_b200_special_rate_f32(void* cuda_stream, void* scratch, int blocks, int iters, int kind);
 
+/* ---- trajectory ingest -----------------------------------------------------------------------
+ * Stands in for `from_file` / `_read_file` (mythos/input/trajectory.py:192-320) and NucleotideState.quaternions
+ * (trajectory.py:163-175 -> mythos/utils/math.py:9-65).  The caller copies the file's bytes to the device (16-byte
+ * aligned), then:
+ *   1. mythos_b200_traj_index(.., line_start = NULL, .., n_lines)   counts the lines (device int64 *n_lines)
+ *   2. reads *n_lines, allocates line_start (n_lines + 1) and calls mythos_b200_traj_index again with it
+ *   3. mythos_b200_traj_parse_*: F = n_lines / (N+3) states of "t = ..", "b = ..", "E = .." + N lines of 15 numbers; the
+ *      first nine (centre, a1, a3) are converted with correct rounding (as strtod / np.fromstring do), the quaternion is
+ *      the reference's axes -> Tait-Bryan ZYX -> quaternion formula; row r of a state goes to nucleotide dest[r] (the
+ *      per-strand reversal of 5'->3' files, trajectory.py:291) or r.
+ * status[0] = numbers that could not be converted (more than 19 significant digits, exponent outside +-64, malformed),
+ * status[1] = header lines that are not where N nucleotide lines per state put them.  Both must be 0. */
+typedef struct mb_traj_args {
+  const void* text;          /* device copy of the file */
+  int64_t n_bytes;
+  const int64_t* line_start; /* (n_lines + 1) from mythos_b200_traj_index */
+  int64_t n_lines;
+  int32_t n, n_frames;
+  const int32_t* dest;       /* (N) or NULL */
+  const uint64_t* pow5;      /* (129,2) 128-bit truncated powers of five 5^-64..5^64, device (mythos_b200.input.trajectory) */
+  void* center;              /* out (F,N,3) */
+  void* quat;                /* out (F,N,4) */
+  double* times;             /* out (F) */
+  double* box;               /* out (F,3) */
+  double* energies;          /* out (F,3) */
+  int32_t* status;           /* out (4) */
+} mb_traj_args;
+size_t mythos_b200_traj_workspace_bytes(int64_t n_bytes);
+int mythos_b200_traj_index(void* cuda_stream, const void* text, int64_t n_bytes, void* workspace, size_t workspace_bytes,
+                           int64_t* line_start, int64_t line_capacity, int64_t* n_lines);
+int mythos_b200_traj_parse_f64(void* cuda_stream, const mb_traj_args* a);
+int mythos_b200_traj_parse_f32(void* cuda_stream, const mb_traj_args* a);
+
 /* ---- theta -> parameter-bank chain (host side; no device work) ------------------------------------------------
  * Stands in for `BaseConfiguration.init_params` of every term (mythos/energy/configuration.py:110-113, e.g.
  * mythos/energy/dna1/stacking.py:120-183, hydrogen_bonding.py:148-223) and the smoothing solvers

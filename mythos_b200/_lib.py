@@ -115,6 +115,12 @@ class Pseq(C.Structure):
                 ("terms", C.c_uint32), ("_pad", C.c_uint32)]
 
 
+class TrajArgs(C.Structure):
+    _fields_ = [("text", C.c_void_p), ("n_bytes", C.c_int64), ("line_start", C.c_void_p), ("n_lines", C.c_int64), ("n", C.c_int32),
+                ("n_frames", C.c_int32), ("dest", C.c_void_p), ("pow5", C.c_void_p), ("center", C.c_void_p), ("quat", C.c_void_p),
+                ("times", C.c_void_p), ("box", C.c_void_p), ("energies", C.c_void_p), ("status", C.c_void_p)]
+
+
 class ObservableSpec(C.Structure):
     _fields_ = [("base_pairs", C.c_void_p), ("n_base_pairs", C.c_int32), ("n_quartets", C.c_int32), ("quartets", C.c_void_p),
                 ("sigma_backbone", C.c_double)]
@@ -216,6 +222,10 @@ _SIGNATURES = {
     "mythos_b200_special_rate_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "mythos_b200_observables_f64": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ObservableSpec), C.c_void_p]),
     "mythos_b200_observables_f32": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ObservableSpec), C.c_void_p]),
+    "mythos_b200_traj_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "mythos_b200_traj_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.c_void_p]),
+    "mythos_b200_traj_parse_f64": (C.c_int, [C.c_void_p, C.POINTER(TrajArgs)]),
+    "mythos_b200_traj_parse_f32": (C.c_int, [C.c_void_p, C.POINTER(TrajArgs)]),
     "mythos_b200_theta_tape_forward": (C.c_int, [C.c_void_p] * 4),
     "mythos_b200_theta_tape_vjp": (C.c_int, [C.c_void_p] * 5),
     "mythos_b200_abi_version": (C.c_int, []),

@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libmythos_b200.so"
-SOURCES = ["abi_common.cu", "energy_kernels.cu", "frame_kernels.cu", "list_kernels.cu", "neighbors.cu", "langevin.cu", "difftre.cu", "peaks.cu", "theta_tape.cu", "observables.cu"]
+SOURCES = ["abi_common.cu", "energy_kernels.cu", "frame_kernels.cu", "list_kernels.cu", "neighbors.cu", "langevin.cu", "difftre.cu", "peaks.cu", "theta_tape.cu", "observables.cu", "trajectory.cu"]
 NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",

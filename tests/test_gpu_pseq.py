@@ -91,8 +91,12 @@ def test_random_pseq_equals_brute_force_expectation_with_gradients(model):
     expected = prob @ E
     np.testing.assert_allclose(e.detach().cpu().numpy(), expected.detach().numpy(), rtol=1e-10)
     (expected * cot.cpu()).sum().backward()
-    np.testing.assert_allclose(up_t.grad.numpy(), up_b.grad.numpy(), rtol=1e-8, atol=1e-10)
-    np.testing.assert_allclose(bp_t.grad.numpy(), bp_b.grad.numpy(), rtol=1e-8, atol=1e-10)
+    # The two expressions are different extensions of the same function off the probability simplex (the product form
+    # multiplies every pair energy by ALL slots' probabilities, the per-pair weights only by the slots the pair touches), so
+    # their gradients differ by a constant per row and agree on the simplex's tangent space: compare with row means removed.
+    tangent = lambda g: (g - g.mean(1, keepdim=True)).numpy()  # noqa: E731
+    np.testing.assert_allclose(tangent(up_t.grad), tangent(up_b.grad), rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(tangent(bp_t.grad), tangent(bp_b.grad), rtol=1e-8, atol=1e-9)
 
 
 def test_table_and_theta_gradients_with_pseq_match_finite_differences():
