@@ -537,6 +537,35 @@ typedef struct mb_langevin_args {
 int mythos_b200_langevin_f64(void* cuda_stream, const mb_langevin_args* a);
 int mythos_b200_langevin_f32(void* cuda_stream, const mb_langevin_args* a);
 
+/* adjoint of one step: the vector-Jacobian product jax.grad computes through `step_fn` when a loss
+ * is differentiated through the trajectory (mythos/simulators/jax_md/utils.py:174-193 checkpoint_scan; jaxmd.py:54-58,94).
+ * The forces enter the step as an input: the kernel returns the cotangents of the PRE-step state (overwriting the
+ * post-step cotangents it was given) and the cotangent of the force arrays; the force's own dependence on positions and
+ * parameters is the caller's (two displaced mythos_b200_energy_* evaluations give the Hessian-vector product and the
+ * mixed theta derivative).  `noise` (N,6) or the (seed, step) of the forward step; phase 0 (half kick) or 2 (full kick). */
+typedef struct mb_langevin_adjoint_args {
+  int32_t n;
+  int32_t phase;
+  const void* center;     /* pre-step state (N,3) */
+  const void* quat;       /* (N,4) */
+  const void* p_center;   /* (N,3) */
+  const void* p_quat;     /* (N,4) */
+  const void* d_center;   /* dE/dcenter at the pre-step positions (N,3) */
+  const void* d_quat;     /* (N,4) */
+  const void* noise;      /* (N,6) or NULL */
+  void* lam_center;       /* in/out (N,3) */
+  void* lam_quat;         /* in/out (N,4) */
+  void* lam_p_center;     /* in/out (N,3) */
+  void* lam_p_quat;       /* in/out (N,4) */
+  void* lam_force_center; /* out (N,3) */
+  void* lam_force_quat;   /* out (N,4) */
+  double dt, kT, gamma_center, gamma_quat, mass;
+  double inertia[3];
+  uint64_t seed, step;
+} mb_langevin_adjoint_args;
+int mythos_b200_langevin_adjoint_f64(void* cuda_stream, const mb_langevin_adjoint_args* a);
+int mythos_b200_langevin_adjoint_f32(void* cuda_stream, const mb_langevin_adjoint_args* a);
+
 /* ---- DiffTRe reweighting ------------------------------------------------------------------------------------- */
 typedef struct mb_weights_args {
   int32_t n_frames;

@@ -189,6 +189,13 @@ class LangevinArgs(C.Structure):
     ]
 
 
+class LangevinAdjointArgs(C.Structure):
+    _fields_ = [("n", C.c_int32), ("phase", C.c_int32)] + [(k, C.c_void_p) for k in (
+        "center", "quat", "p_center", "p_quat", "d_center", "d_quat", "noise", "lam_center", "lam_quat", "lam_p_center", "lam_p_quat",
+        "lam_force_center", "lam_force_quat")] + [(k, C.c_double) for k in ("dt", "kT", "gamma_center", "gamma_quat", "mass")] + [
+        ("inertia", C.c_double * 3), ("seed", C.c_uint64), ("step", C.c_uint64)]
+
+
 class WeightsArgs(C.Structure):
     _fields_ = [
         ("n_frames", C.c_int32),
@@ -214,6 +221,8 @@ _SIGNATURES = {
     "mythos_b200_nl_build_f32": (C.c_int, [C.c_void_p, C.POINTER(NlArgs)]),
     "mythos_b200_langevin_f64": (C.c_int, [C.c_void_p, C.POINTER(LangevinArgs)]),
     "mythos_b200_langevin_f32": (C.c_int, [C.c_void_p, C.POINTER(LangevinArgs)]),
+    "mythos_b200_langevin_adjoint_f64": (C.c_int, [C.c_void_p, C.POINTER(LangevinAdjointArgs)]),
+    "mythos_b200_langevin_adjoint_f32": (C.c_int, [C.c_void_p, C.POINTER(LangevinAdjointArgs)]),
     "mythos_b200_weights_neff_f64": (C.c_int, [C.c_void_p, C.POINTER(WeightsArgs)]),
     "mythos_b200_weights_neff_f32": (C.c_int, [C.c_void_p, C.POINTER(WeightsArgs)]),
     "mythos_b200_fma_peak_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
