@@ -66,3 +66,50 @@ def step(c, q, pc, pq, d_center, d_quat, noise, dt, kT, gamma_c, gamma_q, mass, 
 def kinetic_energies(q, pc, pq, mass, inertia):
     L = angular_momentum(q, pq)
     return (pc * pc).sum(-1) / (2 * mass), (L * L / (2 * np.asarray(inertia))).sum(-1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The same step on torch tensors, so that torch.autograd can differentiate THROUGH it: the oracle for the adjoint of the
+# step (what jax.grad does through step_fn inside checkpoint_scan, mythos/simulators/jax_md/utils.py:174-193).
+def _perm_t(k, q):
+    import torch
+
+    q0, q1, q2, q3 = q.unbind(-1)
+    if k == 1:
+        return torch.stack([-q1, q0, q3, -q2], -1)
+    if k == 2:
+        return torch.stack([-q2, -q3, q0, q1], -1)
+    return torch.stack([-q3, q2, -q1, q0], -1)
+
+
+def _drift_t(c, q, pc, pq, h, mass, inertia):
+    import torch
+
+    c = c + h * pc / mass
+    for k, st in ((3, 0.5 * h), (2, 0.5 * h), (1, h), (2, 0.5 * h), (3, 0.5 * h)):
+        Pq, Pp = _perm_t(k, q), _perm_t(k, pq)
+        zeta = st * (pq * Pq).sum(-1, keepdim=True) / (4.0 * inertia[k - 1])
+        cz, sz = torch.cos(zeta), torch.sin(zeta)
+        q, pq = cz * q + sz * Pq, cz * pq + sz * Pp
+    return c, q, pq
+
+
+def step_torch(c, q, pc, pq, d_center, d_quat, noise, dt, kT, gamma_c, gamma_q, mass, inertia, kick=None):
+    """``step`` with torch tensors (free space), differentiable in every tensor argument."""
+    import math
+
+    import torch
+
+    h = 0.5 * dt
+    kick = h if kick is None else kick
+    pc = pc - kick * d_center
+    pq = pq - kick * d_quat
+    c, q, pq = _drift_t(c, q, pc, pq, h, mass, inertia)
+    c1 = math.exp(-gamma_c * dt)
+    pc = c1 * pc + math.sqrt(kT * (1 - c1 * c1) * mass) * noise[:, :3]
+    r1 = math.exp(-gamma_q * dt)
+    L = torch.stack([0.5 * (pq * _perm_t(k, q)).sum(-1) for k in (1, 2, 3)], -1)
+    L = r1 * L + torch.sqrt(kT * (1 - r1 * r1) * torch.as_tensor(inertia, dtype=c.dtype)) * noise[:, 3:]
+    pq = 2.0 * sum(L[..., k - 1 : k] * _perm_t(k, q) for k in (1, 2, 3))
+    c, q, pq = _drift_t(c, q, pc, pq, h, mass, inertia)
+    return c, q, pc, pq
