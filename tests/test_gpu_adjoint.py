@@ -40,7 +40,7 @@ def test_integrator_adjoint_matches_autograd_through_the_oracle_step(phase):
     out = lo.step_torch(*leaves, noise, DT, KT, GC, GQ, 1.2, inertia, kick=DT if phase == 2 else None)
     want = torch.autograd.grad(sum((o * l).sum() for o, l in zip(out, lam_out)), leaves)
 
-    st = adjoint._Stepper(DT, KT, RigidBody(torch.tensor(GC), torch.tensor([GQ] * 3)), RigidBody(torch.tensor(1.2), torch.tensor(inertia)), torch.float64)
+    st = adjoint._Stepper(DT, KT, RigidBody(torch.tensor(GC, dtype=torch.float64), torch.tensor([GQ] * 3, dtype=torch.float64)), RigidBody(torch.tensor(1.2, dtype=torch.float64), torch.tensor(inertia, dtype=torch.float64)), torch.float64)
     dev = lambda t: t.to(DEV).contiguous()  # noqa: E731
     lam = [dev(t) for t in lam_out]
     lam_force = [torch.empty((n, 3), device=DEV, dtype=torch.float64), torch.empty((n, 4), device=DEV, dtype=torch.float64)]
@@ -72,7 +72,7 @@ def test_trajectory_gradient_matches_autograd_through_oracle_md():
 
     loss, grads, traj, init_grad = adjoint.simulate_and_grad(
         efn, theta, RigidBody(c0.to(DEV), Quaternion(q0.to(DEV))), steps, loss_fn, dt=DT, kT=KT,
-        gamma=RigidBody(torch.tensor(GC), torch.tensor([GQ] * 3)), noise=noise)
+        gamma=RigidBody(torch.tensor(GC, dtype=torch.float64), torch.tensor([GQ] * 3, dtype=torch.float64)), noise=noise)
 
     # oracle: autograd through oracle step + oracle energy
     th = orc.default_theta("dna1")
