@@ -272,7 +272,7 @@ static int energy_impl(cudaStream_t s, const mb_energy_args* x) {
     a.obs = obs;
     a.obs_out = obs_out;  // epilogue of the same kernel: the frame is already in shared memory
     a.acc_scratch = nullptr;
-    if (wp) {
+    if (wp && frame_scratch_bytes(sizeof(T)) > 0) {
       MB_REQUIRE(x->workspace && x->workspace_bytes >= frame_scratch_bytes(sizeof(T)), MB_ECAPACITY,
                  "energy: dE/dparams through the frame-resident kernel needs a workspace of mythos_b200_energy_workspace_bytes() bytes");
       a.acc_scratch = static_cast<T*>(x->workspace);

@@ -142,11 +142,23 @@ def _launch(
         obs_spec = observables[0].struct()
         a.observables = C.addressof(obs_spec)
         a.observables_out = observables[1].data_ptr()
-    frame_ws = want_param_grad and not want_pos_grad and model.n_banks == 1  # the frame-resident kernel may take this call
-    if ((cap and (cap * F >= 65536 or (flags & (_lib.FLAG_LIST_KERNEL | _lib.FLAG_TAGGED_PAIRS)))) or frame_ws) and not (flags & _lib.FLAG_GENERIC_KERNEL):
-        # scratch of the phase-queued list kernel / parameter-gradient images of the frame-resident kernel (caller-owned,
-        # as everywhere in the C-ABI); the caching allocator makes this a pointer bump, and it is graph-capture safe
-        need = int(_lib.lib().mythos_b200_energy_workspace_bytes(N, F, cap, 8 if dtype == torch.float64 else 4))
+    esize = 8 if dtype == torch.float64 else 4
+    tagged_list = bool(flags & _lib.FLAG_TAGGED_PAIRS)
+    # will the frame-resident kernel take this call?  (same rule as frame_kernel_eligible in csrc/frame_kernels.cu)  It needs
+    # only its own scratch (nothing in the default build); lending it the LIST kernels' workspace -- 0.66 GB per 1024 frames,
+    # a fresh block per launch -- made the caching allocator cudaMalloc at unpredictable passes (~100 ms each).
+    frame_route = (not want_pos_grad and model.n_banks == 1 and not (flags & (_lib.FLAG_GENERIC_KERNEL | _lib.FLAG_LIST_KERNEL))
+                   and N <= 60000 and (not tagged_list or N < 16384)
+                   and bool(_lib.lib().mythos_b200_frame_kernel_fits(N, esize, 1 if want_param_grad else 0)))
+    if frame_route:
+        need = int(_lib.lib().mythos_b200_energy_workspace_bytes(N, F, 0, esize)) if want_param_grad else 0
+        if need:
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            a.workspace, a.workspace_bytes = ws.data_ptr(), need
+    elif cap and (cap * F >= 65536 or (flags & (_lib.FLAG_LIST_KERNEL | _lib.FLAG_TAGGED_PAIRS))) and not (flags & _lib.FLAG_GENERIC_KERNEL):
+        # scratch of the phase-queued list kernels (caller-owned, as everywhere in the C-ABI); the caching allocator makes
+        # this a pointer bump, and it is graph-capture safe
+        need = int(_lib.lib().mythos_b200_energy_workspace_bytes(N, F, cap, esize))
         ws = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
         a.workspace, a.workspace_bytes = ws.data_ptr(), need
     fn = getattr(_lib.lib(), f"mythos_b200_energy_{sfx}")
@@ -204,6 +216,19 @@ class _SizingMemo:
 
 _SIZING = _SizingMemo()
 _PAIR_SCRATCH: dict = {}
+
+
+_NL_SCRATCH: dict = {}
+
+
+def _scratch_nl_workspace(device, n: int, n_frames: int) -> torch.Tensor:
+    """The neighbour build's scratch, one reused buffer per (device, stream) (pair sources are rebuilt every pass)."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    need = int(_lib.lib().mythos_b200_nl_workspace_bytes(n, n_frames))
+    buf = _NL_SCRATCH.get(key)
+    if buf is None or buf.numel() < need:
+        _NL_SCRATCH[key] = buf = torch.empty(int(need * 1.1) + 1024, dtype=torch.uint8, device=device)
+    return buf
 
 
 def _scratch_pairs(device, n_frames: int, cap: int) -> torch.Tensor:
@@ -301,6 +326,7 @@ class CellListPairs:
             overflow = torch.zeros((1,), dtype=torch.int32, device=cc.device)
             mra = torch.empty((F, 2), dtype=torch.int32, device=cc.device)
             mrb = torch.empty((F, 2), dtype=torch.int32, device=cc.device) if ss is not None else None
+            self.workspace = _scratch_nl_workspace(cc.device, cc.shape[1], F)
             _, _, _, self.workspace = neighbors.build_pairs(cc, self.bonded, self.box, max(r_sr, 1e-6), 0.0, cap, self.workspace,
                                                             tag_bits=1 << 30, out=(pairs, count, overflow), max_row=mra,
                                                             warp_slots=(ka, 0, wa))
