@@ -57,7 +57,7 @@ constexpr int kExcl = 2;                // bonded partners per nucleotide (as th
 struct FrameSmem {
   // byte offsets into dynamic shared memory; computed on the host and passed as a kernel parameter so that the
   // kernel re-reads them from the constant bank instead of rematerialising the whole chain under register pressure
-  unsigned c, q, back, p, acc, e, flags, q_nl, q_sr, q_bp, q_cx, wcnt, ctr, cstart, corder, excl, grid, win, total;
+  unsigned c, q, back, p, acc, e, flags, q_nl, q_sr, q_bp, q_cx, wcnt, ctr, cstart, corder, excl, grid, win, bar, total;
   int acc_rows;  // copies of the parameter-gradient image: warps are spread over them so that their shared-memory atomics do not collide
 };
 template <class T>
@@ -88,6 +88,7 @@ inline FrameSmem frame_smem_layout(int n, bool wp, bool cache_back, bool cells, 
   L.excl = take(cells ? sizeof(uint16_t) * kExcl * n : 0);
   L.grid = take(sizeof(T) * 8 + sizeof(int) * 8);
   L.win = take(sizeof(CosWin<T>) * 6);
+  L.bar = take(sizeof(uint64_t));  // mbarrier of the bulk (TMA) frame staging
   L.total = off;
   return L;
 }
@@ -271,6 +272,28 @@ __device__ __forceinline__ void cell_of(const CellGrid<T>* grid, const T* box, b
   }
 }
 
+// ---- bulk asynchronous copy (TMA, cp.async.bulk) global -> shared with mbarrier completion: one thread stages a whole frame
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
+               "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done)
+               : "r"(smem_addr(bar)), "r"(parity)
+               : "memory");
+  return done != 0;
+}
+
 // the observables epilogue as a real call with scalar arguments: its registers are allocated on their own and nothing of the
 // energy phases' state has its address taken (which would push it into local memory)
 template <class T>
@@ -337,6 +360,12 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
     for (int k = threadIdx.x; k < MB_P_COUNT * 32; k += kFB) gimg[k] = T(0);
   GlobAcc<T> pacc{gimg};
 #endif
+  // bulk staging needs 16-byte aligned rows: every frame's centre block starts at a multiple of 24 n bytes
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+  const bool bulk = ((sizeof(T) * 3 * n) % 16 == 0) && ((reinterpret_cast<uintptr_t>(a.center) | reinterpret_cast<uintptr_t>(a.quat)) % 16 == 0) &&
+                    sizeof(T) * 7 * n < (1u << 20);
+  uint32_t bar_parity = 0u;
+  if (bulk && threadIdx.x == 0) mbar_init(bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) bp_windows(sP, sWin);  // visible after the next barrier
   const ModelT<T>& M = a.M;
@@ -348,8 +377,22 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   for (int frame = blockIdx.x; frame < a.n_frames; frame += gridDim.x) {
   __syncthreads();  // the previous frame is finished with shared memory
   const long long fbase = (long long)frame * n;
-  for (int k = threadIdx.x; k < 3 * n; k += kFB) sC[k] = a.center[3 * fbase + k];
-  for (int k = threadIdx.x; k < 4 * n; k += kFB) sQ[k] = a.quat[4 * fbase + k];
+  if (bulk) {
+    // the frame's (center, quat) rows arrive as two bulk asynchronous copies (TMA engine, 114 KB at N = 2040, float64) issued
+    // by one thread; everyone waits on the mbarrier's transaction count instead of each thread moving 28 reals by hand
+    if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy accesses of sC / sQ are ordered first
+      mbar_expect_tx(bar, uint32_t(sizeof(T) * 7 * n));
+      bulk_load(sC, a.center + 3 * fbase, uint32_t(sizeof(T) * 3 * n), bar);
+      bulk_load(sQ, a.quat + 4 * fbase, uint32_t(sizeof(T) * 4 * n), bar);
+    }
+    while (!mbar_try_wait(bar, bar_parity)) {
+    }
+    bar_parity ^= 1u;
+  } else {
+    for (int k = threadIdx.x; k < 3 * n; k += kFB) sC[k] = a.center[3 * fbase + k];
+    for (int k = threadIdx.x; k < 4 * n; k += kFB) sQ[k] = a.quat[4 * fbase + k];
+  }
   if (WP)
     for (int k = threadIdx.x; k < MB_P_COUNT * L.acc_rows; k += kFB) sAcc[k] = T(0);
   if (threadIdx.x < 8) ctr[threadIdx.x] = 0;

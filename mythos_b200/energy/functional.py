@@ -14,6 +14,7 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses as dc
 import os
+import threading
 
 import torch
 
@@ -739,33 +740,39 @@ class deferred_verification:  # noqa: N801 - used as a context manager
         return good
 
 
-_COPY_STREAMS: dict = {}
+_COPY_STREAMS: dict = {}  # per device
 _PREFETCHED: dict = {}  # at most one entry: the first chunk of a pinned trajectory, copied ahead of its pass
+_STREAM_LOCK = threading.Lock()  # guards the three module-level tables below against concurrent host threads
 
 
 def prefetch_frames(center: torch.Tensor, quat: torch.Tensor) -> None:
     """Start the host -> device copy of the first chunk of pinned host frames NOW, before the caller's host-side work
     (the theta -> parameter-bank chain of a DiffTRe step), so the first kernels do not wait for PCIe.  A no-op for
     device tensors; the copy is picked up by the next streamed pass over the same buffers."""
-    _PREFETCHED.clear()
+    with _STREAM_LOCK:
+        _PREFETCHED.clear()
     if center.is_cuda or not (center.is_pinned() and quat.is_pinned() and torch.cuda.is_available()) or center.dim() != 3:
         return
     dev = torch.device("cuda", torch.cuda.current_device())
     sl = _chunks(center.shape[0], CellListPairs, True)[0]  # as a pass with per-frame device lists (the DiffTRe route) cuts it
     key = (center.data_ptr(), quat.data_ptr(), center.shape[0], sl.start, sl.stop, dev)
-    _PREFETCHED[key] = _fetch(center, quat, sl, dev)
+    fetched = _fetch(center, quat, sl, dev)
+    with _STREAM_LOCK:
+        _PREFETCHED[key] = fetched
 
 
 def _fetch(center: torch.Tensor, quat: torch.Tensor, sl: slice, dev):
     """Enqueue the host -> device copy of one chunk of frames on the device's copy stream; -> (center, quat, event)."""
-    if _PREFETCHED:
-        hit = _PREFETCHED.pop((center.data_ptr(), quat.data_ptr(), center.shape[0], sl.start, sl.stop, dev), None)
-        _PREFETCHED.clear()
-        if hit is not None:
-            return hit
-    stream = _COPY_STREAMS.get(dev)
-    if stream is None:
-        stream = _COPY_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    with _STREAM_LOCK:
+        hit = None
+        if _PREFETCHED:
+            hit = _PREFETCHED.pop((center.data_ptr(), quat.data_ptr(), center.shape[0], sl.start, sl.stop, dev), None)
+            _PREFETCHED.clear()
+        stream = _COPY_STREAMS.get(dev)
+        if stream is None:
+            stream = _COPY_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    if hit is not None:
+        return hit
     with torch.cuda.stream(stream):
         c = center[sl].to(dev, non_blocking=True)
         q = quat[sl].to(dev, non_blocking=True)

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import dataclasses as dc
 import re
+import threading
 from functools import lru_cache
 from typing import Any
 
@@ -88,17 +89,20 @@ def geometry_of(transform_fn) -> tuple[str, list[_lib.FlavourGeom]]:
 
 
 # --------------------------------------------------------------------------------------------- caches
-_TOPO_CACHE: dict[tuple, tuple[tuple, Any]] = {}
+_TOPO_CACHE: dict[tuple, tuple[tuple, Any]] = {}  # keys carry the device: per-device entries
+_TOPO_LOCK = threading.Lock()  # evaluations may come from several host threads (XLA executor threads, user threads)
 
 
 def _cached(key: tuple, keep: tuple, make):
-    hit = _TOPO_CACHE.get(key)
-    if hit is not None and all(a is b for a, b in zip(hit[0], keep)):
-        return hit[1]
-    if len(_TOPO_CACHE) > 64:
-        _TOPO_CACHE.pop(next(iter(_TOPO_CACHE)))
-    val = make()
-    _TOPO_CACHE[key] = (keep, val)
+    with _TOPO_LOCK:
+        hit = _TOPO_CACHE.get(key)
+        if hit is not None and all(a is b for a, b in zip(hit[0], keep)):
+            return hit[1]
+    val = make()  # (device copies are made outside the lock; a racing duplicate is harmless, the last one is kept)
+    with _TOPO_LOCK:
+        if len(_TOPO_CACHE) > 64:
+            _TOPO_CACHE.pop(next(iter(_TOPO_CACHE)))
+        _TOPO_CACHE[key] = (keep, val)
     return val
 
 

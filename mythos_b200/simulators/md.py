@@ -272,7 +272,7 @@ class MDSimulator:
             done = min(2, n_steps)
             # steady state: graphs of `block` steps (one host launch per block keeps the replay loop off the CPU's
             # critical path), then single-step replays for the remainder
-            block = 16
+            block = 64  # (fewer host launches per simulated time: the replay loop stays off a slow host's critical path)
             if n_steps - done >= 2 * block:
                 big = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(big, stream=stream):
