@@ -202,6 +202,35 @@ __device__ __forceinline__ void bp_windows(const T* P, CosWin<T> w[6]) {
   w[4] = f4_cos_window(P + MB_P_CROSS_T2_TH0);
   w[5] = f4_cos_window(P + MB_P_CROSS_T3_TH0);
 }
+// nine windows of one bank (frame kernel): [0..5] as bp_windows; [6..8] hydrogen bonding theta4, theta7, theta8 as windows of
+// a3i.a3j, -a3j.dh and -a3i.dh (theta8 = pi - acos(a3i.dh) = acos(-a3i.dh))
+template <class T>
+__device__ __forceinline__ void bp_windows9(const T* P, CosWin<T> w[9]) {
+  bp_windows(P, w);
+  w[6] = f4_cos_window(P + MB_P_HB_T4_TH0);
+  w[7] = f4_cos_window(P + MB_P_HB_T7_TH0);
+  w[8] = f4_cos_window(P + MB_P_HB_T8_TH0);
+}
+// bit 0: hydrogen bonding of the pair can be non-zero (radial window, non-zero table weight, all SIX angular windows);
+// bit 1: cross stacking can be (radial window, the three plain angles).  The two terms are queued separately so that a
+// batch of either runs one term's code with dense lanes.
+template <class T>
+__device__ __forceinline__ unsigned bp_screen2(const T* P, const CosWin<T>* w, unsigned mask, const V3<T>& d, T r2, const V3<T>& a1i,
+                                               const V3<T>& a1j, const V3<T>& a3i, const V3<T>& a3j, int tab) {
+  const T r = sqrt(r2);
+  const bool rad_hb = (mask & (1u << MB_TERM_HB)) && P[MB_P_HB_RCLOW] < r && r < P[MB_P_HB_RCHIGH] && P[MB_P_HB_W00 + tab] != T(0);
+  const bool rad_cr = (mask & (1u << MB_TERM_CROSS)) && P[MB_P_CROSS_RCLOW] < r && r < P[MB_P_CROSS_RCHIGH];
+  if (!(rad_hb || rad_cr) || !(r > T(0))) return 0u;
+  const T ir = T(1) / r;
+  const T x1 = -dot(a1i, a1j), x2 = -dot(a1j, d) * ir, x3 = dot(a1i, d) * ir;
+  bool hb = rad_hb && w[0].lo < x1 && x1 < w[0].hi && w[1].lo < x2 && x2 < w[1].hi && w[2].lo < x3 && x3 < w[2].hi;
+  const bool cr = rad_cr && w[3].lo < x1 && x1 < w[3].hi && w[4].lo < x2 && x2 < w[4].hi && w[5].lo < x3 && x3 < w[5].hi;
+  if (hb) {
+    const T x4 = dot(a3i, a3j), x7 = -dot(a3j, d) * ir, x8 = -dot(a3i, d) * ir;
+    hb = w[6].lo < x4 && x4 < w[6].hi && w[7].lo < x7 && x7 < w[7].hi && w[8].lo < x8 && x8 < w[8].hi;
+  }
+  return (hb ? 1u : 0u) | (cr ? 2u : 0u);
+}
 // true if hydrogen bonding or cross stacking of the pair can be non-zero (d = base_j - base_i, r2 = |d|^2)
 template <class T>
 __device__ __forceinline__ bool bp_screen(const T* P, const CosWin<T>* w, unsigned mask, const V3<T>& d, T r2, const V3<T>& a1i,

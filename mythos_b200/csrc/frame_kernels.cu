@@ -57,7 +57,7 @@ constexpr int kExcl = 2;                // bonded partners per nucleotide (as th
 struct FrameSmem {
   // byte offsets into dynamic shared memory; computed on the host and passed as a kernel parameter so that the
   // kernel re-reads them from the constant bank instead of rematerialising the whole chain under register pressure
-  unsigned c, q, back, p, acc, e, flags, q_nl, q_sr, q_bp, q_cx, wcnt, ctr, cstart, corder, excl, grid, win, bar, total;
+  unsigned c, q, back, p, acc, e, flags, q_nl, q_sr, q_bp, q_cr, q_cx, wcnt, ctr, cstart, corder, excl, grid, win, bar, total;
   int acc_rows;  // copies of the parameter-gradient image: warps are spread over them so that their shared-memory atomics do not collide
 };
 template <class T>
@@ -80,6 +80,7 @@ inline FrameSmem frame_smem_layout(int n, bool wp, bool cache_back, bool cells, 
   L.q_nl = take(sizeof(uint32_t) * kNlCap);
   L.q_sr = take(sizeof(uint32_t) * kSrCap);
   L.q_bp = take(sizeof(uint32_t) * kQCap);
+  L.q_cr = take(sizeof(uint32_t) * kQCap);
   L.q_cx = take(sizeof(uint32_t) * kQCap);
   L.wcnt = take(sizeof(int) * 2 * (kFWarps + 1));
   L.ctr = take(sizeof(int) * 8);
@@ -87,7 +88,7 @@ inline FrameSmem frame_smem_layout(int n, bool wp, bool cache_back, bool cells, 
   L.corder = take(cells ? sizeof(uint16_t) * n : 0);
   L.excl = take(cells ? sizeof(uint16_t) * kExcl * n : 0);
   L.grid = take(sizeof(T) * 8 + sizeof(int) * 8);
-  L.win = take(sizeof(CosWin<T>) * 6);
+  L.win = take(sizeof(CosWin<T>) * 9);
   L.bar = take(sizeof(uint64_t));  // mbarrier of the bulk (TMA) frame staging
   L.total = off;
   return L;
@@ -172,6 +173,30 @@ __device__ __forceinline__ void q_push2_multi(uint32_t* qa, int* na, unsigned bi
   if (threadIdx.x == kFB - 1) {
     *na = old_a + ((before + incl) & 0xffff);
     *nb = old_b + ((before + incl) >> 16);
+  }
+  __syncthreads();
+}
+
+// ordered block-wide append of one entry per thread into up to THREE queues at once (one barrier set, one scan: the three
+// per-warp counts are packed 10 bits each -- a CTA appends at most kFB <= 1023 entries per queue and call)
+__device__ __forceinline__ void q_push3(uint32_t* qa, int* na, bool pa, uint32_t* qb, int* nb, bool pb, uint32_t* qc, int* nc, bool pc,
+                                        int* wcnt, uint32_t val) {
+  static_assert(kFB < 1024, "10-bit packed counts");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned ma = __ballot_sync(kFull, pa), mb_ = __ballot_sync(kFull, pb), mc = __ballot_sync(kFull, pc);
+  if (lane == 0) wcnt[warp] = __popc(ma) | (__popc(mb_) << 10) | (__popc(mc) << 20);
+  __syncthreads();
+  const int old_a = *na, old_b = *nb, old_c = *nc;
+  const int before = warp_prefix(wcnt, warp, lane);
+  const unsigned below = (1u << lane) - 1u;
+  if (pa) qa[old_a + (before & 1023) + __popc(ma & below)] = val;
+  if (pb) qb[old_b + ((before >> 10) & 1023) + __popc(mb_ & below)] = val;
+  if (pc) qc[old_c + (before >> 20) + __popc(mc & below)] = val;
+  __syncthreads();
+  if (threadIdx.x == kFB - 1) {  // last warp: its prefix + own count = total
+    *na = old_a + (before & 1023) + __popc(ma);
+    *nb = old_b + ((before >> 10) & 1023) + __popc(mb_);
+    *nc = old_c + (before >> 20) + __popc(mc);
   }
   __syncthreads();
 }
@@ -330,10 +355,11 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   unsigned char* sF = smem + L.flags;  // bits 0-1 seq, bit 2 is_end
   uint32_t* qNL = reinterpret_cast<uint32_t*>(smem + L.q_nl);
   uint32_t* qSR = reinterpret_cast<uint32_t*>(smem + L.q_sr);
-  uint32_t* qBP = reinterpret_cast<uint32_t*>(smem + L.q_bp);
+  uint32_t* qBP = reinterpret_cast<uint32_t*>(smem + L.q_bp);  // hydrogen-bonding candidates
+  uint32_t* qCR = reinterpret_cast<uint32_t*>(smem + L.q_cr);  // cross-stacking candidates
   uint32_t* qCX = reinterpret_cast<uint32_t*>(smem + L.q_cx);
   int* wcnt = reinterpret_cast<int*>(smem + L.wcnt);
-  int* ctr = reinterpret_cast<int*>(smem + L.ctr);  // [0] n_sr [1] n_bp [2] n_cx [3] n_nl [5] too many bonds [6] more tiles
+  int* ctr = reinterpret_cast<int*>(smem + L.ctr);  // [0] n_sr [1] n_bp (hydrogen bonding) [2] n_cx [3] n_nl [4] n_cr (cross stacking) [5] too many bonds [6] more tiles
   // packed cell coordinates (10 bits per axis): needed only while the cell list is built, aliases queues SR/BP/CX
   uint32_t* sCell = reinterpret_cast<uint32_t*>(smem + L.q_sr);
   int* sCstart = reinterpret_cast<int*>(smem + L.cstart);
@@ -367,7 +393,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   uint32_t bar_parity = 0u;
   if (bulk && threadIdx.x == 0) mbar_init(bar, 1);
   __syncthreads();
-  if (threadIdx.x == 0) bp_windows(sP, sWin);  // visible after the next barrier
+  if (threadIdx.x == 0) bp_windows9(sP, sWin);  // visible after the next barrier
   const ModelT<T>& M = a.M;
   const Geom<T>& g = M.geom[0];
   const mb_bank_forms F = M.forms[0];
@@ -681,10 +707,11 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
     const T rc_debye2 = want_debye ? sP[MB_P_DEBYE_RCUT] * sP[MB_P_DEBYE_RCUT] : T(-1);
     bool flush = false;
     while (true) {
-      const int n_sr = ctr[0], n_bp = ctr[1], n_cx = ctr[2], n_nl = ctr[3];
+      const int n_sr = ctr[0], n_bp = ctr[1], n_cx = ctr[2], n_nl = ctr[3], n_cr = ctr[4];
       __syncthreads();  // everyone has read the counters before anyone updates them
       if (n_bp >= kFB || (flush && n_bp > 0)) {
-        // ---------------- phase 3a: hydrogen bonding + cross stacking on the BP queue
+        // ---------------- phase 3a: hydrogen bonding on the HB queue (every entry passed the term's radial window and all six
+        // angular windows in phase 2, so the lanes of a batch are dense in this term's code)
         const int cnt = n_bp >= kFB ? kFB : n_bp;
         const int t = threadIdx.x;
         const bool valid = t < cnt;
@@ -693,32 +720,47 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
         const V3<T> d = disp(site(nj, g.base, T(0), T(0)), site(ni, g.base, T(0), T(0)), M.box);
         const T r = sqrt(dot(d, d));
-        const bool in_hb = valid && (mask & (1u << MB_TERM_HB)) && sP[MB_P_HB_RCLOW] < r && r < sP[MB_P_HB_RCHIGH];
-        const bool in_cr = valid && (mask & (1u << MB_TERM_CROSS)) && sP[MB_P_CROSS_RCLOW] < r && r < sP[MB_P_CROSS_RCHIGH];
+        const bool in_hb = valid && sP[MB_P_HB_RCLOW] < r && r < sP[MB_P_HB_RCHIGH];
         const V3<T> dh = (valid && r > T(0)) ? (T(1) / r) * d : v3<T>(0, 0, 0);
         HbAngles<T> A;
         A.ready = false;
         HbGrad<T> HG;
         const int tab = (sF[i] & 3) * 4 + (sF[j] & 3);
-        if (mask & (1u << MB_TERM_HB)) {
-          if (WP)
-            e[MB_TERM_HB] += hb_term<T, false, true>(sP, 0, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, tab, cot[MB_TERM_HB], HG, pacc);
-          else
-            e[MB_TERM_HB] += hb_term<T, false, false>(sP, 0, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, tab, cot[MB_TERM_HB], HG, nacc);
-        }
-        if (mask & (1u << MB_TERM_CROSS)) {
-          if (WP)
-            e[MB_TERM_CROSS] += cross_term<T, false, true>(sP, 0, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, cot[MB_TERM_CROSS], HG, pacc);
-          else
-            e[MB_TERM_CROSS] += cross_term<T, false, false>(sP, 0, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, cot[MB_TERM_CROSS], HG, nacc);
-        }
+        if (WP)
+          e[MB_TERM_HB] += hb_term<T, false, true>(sP, 0, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, tab, cot[MB_TERM_HB], HG, pacc);
+        else
+          e[MB_TERM_HB] += hb_term<T, false, false>(sP, 0, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, tab, cot[MB_TERM_HB], HG, nacc);
         if (threadIdx.x == 0) ctr[1] = n_bp - cnt;
         __syncthreads();
         MB_TICK(5)
         continue;
       }
+      if (n_cr >= kFB || (flush && n_cr > 0)) {
+        // ---------------- phase 3b: cross stacking on the CR queue
+        const int cnt = n_cr >= kFB ? kFB : n_cr;
+        const int t = threadIdx.x;
+        const bool valid = t < cnt;
+        const uint32_t pk = valid ? qCR[n_cr - cnt + t] : 0u;
+        const int i = pk & 0xffff, j = pk >> 16;
+        const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
+        const V3<T> d = disp(site(nj, g.base, T(0), T(0)), site(ni, g.base, T(0), T(0)), M.box);
+        const T r = sqrt(dot(d, d));
+        const bool in_cr = valid && sP[MB_P_CROSS_RCLOW] < r && r < sP[MB_P_CROSS_RCHIGH];
+        const V3<T> dh = (valid && r > T(0)) ? (T(1) / r) * d : v3<T>(0, 0, 0);
+        HbAngles<T> A;
+        A.ready = false;
+        HbGrad<T> HG;
+        if (WP)
+          e[MB_TERM_CROSS] += cross_term<T, false, true>(sP, 0, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, cot[MB_TERM_CROSS], HG, pacc);
+        else
+          e[MB_TERM_CROSS] += cross_term<T, false, false>(sP, 0, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, cot[MB_TERM_CROSS], HG, nacc);
+        if (threadIdx.x == 0) ctr[4] = n_cr - cnt;
+        __syncthreads();
+        MB_TICK(7)
+        continue;
+      }
       if (n_cx >= kFB || (flush && n_cx > 0)) {
-        // ---------------- phase 3b: coaxial stacking on the CX queue
+        // ---------------- phase 3c: coaxial stacking on the CX queue
         const int cnt = n_cx >= kFB ? kFB : n_cx;
         const int t = threadIdx.x;
         const bool valid = t < cnt;
@@ -768,10 +810,10 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
           e[MB_TERM_UEXC] += ex;
         }
         const T r2 = dot(d_base, d_base);
-        bool to_bp = valid && bp_hi > T(0) && r2 > bp_lo * bp_lo && r2 < bp_hi * bp_hi;
-        // radial window passed: cheap cosine tests of the three plain angles decide whether the six-acos evaluation can
-        // be non-zero at all (most pairs inside the window have the wrong orientation)
-        if (to_bp) to_bp = bp_screen(sP, sWin, mask, d_base, r2, ni.a1, nj.a1, (sF[i] & 3) * 4 + (sF[j] & 3));
+        unsigned to_bp = (valid && bp_hi > T(0) && r2 > bp_lo * bp_lo && r2 < bp_hi * bp_hi) ? 1u : 0u;
+        // radial window passed: cheap cosine tests of the angles decide whether the six-acos evaluations can be non-zero at
+        // all (most pairs inside the window have the wrong orientation) -- bit 0 hydrogen bonding, bit 1 cross stacking
+        if (to_bp) to_bp = bp_screen2(sP, sWin, mask, d_base, r2, ni.a1, nj.a1, ni.a3, nj.a3, (sF[i] & 3) * 4 + (sF[j] & 3));
         bool to_cx = false;
         if (mask & (1u << MB_TERM_COAX)) {
           const V3<T> ds = disp(site(nj, g.stack, T(0), T(0)), site(ni, g.stack, T(0), T(0)), M.box);
@@ -779,8 +821,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
           to_cx = valid && s2 > sP[MB_P_COAX_RCLOW] * sP[MB_P_COAX_RCLOW] && s2 < sP[MB_P_COAX_RCHIGH] * sP[MB_P_COAX_RCHIGH];
         }
         if (threadIdx.x == 0) ctr[0] = n_sr - cnt;
-        q_push(qBP, &ctr[1], wcnt, to_bp, pk);
-        q_push(qCX, &ctr[2], wcnt, to_cx, pk);
+        q_push3(qBP, &ctr[1], (to_bp & 1u) != 0u, qCR, &ctr[4], (to_bp & 2u) != 0u, qCX, &ctr[2], to_cx, wcnt, pk);
         MB_TICK(4)
         continue;
       }
@@ -967,15 +1008,15 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
 #ifdef MB_FRAME_PROFILE
   if (threadIdx.x == 0 && blockIdx.x == 0)
     printf("frame-kernel cycles: stage+bonded %lld | cells %lld | producer %lld (%d steps) | phase1 %lld (%d) | phase2 %lld (%d) | "
-           "hb+cross %lld (%d) | coax %lld (%d)\n", prof_t[0], prof_t[1], prof_t[2], prof_n[2], prof_t[3], prof_n[3], prof_t[4],
-           prof_n[4], prof_t[5], prof_n[5], prof_t[6], prof_n[6]);
+           "hb %lld (%d) | cross %lld (%d) | coax %lld (%d)\n", prof_t[0], prof_t[1], prof_t[2], prof_n[2], prof_t[3], prof_n[3], prof_t[4],
+           prof_n[4], prof_t[5], prof_n[5], prof_t[7], prof_n[7], prof_t[6], prof_n[6]);
 #endif
   // ---------------------------------------------------------------- flush
   if (WP) {
 #pragma unroll
-    for (int k = 0; k < 5; ++k) block_sum_to(dacc.r[k], &sAcc[MB_P_DEBYE_KAPPA + k]);
+    for (int k = 0; k < 5; ++k) block_sum_to(dacc.r[k], &sacc.sh[MB_P_DEBYE_KAPPA + k]);  // this warp's copy of the image: no 16-way CAS contention
 #pragma unroll
-    for (int k = 0; k < 17; ++k) block_sum_to(xacc.r[k], &sAcc[MB_P_UEXC_EPS + k]);
+    for (int k = 0; k < 17; ++k) block_sum_to(xacc.r[k], &sacc.sh[MB_P_UEXC_EPS + k]);
   }
 #pragma unroll
   for (int t = 0; t < MB_N_TERMS; ++t) {
@@ -1032,7 +1073,7 @@ template <class T>
 static bool pick_layout(const EnergyDev<T>& a, bool wp, bool* cache_back, FrameSmem* L) {
   const bool cells = a.all_pairs_cutoff > T(0);
   if ((long long)a.n * 11 * (long long)sizeof(T) > 227 * 1024) return false;
-  if (cells && (size_t)a.n * 4 > sizeof(uint32_t) * (kSrCap + 2 * kQCap)) return false;  // sCell aliases the SR/BP/CX queues
+  if (cells && (size_t)a.n * 4 > sizeof(uint32_t) * (kSrCap + 3 * kQCap)) return false;  // sCell aliases the SR/HB/CR/CX queues
   for (int cb = 1; cb >= 0; --cb) {
     for (int rows = wp ? kFWarps : 1; rows >= 1; rows >>= 1) {  // as many image copies as fit (16 = one per warp)
       *L = frame_smem_layout<T>(a.n, wp, cb != 0, cells, rows);
