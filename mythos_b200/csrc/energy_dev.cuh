@@ -143,6 +143,49 @@ struct SmemAcc {
 };
 
 
+// Group form for the warp-reducing accumulator: a reduce-scatter butterfly.  In the first rounds every lane keeps half of
+// its values and hands the other half to its partner, so N values cost N - 1 + (5 - log2 N) shuffle-adds instead of
+// 5 N, and the N sums end up on N different lanes, which issue their shared-memory atomics in ONE instruction.
+template <class T, int N>
+__device__ __forceinline__ void acc_add_group(SmemAcc<T>& acc, int bank, const int (&idx)[N], const T (&v)[N]) {
+  static_assert(N >= 1 && N <= 8, "group of at most eight values");
+  if (acc.per_lane) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc.add(bank, idx[k], v[k]);
+    return;
+  }
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < N; ++k) any |= (v[k] != T(0));
+  if (!__any_sync(kFull, any)) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int W = N > 4 ? 8 : (N > 2 ? 4 : (N > 1 ? 2 : 1));  // padded width
+  T a[W];
+#pragma unroll
+  for (int k = 0; k < W; ++k) a[k] = k < N ? v[k] : T(0);
+  int p = 0;  // which value this lane ends up holding
+  int o = 16;
+#pragma unroll
+  for (int w = W; w > 1; w >>= 1, o >>= 1) {
+    const bool hi = (lane & o) != 0;
+#pragma unroll
+    for (int k = 0; k < w / 2; ++k) {
+      const T send = hi ? a[k] : a[k + w / 2];
+      const T keep = hi ? a[k + w / 2] : a[k];
+      a[k] = keep + __shfl_xor_sync(kFull, send, o);
+    }
+    p = 2 * p + (hi ? 1 : 0);
+  }
+  T t = a[0];
+  for (; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+  // the lanes whose low bits (below the rounds that split) are zero hold the finished sums
+  constexpr int kLow = 32 / W;  // lanes per value
+  int id = idx[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k) id = (p == k) ? idx[k] : id;
+  if ((lane & (kLow - 1)) == 0 && p < N && t != T(0)) atomicAdd(&acc.sh[id], t);
+}
+
 // Parameter-gradient accumulator in GLOBAL memory, one slot per (parameter, lane) of this CTA's scratch image: every lane
 // adds its own contribution with a fire-and-forget RED.ADD (no warp reduction, no shuffles, no dependent chain); the 32
 // lane slots of a parameter are summed once per frame.  The image is L2-resident (232 x 32 reals per resident CTA).

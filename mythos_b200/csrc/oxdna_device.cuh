@@ -178,6 +178,15 @@ MB_HD V3<T> disp(const V3<T>& a, const V3<T>& b, const T box[3]) {
 // accumulator (only the differentiable slots; the branch limits r_low, r_high, delta_star, x_star carry no
 // gradient because they only appear in where-conditions).
 // Parameter accumulator concept:  acc.add(bank_offset, index, value)  -- warp-convergent on the device.
+// Group form: N (<= 8) values with their indices at once.  Accumulators that reduce across the warp overload it so that
+// the N values share the shuffle rounds (energy_dev.cuh: SmemAcc); every other accumulator takes N single adds.
+template <class Acc, class T, int N>
+MB_HD void acc_add_group(Acc& acc, int bank, const int (&idx)[N], const T (&v)[N]) {
+#ifdef __CUDA_ARCH__
+  #pragma unroll
+#endif
+  for (int k = 0; k < N; ++k) acc.add(bank, idx[k], v[k]);
+}
 
 template <class T>
 MB_HD T clamp1(T x) {
@@ -233,13 +242,9 @@ MB_HD void f1_par(T r, const T* p, T coef, int bank, int base, Acc& acc) {
       g_rch = coef * T(2) * p[8] * t;
     }
   }
-  acc.add(bank, base + 2, g_rcl);
-  acc.add(bank, base + 3, g_rch);
-  acc.add(bank, base + 4, g_a);
-  acc.add(bank, base + 5, g_r0);
-  acc.add(bank, base + 6, g_rc);
-  acc.add(bank, base + 7, g_bl);
-  acc.add(bank, base + 8, g_bh);
+  const int idx[7] = {base + 2, base + 3, base + 4, base + 5, base + 6, base + 7, base + 8};
+  const T val[7] = {g_rcl, g_rch, g_a, g_r0, g_rc, g_bl, g_bh};
+  acc_add_group(acc, bank, idx, val);
 }
 
 // f2 block layout: [r_low, r_high, r_c_low, r_c_high, k, r0, r_c, b_low, b_high]
@@ -282,13 +287,9 @@ MB_HD void f2_par(T r, const T* p, T coef, int bank, int base, Acc& acc) {
       g_rch = coef * T(2) * p[4] * p[8] * t;
     }
   }
-  acc.add(bank, base + 2, g_rcl);
-  acc.add(bank, base + 3, g_rch);
-  acc.add(bank, base + 4, g_k);
-  acc.add(bank, base + 5, g_r0);
-  acc.add(bank, base + 6, g_rc);
-  acc.add(bank, base + 7, g_bl);
-  acc.add(bank, base + 8, g_bh);
+  const int idx[7] = {base + 2, base + 3, base + 4, base + 5, base + 6, base + 7, base + 8};
+  const T val[7] = {g_rcl, g_rch, g_k, g_r0, g_rc, g_bl, g_bh};
+  acc_add_group(acc, bank, idx, val);
 }
 
 // f3 block layout: [r_star, sigma, b, r_c]; eps separate
@@ -322,10 +323,9 @@ MB_HD void f3_par(T r, const T* p, T eps, T coef, int bank, int base, int eps_id
       g_rc = coef * T(2) * eps * p[2] * t;
     }
   }
-  acc.add(bank, eps_idx, g_eps);
-  acc.add(bank, base + 1, g_sig);
-  acc.add(bank, base + 2, g_b);
-  acc.add(bank, base + 3, g_rc);
+  const int idx[4] = {eps_idx, base + 1, base + 2, base + 3};
+  const T val[4] = {g_eps, g_sig, g_b, g_rc};
+  acc_add_group(acc, bank, idx, val);
 }
 
 // f4 block layout: [theta0, delta_star, delta_c, a, b]
@@ -378,10 +378,16 @@ MB_HD void f4_par_add(T th, const T* p, T coef, T g[4]) {
 }
 template <class T, class Acc>
 MB_HD void f4_par_flush(const T g[4], int bank, int base, Acc& acc) {
-  acc.add(bank, base + 0, g[0]);
-  acc.add(bank, base + 2, g[1]);
-  acc.add(bank, base + 3, g[2]);
-  acc.add(bank, base + 4, g[3]);
+  const int idx[4] = {base + 0, base + 2, base + 3, base + 4};
+  const T val[4] = {g[0], g[1], g[2], g[3]};
+  acc_add_group(acc, bank, idx, val);
+}
+// two f4 blocks at once (eight values share the reduction rounds)
+template <class T, class Acc>
+MB_HD void f4_par_flush2(const T ga[4], int base_a, const T gb[4], int base_b, int bank, Acc& acc) {
+  const int idx[8] = {base_a + 0, base_a + 2, base_a + 3, base_a + 4, base_b + 0, base_b + 2, base_b + 3, base_b + 4};
+  const T val[8] = {ga[0], ga[1], ga[2], ga[3], gb[0], gb[1], gb[2], gb[3]};
+  acc_add_group(acc, bank, idx, val);
 }
 
 // f5 block layout: [x_star, x_c, a, b]
@@ -412,9 +418,9 @@ MB_HD void f5_par(T x, const T* p, T coef, int bank, int base, Acc& acc) {
       g_xc = coef * T(2) * p[3] * t;
     }
   }
-  acc.add(bank, base + 1, g_xc);
-  acc.add(bank, base + 2, g_a);
-  acc.add(bank, base + 3, g_b);
+  const int idx[3] = {base + 1, base + 2, base + 3};
+  const T val[3] = {g_xc, g_a, g_b};
+  acc_add_group(acc, bank, idx, val);
 }
 
 // f6 block layout: [a, b]
@@ -489,11 +495,9 @@ MB_HD T fene_term(const T* P, int bank, bool act, T r, T cot, T& dEdr, Acc& acc)
     }
   }
   if (WP) {
-    acc.add(bank, MB_P_FENE_EPS, g_eps);
-    acc.add(bank, MB_P_FENE_R0, g_r0);
-    acc.add(bank, MB_P_FENE_DELTA, g_dl);
-    acc.add(bank, MB_P_FENE_FMAX, g_fmax);
-    acc.add(bank, MB_P_FENE_FINF, g_finf);
+    const int idx[5] = {MB_P_FENE_EPS, MB_P_FENE_R0, MB_P_FENE_DELTA, MB_P_FENE_FMAX, MB_P_FENE_FINF};
+    const T val[5] = {g_eps, g_r0, g_dl, g_fmax, g_finf};
+    acc_add_group(acc, bank, idx, val);
   }
   return e;
 }
@@ -756,10 +760,13 @@ MB_HD T hb_term(const T* P, int bank, bool act, T r, const V3<T>& dh, const V3<T
   if (WP) {
     f1_par(r, P + MB_P_HB_RLOW, othr, bank, MB_P_HB_RLOW, acc);
     #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      T g[4] = {T(0), T(0), T(0), T(0)};
-      if (nz) f4_par_add(A.th[k], P + b4[k], oth[k], g);
-      f4_par_flush(g, bank, b4[k], acc);
+    for (int k = 0; k < 6; k += 2) {
+      T ga[4] = {T(0), T(0), T(0), T(0)}, gb[4] = {T(0), T(0), T(0), T(0)};
+      if (nz) {
+        f4_par_add(A.th[k], P + b4[k], oth[k], ga);
+        f4_par_add(A.th[k + 1], P + b4[k + 1], oth[k + 1], gb);
+      }
+      f4_par_flush2(ga, b4[k], gb, b4[k + 1], bank, acc);
     }
     if (!has_w_ext) acc.add_scatter(bank, MB_P_HB_W00 + tab, nz ? cot * e / w : T(0), nz);
   }
@@ -832,13 +839,17 @@ MB_HD T cross_term(const T* P, int bank, int form, bool act, T r, const V3<T>& d
   if (WP) {
     f2_par(r, P + MB_P_CROSS_RLOW, othr, bank, MB_P_CROSS_RLOW, acc);
     #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      T g[4] = {T(0), T(0), T(0), T(0)};
-      if (nz && !(k == 3 && rna)) {
-        f4_par_add(A.th[k], P + b4[k], oth[k], g);
-        if (k >= 3) f4_par_add(pi - A.th[k], P + b4[k], oth[k], g);
+    for (int k = 0; k < 6; k += 2) {
+      T g2[2][4] = {{T(0), T(0), T(0), T(0)}, {T(0), T(0), T(0), T(0)}};
+      #pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int kk = k + h;
+        if (nz && !(kk == 3 && rna)) {
+          f4_par_add(A.th[kk], P + b4[kk], oth[kk], g2[h]);
+          if (kk >= 3) f4_par_add(pi - A.th[kk], P + b4[kk], oth[kk], g2[h]);
+        }
       }
-      f4_par_flush(g, bank, b4[k], acc);
+      f4_par_flush2(g2[0], b4[k], g2[1], b4[k + 1], bank, acc);
     }
   }
   return e;
@@ -976,14 +987,16 @@ MB_HD T coax_term(const T* P, int bank, int form, bool act, const V3<T>& ds, T r
       }
     }
     f4_par_flush(g, bank, b4[1], acc);
-    #pragma unroll
-    for (int k = 2; k < 4; ++k) {
-      g[0] = g[1] = g[2] = g[3] = T(0);
-      if (nz) {
-        f4_par_add(th[k], P + b4[k], oth[k], g);
-        f4_par_add(pi - th[k], P + b4[k], oth[k], g);
+    {
+      T g2[2][4] = {{T(0), T(0), T(0), T(0)}, {T(0), T(0), T(0), T(0)}};
+      #pragma unroll
+      for (int k = 2; k < 4; ++k) {
+        if (nz) {
+          f4_par_add(th[k], P + b4[k], oth[k], g2[k - 2]);
+          f4_par_add(pi - th[k], P + b4[k], oth[k], g2[k - 2]);
+        }
       }
-      f4_par_flush(g, bank, b4[k], acc);
+      f4_par_flush2(g2[0], b4[2], g2[1], b4[3], bank, acc);
     }
     f5_par(cphi[0], P + MB_P_COAX_PHI3_XSTAR, (nz && !d2form) ? oth[4] : T(0), bank, MB_P_COAX_PHI3_XSTAR, acc);
     f5_par(cphi[1], P + MB_P_COAX_PHI4_XSTAR, (nz && !d2form) ? oth[5] : T(0), bank, MB_P_COAX_PHI4_XSTAR, acc);
@@ -1026,10 +1039,9 @@ MB_HD T debye_term(const T* P, int bank, bool act, const V3<T>& d, T m, T cot, V
     }
   }
   if (WP) {
-    acc.add(bank, MB_P_DEBYE_KAPPA, g_k);
-    acc.add(bank, MB_P_DEBYE_PREF, g_A);
-    acc.add(bank, MB_P_DEBYE_SMOOTH, g_S);
-    acc.add(bank, MB_P_DEBYE_RCUT, g_rc);
+    const int idx[4] = {MB_P_DEBYE_KAPPA, MB_P_DEBYE_PREF, MB_P_DEBYE_SMOOTH, MB_P_DEBYE_RCUT};
+    const T val[4] = {g_k, g_A, g_S, g_rc};
+    acc_add_group(acc, bank, idx, val);
   }
   return e;
 }
