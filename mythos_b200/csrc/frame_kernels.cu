@@ -57,7 +57,7 @@ constexpr int kExcl = 2;                // bonded partners per nucleotide (as th
 struct FrameSmem {
   // byte offsets into dynamic shared memory; computed on the host and passed as a kernel parameter so that the
   // kernel re-reads them from the constant bank instead of rematerialising the whole chain under register pressure
-  unsigned c, q, back, p, acc, e, flags, q_nl, q_sr, q_bp, q_cr, q_cx, wcnt, ctr, cstart, corder, excl, grid, win, bar, total;
+  unsigned c, q, back, p, acc, e, flags, q_nl, q_sr, q_bp, q_cr, q_cx, wcnt, ctr, cstart, corder, excl, grid, win, cot, bar, total;
   int acc_rows;  // copies of the parameter-gradient image: warps are spread over them so that their shared-memory atomics do not collide
 };
 template <class T>
@@ -89,6 +89,7 @@ inline FrameSmem frame_smem_layout(int n, bool wp, bool cache_back, bool cells, 
   L.excl = take(cells ? sizeof(uint16_t) * kExcl * n : 0);
   L.grid = take(sizeof(T) * 8 + sizeof(int) * 8);
   L.win = take(sizeof(CosWin<T>) * 9);
+  L.cot = take(sizeof(T) * MB_N_TERMS);  // the frame's cotangent row (shared: eight registers fewer live across the phases)
   L.bar = take(sizeof(uint64_t));  // mbarrier of the bulk (TMA) frame staging
   L.total = off;
   return L;
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   uint16_t* sCorder = reinterpret_cast<uint16_t*>(smem + L.corder);
   uint16_t* sExcl = reinterpret_cast<uint16_t*>(smem + L.excl);
   CellGrid<T>* grid = reinterpret_cast<CellGrid<T>*>(smem + L.grid);
+  T* sCot = reinterpret_cast<T*>(smem + L.cot);
   CosWin<T>* sWin = reinterpret_cast<CosWin<T>*>(smem + L.win);  // angular pre-screen of the hydrogen-bond / cross queue
   int* sCursor = reinterpret_cast<int*>(smem + L.q_nl);  // per-cell fill cursors; aliases queue NL, used only during the cell build
 
@@ -422,6 +424,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   if (WP)
     for (int k = threadIdx.x; k < MB_P_COUNT * L.acc_rows; k += kFB) sAcc[k] = T(0);
   if (threadIdx.x < 8) ctr[threadIdx.x] = 0;
+  if (threadIdx.x < MB_N_TERMS) sCot[threadIdx.x] = a.cot ? a.cot[(long long)frame * MB_N_TERMS + threadIdx.x] : T(1);
   __syncthreads();
 
   if (CACHE_BACK) {
@@ -433,9 +436,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
       sB[3 * i + 2] = b.z;
     }
   }
-  T cot[MB_N_TERMS];
-#pragma unroll
-  for (int t = 0; t < MB_N_TERMS; ++t) cot[t] = a.cot ? a.cot[(long long)frame * MB_N_TERMS + t] : T(1);
+  const T* cot = sCot;
   T e[MB_N_TERMS];
 #pragma unroll
   for (int t = 0; t < MB_N_TERMS; ++t) e[t] = T(0);
@@ -468,10 +469,8 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
 
   MB_TICK(0)  // staging + bonded
   // ---------------------------------------------------------------- unbonded pairs
-  RegAcc<T, MB_P_DEBYE_KAPPA, 5> dacc;
-  RegAcc<T, MB_P_UEXC_EPS, 17> xacc;
-  dacc.zero();
-  xacc.zero();
+  // (parameter gradients of every phase leave per batch through the grouped warp reduction of SmemAcc: accumulators held in
+  // registers across the whole scheduler loop -- 17 + 5 doubles -- were what pushed the loop's state into local memory)
   const bool want_debye = (mask & (1u << MB_TERM_DEBYE)) && F.has_debye;
   const bool want_sr = (mask & ((1u << MB_TERM_UEXC) | (1u << MB_TERM_HB) | (1u << MB_TERM_CROSS) | (1u << MB_TERM_COAX))) != 0;
   // short-range centre cutoff: the widest site-pair cutoff plus both site offsets
@@ -797,10 +796,10 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
           V3<T> gs;
           T ex = T(0);
           if (WP) {
-            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BACKBONE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_j, back_i, M.box), c, gs, xacc);
-            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BASE_RSTAR, MB_P_UEXC_EPS, valid, d_base, c, gs, xacc);
-            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BACK_BASE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_i, base_j, M.box), c, gs, xacc);
-            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BASE_BACK_RSTAR, MB_P_UEXC_EPS, valid, disp(base_i, back_j, M.box), c, gs, xacc);
+            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BACKBONE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_j, back_i, M.box), c, gs, pacc);
+            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BASE_RSTAR, MB_P_UEXC_EPS, valid, d_base, c, gs, pacc);
+            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BACK_BASE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_i, base_j, M.box), c, gs, pacc);
+            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BASE_BACK_RSTAR, MB_P_UEXC_EPS, valid, disp(base_i, back_j, M.box), c, gs, pacc);
           } else {
             ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BACKBONE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_j, back_i, M.box), c, gs, nacc);
             ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BASE_RSTAR, MB_P_UEXC_EPS, valid, d_base, c, gs, nacc);
@@ -830,6 +829,8 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         // has only 16 warps, so latency is hidden inside the thread)
         const int cnt = n_nl >= kU1 * kFB ? kU1 * kFB : n_nl;
         const int first = n_nl - cnt;
+        RegAcc<T, MB_P_DEBYE_KAPPA, 5> dacc;  // the batch's kU1 pairs of this thread; reduced once per batch below
+        dacc.zero();
 #pragma unroll
         for (int u = 0; u < kU1; ++u) {
           const int t = threadIdx.x + u * kFB;
@@ -850,6 +851,12 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
             e[MB_TERM_DEBYE] += debye_term<T, false, true>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, dacc);
           else
             e[MB_TERM_DEBYE] += debye_term<T, false, false>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, nacc);
+        }
+        if (WP) {
+          const int idx[4] = {MB_P_DEBYE_KAPPA, MB_P_DEBYE_PREF, MB_P_DEBYE_SMOOTH, MB_P_DEBYE_RCUT};
+          const T val[4] = {dacc.r[MB_P_DEBYE_KAPPA - MB_P_DEBYE_KAPPA], dacc.r[MB_P_DEBYE_PREF - MB_P_DEBYE_KAPPA],
+                            dacc.r[MB_P_DEBYE_SMOOTH - MB_P_DEBYE_KAPPA], dacc.r[MB_P_DEBYE_RCUT - MB_P_DEBYE_KAPPA]};
+          acc_add_group(pacc, 0, idx, val);
         }
         __syncthreads();  // the batch has been read before the counter moves
         if (threadIdx.x == 0) ctr[3] = first;
@@ -1012,12 +1019,6 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
            prof_n[4], prof_t[5], prof_n[5], prof_t[7], prof_n[7], prof_t[6], prof_n[6]);
 #endif
   // ---------------------------------------------------------------- flush
-  if (WP) {
-#pragma unroll
-    for (int k = 0; k < 5; ++k) block_sum_to(dacc.r[k], &sacc.sh[MB_P_DEBYE_KAPPA + k]);  // this warp's copy of the image: no 16-way CAS contention
-#pragma unroll
-    for (int k = 0; k < 17; ++k) block_sum_to(xacc.r[k], &sacc.sh[MB_P_UEXC_EPS + k]);
-  }
 #pragma unroll
   for (int t = 0; t < MB_N_TERMS; ++t) {
     T v = e[t];
