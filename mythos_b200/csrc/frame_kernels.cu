@@ -210,6 +210,14 @@ __device__ __forceinline__ Nuc<T> smem_nuc(const T* sC, const T* sQ, int i) {
   return n;
 }
 
+// a phase's energy of this warp's pairs -> this warp's row of the per-warp energy table (the warp owns the row: plain add)
+template <class T>
+__device__ __forceinline__ void warp_energy_to(T v, T* row_entry) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  if ((threadIdx.x & 31) == 0) *row_entry += v;
+}
+
 template <class T>
 __device__ __forceinline__ void block_sum_to(T v, T* dst) {
 #pragma unroll
@@ -424,6 +432,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   if (WP)
     for (int k = threadIdx.x; k < MB_P_COUNT * L.acc_rows; k += kFB) sAcc[k] = T(0);
   if (threadIdx.x < 8) ctr[threadIdx.x] = 0;
+  if (threadIdx.x < MB_N_TERMS * kFWarps) sE[threadIdx.x] = T(0);
   if (threadIdx.x < MB_N_TERMS) sCot[threadIdx.x] = a.cot ? a.cot[(long long)frame * MB_N_TERMS + threadIdx.x] : T(1);
   __syncthreads();
 
@@ -437,9 +446,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
     }
   }
   const T* cot = sCot;
-  T e[MB_N_TERMS];
-#pragma unroll
-  for (int t = 0; t < MB_N_TERMS; ++t) e[t] = T(0);
+  T* const eW = sE + warp * MB_N_TERMS;  // this warp's energy row: every phase adds its batch's energy here (no registers held)
   // warp-reduced shared-memory image: the bonded phase (a burst of ~60 parameters x 4 batches from every thread at once
   // throttles the load/store unit when it goes out as RED.ADDs: measured) -- and every phase when MB_FRAME_GLOBACC is 0
   SmemAcc<T> sacc{sAcc + ((warp * L.acc_rows) / kFWarps) * MB_P_COUNT, false};  // this warp's copy of the image
@@ -451,6 +458,9 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
 
   // ---------------------------------------------------------------- phase B: bonded pairs
   if (mask & MB_BONDED_TERMS) {
+    T e[MB_N_TERMS];
+#pragma unroll
+    for (int t = 0; t < MB_N_TERMS; ++t) e[t] = T(0);
     for (int base = 0; base < a.n_bonded; base += kFB) {
       const int k = base + threadIdx.x;
       const bool valid = k < a.n_bonded;
@@ -465,6 +475,9 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
       else
         bonded_pair<T, false, false>(M, sP, valid, ni, nj, sF[i] & 3, sF[j] & 3, 1, 1, 1, 1, mask, cot, e, G0, G1, nacc);
     }
+    warp_energy_to(e[MB_TERM_FENE], &eW[MB_TERM_FENE]);
+    warp_energy_to(e[MB_TERM_BEXC], &eW[MB_TERM_BEXC]);
+    warp_energy_to(e[MB_TERM_STACK], &eW[MB_TERM_STACK]);
   }
 
   MB_TICK(0)  // staging + bonded
@@ -519,7 +532,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
           hi[d] = fmax(hi[d], x);
         }
     }
-    T* red = sE;  // scratch: 6 x kFWarps reals fit in the 8 x kFWarps energy buffer
+    T* red = reinterpret_cast<T*>(smem + L.q_nl);  // scratch: 6 x kFWarps reals in the (still empty) DB queue; read back before the cell cursors, which alias it, are written
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       T l = lo[d], h = hi[d];
@@ -725,10 +738,12 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         A.ready = false;
         HbGrad<T> HG;
         const int tab = (sF[i] & 3) * 4 + (sF[j] & 3);
+        T ev;
         if (WP)
-          e[MB_TERM_HB] += hb_term<T, false, true>(sP, 0, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, tab, cot[MB_TERM_HB], HG, pacc);
+          ev = hb_term<T, false, true>(sP, 0, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, tab, cot[MB_TERM_HB], HG, pacc);
         else
-          e[MB_TERM_HB] += hb_term<T, false, false>(sP, 0, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, tab, cot[MB_TERM_HB], HG, nacc);
+          ev = hb_term<T, false, false>(sP, 0, in_hb, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, tab, cot[MB_TERM_HB], HG, nacc);
+        warp_energy_to(ev, &eW[MB_TERM_HB]);
         if (threadIdx.x == 0) ctr[1] = n_bp - cnt;
         __syncthreads();
         MB_TICK(5)
@@ -749,10 +764,12 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         HbAngles<T> A;
         A.ready = false;
         HbGrad<T> HG;
+        T ev;
         if (WP)
-          e[MB_TERM_CROSS] += cross_term<T, false, true>(sP, 0, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, cot[MB_TERM_CROSS], HG, pacc);
+          ev = cross_term<T, false, true>(sP, 0, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, cot[MB_TERM_CROSS], HG, pacc);
         else
-          e[MB_TERM_CROSS] += cross_term<T, false, false>(sP, 0, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, cot[MB_TERM_CROSS], HG, nacc);
+          ev = cross_term<T, false, false>(sP, 0, F.cross_form, in_cr, r, dh, ni.a1, nj.a1, ni.a3, nj.a3, A, cot[MB_TERM_CROSS], HG, nacc);
+        warp_energy_to(ev, &eW[MB_TERM_CROSS]);
         if (threadIdx.x == 0) ctr[4] = n_cr - cnt;
         __syncthreads();
         MB_TICK(7)
@@ -771,10 +788,12 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         const bool in = valid && sP[MB_P_COAX_RCLOW] < rs && rs < sP[MB_P_COAX_RCHIGH];
         const V3<T> db = disp(site(nj, g.back[0], g.back[1], g.back[2]), site(ni, g.back[0], g.back[1], g.back[2]), M.box);
         CoaxGrad<T> CG;
+        T ev;
         if (WP)
-          e[MB_TERM_COAX] += coax_term<T, false, true>(sP, 0, F.coax_form, in, ds, rs, db, ni.a1, nj.a1, ni.a3, nj.a3, cot[MB_TERM_COAX], CG, pacc);
+          ev = coax_term<T, false, true>(sP, 0, F.coax_form, in, ds, rs, db, ni.a1, nj.a1, ni.a3, nj.a3, cot[MB_TERM_COAX], CG, pacc);
         else
-          e[MB_TERM_COAX] += coax_term<T, false, false>(sP, 0, F.coax_form, in, ds, rs, db, ni.a1, nj.a1, ni.a3, nj.a3, cot[MB_TERM_COAX], CG, nacc);
+          ev = coax_term<T, false, false>(sP, 0, F.coax_form, in, ds, rs, db, ni.a1, nj.a1, ni.a3, nj.a3, cot[MB_TERM_COAX], CG, nacc);
+        warp_energy_to(ev, &eW[MB_TERM_COAX]);
         if (threadIdx.x == 0) ctr[2] = n_cx - cnt;
         __syncthreads();
         MB_TICK(6)
@@ -806,7 +825,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
             ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BACK_BASE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_i, base_j, M.box), c, gs, nacc);
             ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BASE_BACK_RSTAR, MB_P_UEXC_EPS, valid, disp(base_i, back_j, M.box), c, gs, nacc);
           }
-          e[MB_TERM_UEXC] += ex;
+          warp_energy_to(ex, &eW[MB_TERM_UEXC]);
         }
         const T r2 = dot(d_base, d_base);
         unsigned to_bp = (valid && bp_hi > T(0) && r2 > bp_lo * bp_lo && r2 < bp_hi * bp_hi) ? 1u : 0u;
@@ -831,6 +850,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         const int first = n_nl - cnt;
         RegAcc<T, MB_P_DEBYE_KAPPA, 5> dacc;  // the batch's kU1 pairs of this thread; reduced once per batch below
         dacc.zero();
+        T ev = T(0);
 #pragma unroll
         for (int u = 0; u < kU1; ++u) {
           const int t = threadIdx.x + u * kFB;
@@ -848,10 +868,11 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
           if (M.half_charged_ends) m = ((sF[i] & 4) ? T(0.5) : T(1)) * ((sF[j] & 4) ? T(0.5) : T(1));
           V3<T> gd;
           if (WP)
-            e[MB_TERM_DEBYE] += debye_term<T, false, true>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, dacc);
+            ev += debye_term<T, false, true>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, dacc);
           else
-            e[MB_TERM_DEBYE] += debye_term<T, false, false>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, nacc);
+            ev += debye_term<T, false, false>(sP, 0, valid, db, m, cot[MB_TERM_DEBYE], gd, nacc);
         }
+        warp_energy_to(ev, &eW[MB_TERM_DEBYE]);
         if (WP) {
           const int idx[4] = {MB_P_DEBYE_KAPPA, MB_P_DEBYE_PREF, MB_P_DEBYE_SMOOTH, MB_P_DEBYE_RCUT};
           const T val[4] = {dacc.r[MB_P_DEBYE_KAPPA - MB_P_DEBYE_KAPPA], dacc.r[MB_P_DEBYE_PREF - MB_P_DEBYE_KAPPA],
@@ -1019,13 +1040,6 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
            prof_n[4], prof_t[5], prof_n[5], prof_t[7], prof_n[7], prof_t[6], prof_n[6]);
 #endif
   // ---------------------------------------------------------------- flush
-#pragma unroll
-  for (int t = 0; t < MB_N_TERMS; ++t) {
-    T v = e[t];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-    if (lane == 0) sE[warp * MB_N_TERMS + t] = v;
-  }
 #if MB_FRAME_GLOBACC
   if (WP) __threadfence();  // this thread's RED.ADDs are performed before the barrier releases the readers below
 #endif
