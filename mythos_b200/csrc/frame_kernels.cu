@@ -54,43 +54,52 @@ constexpr int kSrCap = kFB + kFB * kSlice;        // queue SR: a phase-2 backlog
 constexpr int kMaxCells = 2048;
 constexpr int kExcl = 2;                // bonded partners per nucleotide (as the reference's (N,2) dense mask)
 
+// Shared-memory layout.  Every fixed-size array sits at a COMPILE-TIME offset in front (FixedSmem: the kernel addresses them
+// with immediates -- with run-time offsets the compiler, short of registers, re-derived these pointers from the constant
+// bank all over the phases: 7 % of the issued instructions); the arrays whose size depends on n or on the number of
+// parameter-gradient image copies follow at run-time offsets (FrameSmem, a kernel parameter).
+constexpr unsigned smem_up(size_t bytes) { return (unsigned(bytes) + 15u) & ~15u; }
+template <class T>
+struct FixedSmem {
+  static constexpr unsigned p = 0;
+  static constexpr unsigned e = p + smem_up(sizeof(T) * MB_P_COUNT);
+  static constexpr unsigned q_nl = e + smem_up(sizeof(T) * MB_N_TERMS * kFWarps);
+  static constexpr unsigned q_sr = q_nl + smem_up(sizeof(uint32_t) * kNlCap);
+  static constexpr unsigned q_bp = q_sr + smem_up(sizeof(uint32_t) * kSrCap);
+  static constexpr unsigned q_cr = q_bp + smem_up(sizeof(uint32_t) * kQCap);
+  static constexpr unsigned q_cx = q_cr + smem_up(sizeof(uint32_t) * kQCap);
+  static constexpr unsigned wcnt = q_cx + smem_up(sizeof(uint32_t) * kQCap);
+  static constexpr unsigned ctr = wcnt + smem_up(sizeof(int) * 2 * (kFWarps + 1));
+  static constexpr unsigned grid = ctr + smem_up(sizeof(int) * 8);
+  static constexpr unsigned win = grid + smem_up(sizeof(T) * 8 + sizeof(int) * 8);
+  static constexpr unsigned cot = win + smem_up(sizeof(T) * 2 * 9);  // nine CosWin<T>
+  static constexpr unsigned cst = cot + smem_up(sizeof(T) * MB_N_TERMS);  // loop-invariant scalars (squared cutoffs / windows)
+  static constexpr unsigned bar = cst + smem_up(sizeof(T) * 8);           // mbarrier of the bulk (TMA) frame staging
+  static constexpr unsigned acc = bar + smem_up(sizeof(uint64_t));        // acc_rows copies of the parameter-gradient image
+};
 struct FrameSmem {
-  // byte offsets into dynamic shared memory; computed on the host and passed as a kernel parameter so that the
-  // kernel re-reads them from the constant bank instead of rematerialising the whole chain under register pressure
-  unsigned c, q, back, p, acc, e, flags, q_nl, q_sr, q_bp, q_cr, q_cx, wcnt, ctr, cstart, corder, excl, grid, win, cot, bar, total;
+  // byte offsets into dynamic shared memory of the run-time sized arrays; computed on the host, passed as a kernel parameter
+  unsigned c, q, back, flags, cstart, corder, excl, total;
   int acc_rows;  // copies of the parameter-gradient image: warps are spread over them so that their shared-memory atomics do not collide
 };
 template <class T>
 inline FrameSmem frame_smem_layout(int n, bool wp, bool cache_back, bool cells, int acc_rows) {
   FrameSmem L;
-  unsigned off = 0;
+  unsigned off = FixedSmem<T>::acc;
   auto take = [&](size_t bytes) {
     unsigned o = off;
-    off += (unsigned(bytes) + 15u) & ~15u;
+    off += smem_up(bytes);
     return o;
   };
+  L.acc_rows = acc_rows;
+  take(wp ? sizeof(T) * MB_P_COUNT * acc_rows : 0);
   L.c = take(sizeof(T) * 3 * n);
   L.q = take(sizeof(T) * 4 * n);
   L.back = take(cache_back ? sizeof(T) * 3 * n : 0);
-  L.p = take(sizeof(T) * MB_P_COUNT);
-  L.acc_rows = acc_rows;
-  L.acc = take(wp ? sizeof(T) * MB_P_COUNT * acc_rows : 0);
-  L.e = take(sizeof(T) * MB_N_TERMS * kFWarps);
   L.flags = take(n);
-  L.q_nl = take(sizeof(uint32_t) * kNlCap);
-  L.q_sr = take(sizeof(uint32_t) * kSrCap);
-  L.q_bp = take(sizeof(uint32_t) * kQCap);
-  L.q_cr = take(sizeof(uint32_t) * kQCap);
-  L.q_cx = take(sizeof(uint32_t) * kQCap);
-  L.wcnt = take(sizeof(int) * 2 * (kFWarps + 1));
-  L.ctr = take(sizeof(int) * 8);
   L.cstart = take(cells ? sizeof(int) * (kMaxCells + 1) : 0);
   L.corder = take(cells ? sizeof(uint16_t) * n : 0);
   L.excl = take(cells ? sizeof(uint16_t) * kExcl * n : 0);
-  L.grid = take(sizeof(T) * 8 + sizeof(int) * 8);
-  L.win = take(sizeof(CosWin<T>) * 9);
-  L.cot = take(sizeof(T) * MB_N_TERMS);  // the frame's cotangent row (shared: eight registers fewer live across the phases)
-  L.bar = take(sizeof(uint64_t));  // mbarrier of the bulk (TMA) frame staging
   L.total = off;
   return L;
 }
@@ -354,30 +363,32 @@ __device__ __noinline__ void frame_observables_smem(const int32_t* base_pairs, c
 template <class T, bool WP, bool CACHE_BACK, bool CELLS>
 __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, const FrameSmem L) {
   extern __shared__ __align__(16) unsigned char smem[];
+  using K = FixedSmem<T>;
   constexpr bool cells = CELLS;  // all-pairs mode (in-kernel cell list) vs an explicit pair list
   T* sC = reinterpret_cast<T*>(smem + L.c);
   T* sQ = reinterpret_cast<T*>(smem + L.q);
   T* sB = reinterpret_cast<T*>(smem + L.back);
-  T* sP = reinterpret_cast<T*>(smem + L.p);
-  T* sAcc = reinterpret_cast<T*>(smem + L.acc);
-  T* sE = reinterpret_cast<T*>(smem + L.e);
+  T* sP = reinterpret_cast<T*>(smem + K::p);
+  T* sAcc = reinterpret_cast<T*>(smem + K::acc);
+  T* sE = reinterpret_cast<T*>(smem + K::e);
   unsigned char* sF = smem + L.flags;  // bits 0-1 seq, bit 2 is_end
-  uint32_t* qNL = reinterpret_cast<uint32_t*>(smem + L.q_nl);
-  uint32_t* qSR = reinterpret_cast<uint32_t*>(smem + L.q_sr);
-  uint32_t* qBP = reinterpret_cast<uint32_t*>(smem + L.q_bp);  // hydrogen-bonding candidates
-  uint32_t* qCR = reinterpret_cast<uint32_t*>(smem + L.q_cr);  // cross-stacking candidates
-  uint32_t* qCX = reinterpret_cast<uint32_t*>(smem + L.q_cx);
-  int* wcnt = reinterpret_cast<int*>(smem + L.wcnt);
-  int* ctr = reinterpret_cast<int*>(smem + L.ctr);  // [0] n_sr [1] n_bp (hydrogen bonding) [2] n_cx [3] n_nl [4] n_cr (cross stacking) [5] too many bonds [6] more tiles
+  uint32_t* qNL = reinterpret_cast<uint32_t*>(smem + K::q_nl);
+  uint32_t* qSR = reinterpret_cast<uint32_t*>(smem + K::q_sr);
+  uint32_t* qBP = reinterpret_cast<uint32_t*>(smem + K::q_bp);  // hydrogen-bonding candidates
+  uint32_t* qCR = reinterpret_cast<uint32_t*>(smem + K::q_cr);  // cross-stacking candidates
+  uint32_t* qCX = reinterpret_cast<uint32_t*>(smem + K::q_cx);
+  int* wcnt = reinterpret_cast<int*>(smem + K::wcnt);
+  int* ctr = reinterpret_cast<int*>(smem + K::ctr);  // [0] n_sr [1] n_bp (hydrogen bonding) [2] n_cx [3] n_nl [4] n_cr (cross stacking) [5] too many bonds [6] more tiles
   // packed cell coordinates (10 bits per axis): needed only while the cell list is built, aliases queues SR/BP/CX
-  uint32_t* sCell = reinterpret_cast<uint32_t*>(smem + L.q_sr);
+  uint32_t* sCell = reinterpret_cast<uint32_t*>(smem + K::q_sr);
   int* sCstart = reinterpret_cast<int*>(smem + L.cstart);
   uint16_t* sCorder = reinterpret_cast<uint16_t*>(smem + L.corder);
   uint16_t* sExcl = reinterpret_cast<uint16_t*>(smem + L.excl);
-  CellGrid<T>* grid = reinterpret_cast<CellGrid<T>*>(smem + L.grid);
-  T* sCot = reinterpret_cast<T*>(smem + L.cot);
-  CosWin<T>* sWin = reinterpret_cast<CosWin<T>*>(smem + L.win);  // angular pre-screen of the hydrogen-bond / cross queue
-  int* sCursor = reinterpret_cast<int*>(smem + L.q_nl);  // per-cell fill cursors; aliases queue NL, used only during the cell build
+  CellGrid<T>* grid = reinterpret_cast<CellGrid<T>*>(smem + K::grid);
+  T* sCot = reinterpret_cast<T*>(smem + K::cot);
+  T* sK = reinterpret_cast<T*>(smem + K::cst);  // [0] short-range centre cutoff^2 [1] [2] base-site window (low^2, high^2) [3] Debye cutoff^2 [4] all-pairs cutoff^2
+  CosWin<T>* sWin = reinterpret_cast<CosWin<T>*>(smem + K::win);  // angular pre-screen of the hydrogen-bond / cross queue
+  int* sCursor = reinterpret_cast<int*>(smem + K::q_nl);  // per-cell fill cursors; aliases queue NL, used only during the cell build
 
 #ifdef MB_FRAME_PROFILE
   long long prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_last = clock64();
@@ -397,13 +408,48 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   GlobAcc<T> pacc{gimg};
 #endif
   // bulk staging needs 16-byte aligned rows: every frame's centre block starts at a multiple of 24 n bytes
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + K::bar);
   const bool bulk = ((sizeof(T) * 3 * n) % 16 == 0) && ((reinterpret_cast<uintptr_t>(a.center) | reinterpret_cast<uintptr_t>(a.quat)) % 16 == 0) &&
                     sizeof(T) * 7 * n < (1u << 20);
   uint32_t bar_parity = 0u;
   if (bulk && threadIdx.x == 0) mbar_init(bar, 1);
   __syncthreads();
-  if (threadIdx.x == 0) bp_windows9(sP, sWin);  // visible after the next barrier
+  if (threadIdx.x == 0) {
+    bp_windows9(sP, sWin);  // visible after the next barrier
+    // loop-invariant scalars of the unbonded phases, kept in shared memory instead of registers that live across the loop
+    // short-range centre cutoff: the widest site-pair cutoff plus both site offsets
+    const Geom<T>& g = a.M.geom[0];
+    const unsigned mask = a.mask;
+    T sr_cut;
+    {
+      const T ob = sqrt(g.back[0] * g.back[0] + g.back[1] * g.back[1] + g.back[2] * g.back[2]);
+      const T oh = fabs(g.base), os = fabs(g.stack);
+      T r = T(0);
+      if (mask & (1u << MB_TERM_UEXC)) {
+        r = fmax(r, sP[MB_P_UEXC_BACKBONE_RC] + 2 * ob);
+        r = fmax(r, sP[MB_P_UEXC_BASE_RC] + 2 * oh);
+        r = fmax(r, fmax(sP[MB_P_UEXC_BACK_BASE_RC], sP[MB_P_UEXC_BASE_BACK_RC]) + ob + oh);
+      }
+      if (mask & (1u << MB_TERM_HB)) r = fmax(r, sP[MB_P_HB_RCHIGH] + 2 * oh);
+      if (mask & (1u << MB_TERM_CROSS)) r = fmax(r, sP[MB_P_CROSS_RCHIGH] + 2 * oh);
+      if (mask & (1u << MB_TERM_COAX)) r = fmax(r, sP[MB_P_COAX_RCHIGH] + 2 * os);
+      sr_cut = r * T(1.000001);
+    }
+    T bp_lo = T(1e30), bp_hi = T(0);
+    if (mask & (1u << MB_TERM_HB)) {
+      bp_lo = fmin(bp_lo, sP[MB_P_HB_RCLOW]);
+      bp_hi = fmax(bp_hi, sP[MB_P_HB_RCHIGH]);
+    }
+    if (mask & (1u << MB_TERM_CROSS)) {
+      bp_lo = fmin(bp_lo, sP[MB_P_CROSS_RCLOW]);
+      bp_hi = fmax(bp_hi, sP[MB_P_CROSS_RCHIGH]);
+    }
+    sK[0] = sr_cut * sr_cut;
+    sK[1] = bp_lo * bp_lo;
+    sK[2] = bp_hi * bp_hi;  // 0: neither term requested
+    sK[3] = ((mask & (1u << MB_TERM_DEBYE)) && a.M.forms[0].has_debye) ? sP[MB_P_DEBYE_RCUT] * sP[MB_P_DEBYE_RCUT] : T(-1);
+    sK[4] = a.all_pairs_cutoff * a.all_pairs_cutoff;
+  }
   const ModelT<T>& M = a.M;
   const Geom<T>& g = M.geom[0];
   const mb_bank_forms F = M.forms[0];
@@ -486,36 +532,8 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   // registers across the whole scheduler loop -- 17 + 5 doubles -- were what pushed the loop's state into local memory)
   const bool want_debye = (mask & (1u << MB_TERM_DEBYE)) && F.has_debye;
   const bool want_sr = (mask & ((1u << MB_TERM_UEXC) | (1u << MB_TERM_HB) | (1u << MB_TERM_CROSS) | (1u << MB_TERM_COAX))) != 0;
-  // short-range centre cutoff: the widest site-pair cutoff plus both site offsets
-  T sr_cut;
-  {
-    const T ob = sqrt(g.back[0] * g.back[0] + g.back[1] * g.back[1] + g.back[2] * g.back[2]);
-    const T oh = fabs(g.base), os = fabs(g.stack);
-    T r = T(0);
-    if (mask & (1u << MB_TERM_UEXC)) {
-      r = fmax(r, sP[MB_P_UEXC_BACKBONE_RC] + 2 * ob);
-      r = fmax(r, sP[MB_P_UEXC_BASE_RC] + 2 * oh);
-      r = fmax(r, fmax(sP[MB_P_UEXC_BACK_BASE_RC], sP[MB_P_UEXC_BASE_BACK_RC]) + ob + oh);
-    }
-    if (mask & (1u << MB_TERM_HB)) r = fmax(r, sP[MB_P_HB_RCHIGH] + 2 * oh);
-    if (mask & (1u << MB_TERM_CROSS)) r = fmax(r, sP[MB_P_CROSS_RCHIGH] + 2 * oh);
-    if (mask & (1u << MB_TERM_COAX)) r = fmax(r, sP[MB_P_COAX_RCHIGH] + 2 * os);
-    sr_cut = r * T(1.000001);
-  }
-  const T sr_cut2 = sr_cut * sr_cut;
-  T bp_lo = T(1e30), bp_hi = T(0);
-  if (mask & (1u << MB_TERM_HB)) {
-    bp_lo = fmin(bp_lo, sP[MB_P_HB_RCLOW]);
-    bp_hi = fmax(bp_hi, sP[MB_P_HB_RCHIGH]);
-  }
-  if (mask & (1u << MB_TERM_CROSS)) {
-    bp_lo = fmin(bp_lo, sP[MB_P_CROSS_RCLOW]);
-    bp_hi = fmax(bp_hi, sP[MB_P_CROSS_RCHIGH]);
-  }
-
   const bool have_unbonded = (mask & MB_UNBONDED_TERMS) && (cells || a.pair_capacity > 0);
   const bool periodic = M.box[0] > T(0);
-  const T cut2 = a.all_pairs_cutoff * a.all_pairs_cutoff;
 
   // ---------------------------------------------------------------- all-pairs mode: shared-memory cell list
   if (have_unbonded && cells) {
@@ -532,7 +550,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
           hi[d] = fmax(hi[d], x);
         }
     }
-    T* red = reinterpret_cast<T*>(smem + L.q_nl);  // scratch: 6 x kFWarps reals in the (still empty) DB queue; read back before the cell cursors, which alias it, are written
+    T* red = reinterpret_cast<T*>(smem + K::q_nl);  // scratch: 6 x kFWarps reals in the (still empty) DB queue; read back before the cell cursors, which alias it, are written
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       T l = lo[d], h = hi[d];
@@ -716,7 +734,6 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
     };
     if (!cells) issue_loads(0);
     const int n_rows = cells ? half_shell_rows(grid->S) : 0;
-    const T rc_debye2 = want_debye ? sP[MB_P_DEBYE_RCUT] * sP[MB_P_DEBYE_RCUT] : T(-1);
     bool flush = false;
     while (true) {
       const int n_sr = ctr[0], n_bp = ctr[1], n_cx = ctr[2], n_nl = ctr[3], n_cr = ctr[4];
@@ -828,7 +845,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
           warp_energy_to(ex, &eW[MB_TERM_UEXC]);
         }
         const T r2 = dot(d_base, d_base);
-        unsigned to_bp = (valid && bp_hi > T(0) && r2 > bp_lo * bp_lo && r2 < bp_hi * bp_hi) ? 1u : 0u;
+        unsigned to_bp = (valid && r2 > sK[1] && r2 < sK[2]) ? 1u : 0u;
         // radial window passed: cheap cosine tests of the angles decide whether the six-acos evaluations can be non-zero at
         // all (most pairs inside the window have the wrong orientation) -- bit 0 hydrogen bonding, bit 1 cross stacking
         if (to_bp) to_bp = bp_screen2(sP, sWin, mask, d_base, r2, ni.a1, nj.a1, ni.a3, nj.a3, (sF[i] & 3) * 4 + (sF[j] & 3));
@@ -915,7 +932,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
             {
               found[u] = cur;
               const V3<T> dc = disp(v3<T>(sC[3 * j], sC[3 * j + 1], sC[3 * j + 2]), v3<T>(sC[3 * i], sC[3 * i + 1], sC[3 * i + 2]), M.box);
-              if (want_sr && dot(dc, dc) < sr_cut2) acc_sr |= 1u << u;
+              if (want_sr && dot(dc, dc) < sK[0]) acc_sr |= 1u << u;
               if (want_debye) {
                 V3<T> db;
                 if (CACHE_BACK) {
@@ -924,7 +941,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
                   const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
                   db = disp(site(nj, g.back[0], g.back[1], g.back[2]), site(ni, g.back[0], g.back[1], g.back[2]), M.box);
                 }
-                if (dot(db, db) < rc_debye2) acc_db |= 1u << u;
+                if (dot(db, db) < sK[3]) acc_db |= 1u << u;
               }
             }
           }
@@ -995,17 +1012,17 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
             if (r != st_e0 && r != st_e1) {
               T dx = sC[3 * r] - st_x;
               if (periodic) dx = wrap1(dx, M.box[0]);
-              if (dx * dx < cut2) {
+              if (dx * dx < sK[4]) {
                 T dy = sC[3 * r + 1] - st_y, dz = sC[3 * r + 2] - st_z;
                 if (periodic) {
                   dy = wrap1(dy, M.box[1]);
                   dz = wrap1(dz, M.box[2]);
                 }
                 const T d2 = dx * dx + dy * dy + dz * dz;
-                if (d2 < cut2) {
+                if (d2 < sK[4]) {
                   const int i = st_p < r ? st_p : r, j = st_p < r ? r : st_p;
                   found[u] = uint32_t(i) | (uint32_t(j) << 16);
-                  if (want_sr && d2 < sr_cut2) acc_sr |= 1u << u;
+                  if (want_sr && d2 < sK[0]) acc_sr |= 1u << u;
                   if (want_debye) {
                     V3<T> db;
                     if (CACHE_BACK) {
@@ -1014,7 +1031,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
                       const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
                       db = disp(site(nj, g.back[0], g.back[1], g.back[2]), site(ni, g.back[0], g.back[1], g.back[2]), M.box);
                     }
-                    if (dot(db, db) < rc_debye2) acc_db |= 1u << u;
+                    if (dot(db, db) < sK[3]) acc_db |= 1u << u;
                   }
                 }
               }

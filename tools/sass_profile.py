@@ -49,9 +49,27 @@ def classify(ch):
     return outer, inner
 
 
-PHASES = [(321, 376, "prologue"), (377, 424, "stage"), (425, 443, "bonded"), (444, 481, "setup"), (482, 636, "cells"),
-          (637, 685, "loop-head"), (686, 719, "hb+cross"), (720, 741, "coax"), (742, 786, "phase2-exc"), (787, 818, "phase1-debye"),
-          (819, 966, "producer"), (967, 1018, "flush"), (1019, 1030, "observables")]
+def _phases():
+    """line ranges of the kernel's phases, from the marker comments of the current frame_kernels.cu"""
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "mythos_b200", "csrc", "frame_kernels.cu")).read().split("\n")
+    marks = [("__global__ void __launch_bounds__(kFB, 1) k_frame_energy", "prologue"), ("// persistent CTA: frames", "stage"),
+             ("phase B: bonded pairs", "bonded"), ("-- unbonded pairs", "setup"), ("all-pairs mode: shared-memory cell list", "cells"),
+             ("-- scheduler loop", "loop-head"), ("phase 3a:", "hb"), ("phase 3b:", "cross"), ("phase 3c:", "coax"),
+             ("phase 2:", "phase2-exc"), ("phase 1:", "phase1-debye"), ("if (flush) break;", "producer"),
+             ("#ifdef MB_FRAME_PROFILE\n  if (threadIdx.x == 0 && blockIdx.x == 0)", "flush"), ("fused observables", "observables"),
+             ("static bool pick_layout", "end")]
+    found = []
+    for text, name in marks:
+        first = text.split("\n")[0]
+        for n, line in enumerate(src, 1):
+            if first in line and (not found or n > found[-1][0]):
+                found.append((n, name))
+                break
+    return [(found[k][0], found[k + 1][0] - 1, found[k][1]) for k in range(len(found) - 1)]
+
+
+PHASES = _phases()
 
 
 def phase_of(line):
