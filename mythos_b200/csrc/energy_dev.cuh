@@ -260,17 +260,24 @@ __device__ __forceinline__ void bp_windows9(const T* P, CosWin<T> w[9]) {
 template <class T>
 __device__ __forceinline__ unsigned bp_screen2(const T* P, const CosWin<T>* w, unsigned mask, const V3<T>& d, T r2, const V3<T>& a1i,
                                                const V3<T>& a1j, const V3<T>& a3i, const V3<T>& a3j, int tab) {
-  const T r = sqrt(r2);
-  const bool rad_hb = (mask & (1u << MB_TERM_HB)) && P[MB_P_HB_RCLOW] < r && r < P[MB_P_HB_RCHIGH] && P[MB_P_HB_W00 + tab] != T(0);
-  const bool rad_cr = (mask & (1u << MB_TERM_CROSS)) && P[MB_P_CROSS_RCLOW] < r && r < P[MB_P_CROSS_RCHIGH];
-  if (!(rad_hb || rad_cr) || !(r > T(0))) return 0u;
-  const T ir = T(1) / r;
+  // A screen only has to be a SUPERSET of the pairs with a non-zero term (the terms themselves are evaluated exactly in
+  // phase 3), so it avoids the double-precision square root and division: radial windows on r^2 against the squared limits
+  // (widened by 1e-9 relative), 1/r from the float32 rsqrt (relative error < 3e-7) with the cosine windows widened by 1e-6.
+  const T lo_hb = P[MB_P_HB_RCLOW] * P[MB_P_HB_RCLOW] * T(1 - 1e-9), hi_hb = P[MB_P_HB_RCHIGH] * P[MB_P_HB_RCHIGH] * T(1 + 1e-9);
+  const T lo_cr = P[MB_P_CROSS_RCLOW] * P[MB_P_CROSS_RCLOW] * T(1 - 1e-9), hi_cr = P[MB_P_CROSS_RCHIGH] * P[MB_P_CROSS_RCHIGH] * T(1 + 1e-9);
+  const bool rad_hb = (mask & (1u << MB_TERM_HB)) && lo_hb < r2 && r2 < hi_hb && P[MB_P_HB_W00 + tab] != T(0);
+  const bool rad_cr = (mask & (1u << MB_TERM_CROSS)) && lo_cr < r2 && r2 < hi_cr;
+  if (!(rad_hb || rad_cr) || !(r2 > T(0))) return 0u;
+  const T ir = T(rsqrtf(float(r2)));
+  const T eps = T(1e-6);
   const T x1 = -dot(a1i, a1j), x2 = -dot(a1j, d) * ir, x3 = dot(a1i, d) * ir;
-  bool hb = rad_hb && w[0].lo < x1 && x1 < w[0].hi && w[1].lo < x2 && x2 < w[1].hi && w[2].lo < x3 && x3 < w[2].hi;
-  const bool cr = rad_cr && w[3].lo < x1 && x1 < w[3].hi && w[4].lo < x2 && x2 < w[4].hi && w[5].lo < x3 && x3 < w[5].hi;
+  bool hb = rad_hb && w[0].lo - eps < x1 && x1 < w[0].hi + eps && w[1].lo - eps < x2 && x2 < w[1].hi + eps && w[2].lo - eps < x3 &&
+            x3 < w[2].hi + eps;
+  const bool cr = rad_cr && w[3].lo - eps < x1 && x1 < w[3].hi + eps && w[4].lo - eps < x2 && x2 < w[4].hi + eps && w[5].lo - eps < x3 &&
+                  x3 < w[5].hi + eps;
   if (hb) {
     const T x4 = dot(a3i, a3j), x7 = -dot(a3j, d) * ir, x8 = -dot(a3i, d) * ir;
-    hb = w[6].lo < x4 && x4 < w[6].hi && w[7].lo < x7 && x7 < w[7].hi && w[8].lo < x8 && x8 < w[8].hi;
+    hb = w[6].lo - eps < x4 && x4 < w[6].hi + eps && w[7].lo - eps < x7 && x7 < w[7].hi + eps && w[8].lo - eps < x8 && x8 < w[8].hi + eps;
   }
   return (hb ? 1u : 0u) | (cr ? 2u : 0u);
 }

@@ -68,13 +68,14 @@ struct FixedSmem {
   static constexpr unsigned q_bp = q_sr + smem_up(sizeof(uint32_t) * kSrCap);
   static constexpr unsigned q_cr = q_bp + smem_up(sizeof(uint32_t) * kQCap);
   static constexpr unsigned q_cx = q_cr + smem_up(sizeof(uint32_t) * kQCap);
-  static constexpr unsigned wcnt = q_cx + smem_up(sizeof(uint32_t) * kQCap);
+  static constexpr unsigned q_ev = q_cx + smem_up(sizeof(uint32_t) * kQCap);
+  static constexpr unsigned wcnt = q_ev + smem_up(sizeof(uint32_t) * kQCap);
   static constexpr unsigned ctr = wcnt + smem_up(sizeof(int) * 2 * (kFWarps + 1));
   static constexpr unsigned grid = ctr + smem_up(sizeof(int) * 8);
   static constexpr unsigned win = grid + smem_up(sizeof(T) * 8 + sizeof(int) * 8);
   static constexpr unsigned cot = win + smem_up(sizeof(T) * 2 * 9);  // nine CosWin<T>
   static constexpr unsigned cst = cot + smem_up(sizeof(T) * MB_N_TERMS);  // loop-invariant scalars (squared cutoffs / windows)
-  static constexpr unsigned bar = cst + smem_up(sizeof(T) * 8);           // mbarrier of the bulk (TMA) frame staging
+  static constexpr unsigned bar = cst + smem_up(sizeof(T) * 16);          // mbarrier of the bulk (TMA) frame staging
   static constexpr unsigned acc = bar + smem_up(sizeof(uint64_t));        // acc_rows copies of the parameter-gradient image
 };
 struct FrameSmem {
@@ -207,6 +208,33 @@ __device__ __forceinline__ void q_push3(uint32_t* qa, int* na, bool pa, uint32_t
     *na = old_a + (before & 1023) + __popc(ma);
     *nb = old_b + ((before >> 10) & 1023) + __popc(mb_);
     *nc = old_c + (before >> 20) + __popc(mc);
+  }
+  __syncthreads();
+}
+
+// the same for FOUR queues: two packed words of per-warp counts (16 bits each), one barrier set
+__device__ __forceinline__ void q_push4(uint32_t* qa, int* na, bool pa, uint32_t* qb, int* nb, bool pb, uint32_t* qc, int* nc, bool pc,
+                                        uint32_t* qd, int* nd, bool pd, int* wcnt, uint32_t val) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned ma = __ballot_sync(kFull, pa), mb_ = __ballot_sync(kFull, pb), mc = __ballot_sync(kFull, pc), md = __ballot_sync(kFull, pd);
+  if (lane == 0) {
+    wcnt[warp] = __popc(ma) | (__popc(mb_) << 16);
+    wcnt[kFWarps + 1 + warp] = __popc(mc) | (__popc(md) << 16);
+  }
+  __syncthreads();
+  const int old_a = *na, old_b = *nb, old_c = *nc, old_d = *nd;
+  const int ab = warp_prefix(wcnt, warp, lane), cd = warp_prefix(wcnt + kFWarps + 1, warp, lane);
+  const unsigned below = (1u << lane) - 1u;
+  if (pa) qa[old_a + (ab & 0xffff) + __popc(ma & below)] = val;
+  if (pb) qb[old_b + (ab >> 16) + __popc(mb_ & below)] = val;
+  if (pc) qc[old_c + (cd & 0xffff) + __popc(mc & below)] = val;
+  if (pd) qd[old_d + (cd >> 16) + __popc(md & below)] = val;
+  __syncthreads();
+  if (threadIdx.x == kFB - 1) {  // last warp: its prefix + own count = total
+    *na = old_a + (ab & 0xffff) + __popc(ma);
+    *nb = old_b + (ab >> 16) + __popc(mb_);
+    *nc = old_c + (cd & 0xffff) + __popc(mc);
+    *nd = old_d + (cd >> 16) + __popc(md);
   }
   __syncthreads();
 }
@@ -377,8 +405,9 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   uint32_t* qBP = reinterpret_cast<uint32_t*>(smem + K::q_bp);  // hydrogen-bonding candidates
   uint32_t* qCR = reinterpret_cast<uint32_t*>(smem + K::q_cr);  // cross-stacking candidates
   uint32_t* qCX = reinterpret_cast<uint32_t*>(smem + K::q_cx);
+  uint32_t* qEV = reinterpret_cast<uint32_t*>(smem + K::q_ev);  // pairs with an excluded-volume site pair in range
   int* wcnt = reinterpret_cast<int*>(smem + K::wcnt);
-  int* ctr = reinterpret_cast<int*>(smem + K::ctr);  // [0] n_sr [1] n_bp (hydrogen bonding) [2] n_cx [3] n_nl [4] n_cr (cross stacking) [5] too many bonds [6] more tiles
+  int* ctr = reinterpret_cast<int*>(smem + K::ctr);  // [0] n_sr [1] n_bp (hydrogen bonding) [2] n_cx [3] n_nl [4] n_cr (cross stacking) [5] too many bonds [6] n_ev (excluded volume)
   // packed cell coordinates (10 bits per axis): needed only while the cell list is built, aliases queues SR/BP/CX
   uint32_t* sCell = reinterpret_cast<uint32_t*>(smem + K::q_sr);
   int* sCstart = reinterpret_cast<int*>(smem + L.cstart);
@@ -449,6 +478,11 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
     sK[2] = bp_hi * bp_hi;  // 0: neither term requested
     sK[3] = ((mask & (1u << MB_TERM_DEBYE)) && a.M.forms[0].has_debye) ? sP[MB_P_DEBYE_RCUT] * sP[MB_P_DEBYE_RCUT] : T(-1);
     sK[4] = a.all_pairs_cutoff * a.all_pairs_cutoff;
+    // squared excluded-volume site cutoffs, formed as exc_site forms them (rc * rc): the screen of phase 2 and the evaluation agree bit for bit
+    sK[5] = sP[MB_P_UEXC_BACKBONE_RSTAR + 3] * sP[MB_P_UEXC_BACKBONE_RSTAR + 3];
+    sK[6] = sP[MB_P_UEXC_BASE_RSTAR + 3] * sP[MB_P_UEXC_BASE_RSTAR + 3];
+    sK[7] = sP[MB_P_UEXC_BACK_BASE_RSTAR + 3] * sP[MB_P_UEXC_BACK_BASE_RSTAR + 3];
+    sK[8] = sP[MB_P_UEXC_BASE_BACK_RSTAR + 3] * sP[MB_P_UEXC_BASE_BACK_RSTAR + 3];
   }
   const ModelT<T>& M = a.M;
   const Geom<T>& g = M.geom[0];
@@ -736,7 +770,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
     const int n_rows = cells ? half_shell_rows(grid->S) : 0;
     bool flush = false;
     while (true) {
-      const int n_sr = ctr[0], n_bp = ctr[1], n_cx = ctr[2], n_nl = ctr[3], n_cr = ctr[4];
+      const int n_sr = ctr[0], n_bp = ctr[1], n_cx = ctr[2], n_nl = ctr[3], n_cr = ctr[4], n_ev = ctr[6];
       __syncthreads();  // everyone has read the counters before anyone updates them
       if (n_bp >= kFB || (flush && n_bp > 0)) {
         // ---------------- phase 3a: hydrogen bonding on the HB queue (every entry passed the term's radial window and all six
@@ -816,8 +850,42 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         MB_TICK(6)
         continue;
       }
+      if (n_ev >= kFB || (flush && n_ev > 0)) {
+        // ---------------- phase 2b: excluded volume on the EV queue (pairs with at least one site pair inside its cutoff:
+        // about one short-range pair in a hundred, so it is evaluated with dense lanes here instead of by one or two lanes of
+        // every warp of the screening phase)
+        const int cnt = n_ev >= kFB ? kFB : n_ev;
+        const int t = threadIdx.x;
+        const bool valid = t < cnt;
+        const uint32_t pk = valid ? qEV[n_ev - cnt + t] : 0u;
+        const int i = pk & 0xffff, j = pk >> 16;
+        const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
+        const V3<T> back_i = site(ni, g.back[0], g.back[1], g.back[2]), back_j = site(nj, g.back[0], g.back[1], g.back[2]);
+        const V3<T> base_i = site(ni, g.base, T(0), T(0)), base_j = site(nj, g.base, T(0), T(0));
+        const T c = cot[MB_TERM_UEXC];
+        V3<T> gs;
+        T ex = T(0);
+        if (WP) {
+          ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BACKBONE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_j, back_i, M.box), c, gs, pacc);
+          ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BASE_RSTAR, MB_P_UEXC_EPS, valid, disp(base_j, base_i, M.box), c, gs, pacc);
+          ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BACK_BASE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_i, base_j, M.box), c, gs, pacc);
+          ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BASE_BACK_RSTAR, MB_P_UEXC_EPS, valid, disp(base_i, back_j, M.box), c, gs, pacc);
+        } else {
+          ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BACKBONE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_j, back_i, M.box), c, gs, nacc);
+          ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BASE_RSTAR, MB_P_UEXC_EPS, valid, disp(base_j, base_i, M.box), c, gs, nacc);
+          ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BACK_BASE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_i, base_j, M.box), c, gs, nacc);
+          ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BASE_BACK_RSTAR, MB_P_UEXC_EPS, valid, disp(base_i, back_j, M.box), c, gs, nacc);
+        }
+        warp_energy_to(ex, &eW[MB_TERM_UEXC]);
+        if (threadIdx.x == 0) ctr[6] = n_ev - cnt;
+        __syncthreads();
+        MB_TICK(1)
+        continue;
+      }
       if (n_sr >= kFB || (flush && n_sr > 0)) {
-        // ---------------- phase 2: excluded volume on the SR queue, radial windows feed BP / CX
+        // ---------------- phase 2: SCREEN of the SR queue -- squared site distances against the squared cutoffs / radial windows
+        // and cosine windows only (no square root, division or branch on a term's value): every lane does the same work, and
+        // the survivors go to the queues of the terms that can be non-zero for them (EV / HB / CR / CX)
         const int cnt = n_sr >= kFB ? kFB : n_sr;
         const int t = threadIdx.x;
         const bool valid = t < cnt;
@@ -827,24 +895,12 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         const V3<T> back_i = site(ni, g.back[0], g.back[1], g.back[2]), back_j = site(nj, g.back[0], g.back[1], g.back[2]);
         const V3<T> base_i = site(ni, g.base, T(0), T(0)), base_j = site(nj, g.base, T(0), T(0));
         const V3<T> d_base = disp(base_j, base_i, M.box);
-        if (mask & (1u << MB_TERM_UEXC)) {
-          const T c = cot[MB_TERM_UEXC];
-          V3<T> gs;
-          T ex = T(0);
-          if (WP) {
-            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BACKBONE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_j, back_i, M.box), c, gs, pacc);
-            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BASE_RSTAR, MB_P_UEXC_EPS, valid, d_base, c, gs, pacc);
-            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BACK_BASE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_i, base_j, M.box), c, gs, pacc);
-            ex += exc_site<T, false, true>(sP, 0, MB_P_UEXC_BASE_BACK_RSTAR, MB_P_UEXC_EPS, valid, disp(base_i, back_j, M.box), c, gs, pacc);
-          } else {
-            ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BACKBONE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_j, back_i, M.box), c, gs, nacc);
-            ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BASE_RSTAR, MB_P_UEXC_EPS, valid, d_base, c, gs, nacc);
-            ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BACK_BASE_RSTAR, MB_P_UEXC_EPS, valid, disp(back_i, base_j, M.box), c, gs, nacc);
-            ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BASE_BACK_RSTAR, MB_P_UEXC_EPS, valid, disp(base_i, back_j, M.box), c, gs, nacc);
-          }
-          warp_energy_to(ex, &eW[MB_TERM_UEXC]);
-        }
         const T r2 = dot(d_base, d_base);
+        bool to_ev = false;
+        if (mask & (1u << MB_TERM_UEXC)) {
+          const V3<T> d_bb = disp(back_j, back_i, M.box), d_bh = disp(back_i, base_j, M.box), d_hb = disp(base_i, back_j, M.box);
+          to_ev = valid && (dot(d_bb, d_bb) < sK[5] || r2 < sK[6] || dot(d_bh, d_bh) < sK[7] || dot(d_hb, d_hb) < sK[8]);
+        }
         unsigned to_bp = (valid && r2 > sK[1] && r2 < sK[2]) ? 1u : 0u;
         // radial window passed: cheap cosine tests of the angles decide whether the six-acos evaluations can be non-zero at
         // all (most pairs inside the window have the wrong orientation) -- bit 0 hydrogen bonding, bit 1 cross stacking
@@ -856,7 +912,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
           to_cx = valid && s2 > sP[MB_P_COAX_RCLOW] * sP[MB_P_COAX_RCLOW] && s2 < sP[MB_P_COAX_RCHIGH] * sP[MB_P_COAX_RCHIGH];
         }
         if (threadIdx.x == 0) ctr[0] = n_sr - cnt;
-        q_push3(qBP, &ctr[1], (to_bp & 1u) != 0u, qCR, &ctr[4], (to_bp & 2u) != 0u, qCX, &ctr[2], to_cx, wcnt, pk);
+        q_push4(qBP, &ctr[1], (to_bp & 1u) != 0u, qCR, &ctr[4], (to_bp & 2u) != 0u, qCX, &ctr[2], to_cx, qEV, &ctr[6], to_ev, wcnt, pk);
         MB_TICK(4)
         continue;
       }
@@ -1105,7 +1161,7 @@ template <class T>
 static bool pick_layout(const EnergyDev<T>& a, bool wp, bool* cache_back, FrameSmem* L) {
   const bool cells = a.all_pairs_cutoff > T(0);
   if ((long long)a.n * 11 * (long long)sizeof(T) > 227 * 1024) return false;
-  if (cells && (size_t)a.n * 4 > sizeof(uint32_t) * (kSrCap + 3 * kQCap)) return false;  // sCell aliases the SR/HB/CR/CX queues
+  if (cells && (size_t)a.n * 4 > sizeof(uint32_t) * (kSrCap + 4 * kQCap)) return false;  // sCell aliases the SR/HB/CR/CX/EV queues
   for (int cb = 1; cb >= 0; --cb) {
     for (int rows = wp ? kFWarps : 1; rows >= 1; rows >>= 1) {  // as many image copies as fit (16 = one per warp)
       *L = frame_smem_layout<T>(a.n, wp, cb != 0, cells, rows);
