@@ -772,7 +772,10 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
     while (true) {
       const int n_sr = ctr[0], n_bp = ctr[1], n_cx = ctr[2], n_nl = ctr[3], n_cr = ctr[4], n_ev = ctr[6];
       __syncthreads();  // everyone has read the counters before anyone updates them
-      if (n_bp >= kFB || (flush && n_bp > 0)) {
+      // at the end of the list the screening phase is drained FIRST: a partial batch of a downstream queue waits until nothing
+      // can be appended to it any more (otherwise every downstream queue pays for two partial batches per frame)
+      const bool drain = flush && n_sr == 0;
+      if (n_bp >= kFB || (drain && n_bp > 0)) {
         // ---------------- phase 3a: hydrogen bonding on the HB queue (every entry passed the term's radial window and all six
         // angular windows in phase 2, so the lanes of a batch are dense in this term's code)
         const int cnt = n_bp >= kFB ? kFB : n_bp;
@@ -782,9 +785,11 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         const int i = pk & 0xffff, j = pk >> 16;
         const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
         const V3<T> d = disp(site(nj, g.base, T(0), T(0)), site(ni, g.base, T(0), T(0)), M.box);
-        const T r = sqrt(dot(d, d));
+        const T r2 = dot(d, d);
+        const T ir = (valid && r2 > T(0)) ? inv_sqrt(r2) : T(0);  // (one reciprocal square root instead of a square root and a division)
+        const T r = r2 * ir;
         const bool in_hb = valid && sP[MB_P_HB_RCLOW] < r && r < sP[MB_P_HB_RCHIGH];
-        const V3<T> dh = (valid && r > T(0)) ? (T(1) / r) * d : v3<T>(0, 0, 0);
+        const V3<T> dh = ir * d;
         HbAngles<T> A;
         A.ready = false;
         HbGrad<T> HG;
@@ -800,7 +805,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         MB_TICK(5)
         continue;
       }
-      if (n_cr >= kFB || (flush && n_cr > 0)) {
+      if (n_cr >= kFB || (drain && n_cr > 0)) {
         // ---------------- phase 3b: cross stacking on the CR queue
         const int cnt = n_cr >= kFB ? kFB : n_cr;
         const int t = threadIdx.x;
@@ -809,9 +814,11 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         const int i = pk & 0xffff, j = pk >> 16;
         const Nuc<T> ni = smem_nuc(sC, sQ, i), nj = smem_nuc(sC, sQ, j);
         const V3<T> d = disp(site(nj, g.base, T(0), T(0)), site(ni, g.base, T(0), T(0)), M.box);
-        const T r = sqrt(dot(d, d));
+        const T r2 = dot(d, d);
+        const T ir = (valid && r2 > T(0)) ? inv_sqrt(r2) : T(0);
+        const T r = r2 * ir;
         const bool in_cr = valid && sP[MB_P_CROSS_RCLOW] < r && r < sP[MB_P_CROSS_RCHIGH];
-        const V3<T> dh = (valid && r > T(0)) ? (T(1) / r) * d : v3<T>(0, 0, 0);
+        const V3<T> dh = ir * d;
         HbAngles<T> A;
         A.ready = false;
         HbGrad<T> HG;
@@ -826,7 +833,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         MB_TICK(7)
         continue;
       }
-      if (n_cx >= kFB || (flush && n_cx > 0)) {
+      if (n_cx >= kFB || (drain && n_cx > 0)) {
         // ---------------- phase 3c: coaxial stacking on the CX queue
         const int cnt = n_cx >= kFB ? kFB : n_cx;
         const int t = threadIdx.x;
@@ -850,7 +857,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
         MB_TICK(6)
         continue;
       }
-      if (n_ev >= kFB || (flush && n_ev > 0)) {
+      if (n_ev >= kFB || (drain && n_ev > 0)) {
         // ---------------- phase 2b: excluded volume on the EV queue (pairs with at least one site pair inside its cutoff:
         // about one short-range pair in a hundred, so it is evaluated with dense lanes here instead of by one or two lanes of
         // every warp of the screening phase)

@@ -188,6 +188,16 @@ MB_HD void acc_add_group(Acc& acc, int bank, const int (&idx)[N], const T (&v)[N
   for (int k = 0; k < N; ++k) acc.add(bank, idx[k], v[k]);
 }
 
+// 1 / sqrt(x) for x > 0: the device's rsqrt (one special-function seed + Newton steps, ~1 ulp) -- where a distance and its
+// reciprocal are both needed this replaces a square root and a division
+template <class T>
+MB_HD T inv_sqrt(T x) {
+#ifdef __CUDA_ARCH__
+  return rsqrt(x);
+#else
+  return T(1) / sqrt(x);
+#endif
+}
 template <class T>
 MB_HD T clamp1(T x) {
   return x >= T(1) ? T(1) : (x <= T(-1) ? T(-1) : x);
@@ -1016,12 +1026,13 @@ MB_HD T debye_term(const T* P, int bank, bool act, const V3<T>& d, T m, T cot, V
     const T r2 = dot(d, d);
     const T rc = P[MB_P_DEBYE_RCUT];
     if (r2 < rc * rc && r2 > T(0)) {
-      const T r = sqrt(r2);
+      const T ir = inv_sqrt(r2);  // one reciprocal square root instead of a square root and two divisions
+      const T r = r2 * ir;
       T dEdr;
       if (r < P[MB_P_DEBYE_RHIGH]) {
-        const T ex = exp(-P[MB_P_DEBYE_KAPPA] * r) / r;
+        const T ex = exp(-P[MB_P_DEBYE_KAPPA] * r) * ir;
         e = m * P[MB_P_DEBYE_PREF] * ex;
-        dEdr = -e * (P[MB_P_DEBYE_KAPPA] + T(1) / r);
+        dEdr = -e * (P[MB_P_DEBYE_KAPPA] + ir);
         if (WP) {
           g_k = cot * (-r * e);
           g_A = cot * m * ex;
@@ -1035,7 +1046,7 @@ MB_HD T debye_term(const T* P, int bank, bool act, const V3<T>& d, T m, T cot, V
           g_rc = cot * (-dEdr);
         }
       }
-      if (WF) axpy(gd, cot * dEdr / r, d);
+      if (WF) axpy(gd, cot * dEdr * ir, d);
     }
   }
   if (WP) {
