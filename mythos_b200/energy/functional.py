@@ -273,6 +273,7 @@ class CellListPairs:
     last_split: torch.Tensor | None = None  # (F) of the last tagged chunk: entries before it are short-range pairs
     _last_tagged: bool = False
     _pending: list = dc.field(default_factory=list)
+    _queued: tuple | None = None  # read-back of a pass's flags in flight: (pinned vector, event, ...), see enqueue_verification
 
     _memo_key: tuple | None = None
     keep_lists: bool = False  # the lists of this pass will be remembered: they must not share the reused scratch buffer
@@ -427,10 +428,14 @@ class CellListPairs:
         self._settle_cache(good)
         return good
 
-    def _verify(self) -> bool:
-        if not self._pending:
-            return True
-        # one host read for everything this pass recorded (extent, longest list, overflow flags, slot statistics)
+
+    def enqueue_verification(self) -> None:
+        """Launch the reductions of everything this pass recorded (extent, longest list, overflow flags, slot statistics) and
+        their copy into pinned host memory NOW, without waiting: ``verify`` later only waits for the event.  Called by
+        ``deferred_verification.enqueue`` right after the forward launches, so the read-back rides behind the caller's
+        own device -> host copy instead of adding a second round of tiny kernels and a second sync at the end of the step."""
+        if not self._pending or self._queued is not None:
+            return
         dev = self._pending[0][1].device
         parts = [torch.stack(self._extents).max().double().reshape(1) if self._extents else torch.zeros(1, dtype=torch.float64, device=dev),
                  torch.stack([c.max() for c, _ in self._pending]).max().double().reshape(1),
@@ -440,10 +445,23 @@ class CellListPairs:
             parts.append(torch.stack([m.max(0).values for m, _ in stats]).max(0).values.double())
             if stats[0][1] is not None:
                 parts.append(torch.stack([m.max(0).values for _, m in stats]).max(0).values.double())
-        host = torch.cat(parts).tolist()
-        had_extents = bool(self._extents)
+        dev_vec = torch.cat(parts)
+        host_vec = torch.empty(dev_vec.shape, dtype=dev_vec.dtype, pin_memory=True)
+        host_vec.copy_(dev_vec, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        self._queued = (host_vec, ev, bool(self._extents), stats, dev_vec)
         self._extents.clear()
         self._pending.clear()
+
+    def _verify(self) -> bool:
+        self.enqueue_verification()
+        if self._queued is None:
+            return True
+        host_vec, ev, had_extents, stats, _keep = self._queued
+        self._queued = None
+        ev.synchronize()
+        host = host_vec.tolist()
         if had_extents and host[0] > 1500.0:  # float32 cannot resolve the 1e-3 margin out there: redo the pass with float64 builds
             self.tag_float32 = False
             self._store_memo()
@@ -730,7 +748,14 @@ class deferred_verification:  # noqa: N801 - used as a context manager
                 src._pending.clear()
                 src._extents.clear()
                 src._slot_stats.clear()
+                src._queued = None
         return False
+
+    def enqueue(self) -> None:
+        """Start the read-back of the pass's overflow flags (reductions + copy into pinned memory) without waiting for it;
+        call it when the forward launches are enqueued, ``ok()`` after the step's own host sync."""
+        for src in self.sources:
+            src.enqueue_verification()
 
     def ok(self) -> bool:
         good = True

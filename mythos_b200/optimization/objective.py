@@ -266,18 +266,23 @@ def compute_loss_and_grad(opt_params: dict[str, torch.Tensor], energy_fn, beta, 
         # the pair-list overflow flags are read after the backward (which syncs anyway), not in the middle of the pass
         with functional.deferred_verification() as checks:
             loss, aux = compute_loss(leaves, energy_fn, beta, loss_fn, ref_states, ref_energies, observables)
+            checks.enqueue()  # the flags' read-back is in flight before the backward's own device -> host copy waits
             (g,) = torch.autograd.grad(loss, [leaves.flat], allow_unused=True)
-        if all_ranks_ok(checks.ok()):
+        good = checks.ok()
+        g = torch.zeros_like(leaves.flat) if g is None else g
+        if _world()[1] > 1:
+            # direct dependence of the loss on theta (through loss_fn) is identical on every rank; only the part that
+            # flows through this rank's frames differs.  Each rank's autograd result = direct + own-frames part, so
+            # sum over ranks = world*direct + total frames part; the direct part is recovered from a frames-free pass.
+            # The ranks' "my lists overflowed" flags ride in the same all-reduce (no collective + host read of their own).
+            g, good = _combine_sharded_grads(g, leaves, loss_fn, ref_states, energy_fn, beta, ref_energies, observables, aux, good)
+        if good:
             break
-    g = torch.zeros_like(leaves.flat) if g is None else g
-    rank, world = _world()
-    if world > 1:
-        # direct dependence of the loss on theta (through loss_fn) is identical on every rank; only the part that
-        # flows through this rank's frames differs.  Each rank's autograd result = direct + own-frames part, so
-        # sum over ranks = world*direct + total frames part; the direct part is recovered from a frames-free pass.
-        g = _combine_sharded_grads(g, leaves, loss_fn, ref_states, energy_fn, beta, ref_energies, observables, aux)
-    grads = {k: v.to(torch.as_tensor(opt_params[k]).dtype) if torch.as_tensor(opt_params[k]).is_floating_point() else v
-             for k, v in leaves.unflatten(g).items()}
+    grads = leaves.unflatten(g)
+    for k, v in grads.items():  # (the flat leaf is float64; only parameters given in another floating type are converted)
+        p = opt_params[k]
+        if isinstance(p, torch.Tensor) and p.is_floating_point() and p.dtype != v.dtype:
+            grads[k] = v.to(p.dtype)
     return (loss.detach(), tuple(a.detach() if isinstance(a, torch.Tensor) else a for a in aux)), grads
 
 
@@ -296,6 +301,7 @@ def _loss_and_grad_pytree(opt_params, energy_fn, beta, loss_fn, ref_states, ref_
         leaves = [torch.as_tensor(v, dtype=torch.float64).detach().clone().requires_grad_(True) for v in flat]
         with functional.deferred_verification() as checks:
             loss, aux = compute_loss(pytree.tree_unflatten(leaves, spec), energy_fn, beta, loss_fn, ref_states, ref_energies, observables)
+            checks.enqueue()
             gl = torch.autograd.grad(loss, leaves, allow_unused=True)
         if all_ranks_ok(checks.ok()):
             break
@@ -323,7 +329,7 @@ class _LazyWithParams:
         return self._get()(*args, **kwargs)
 
 
-def _combine_sharded_grads(g, leaves, loss_fn, ref_states, energy_fn, beta, ref_energies, observables, aux):
+def _combine_sharded_grads(g, leaves, loss_fn, ref_states, energy_fn, beta, ref_energies, observables, aux, good=True):
     # frames-free pass: weights held constant -> gradient of the loss through loss_fn's direct theta dependence only
     neff, _, new_e = aux
     w_const, _ = compute_weights_and_neff(beta, new_e.detach(), ref_energies)
@@ -334,7 +340,8 @@ def _combine_sharded_grads(g, leaves, loss_fn, ref_states, energy_fn, beta, ref_
         (gd,) = torch.autograd.grad(loss2, [l2.flat], allow_unused=True)
         if gd is not None:
             direct = gd
-    return allreduce_grads({"flat": g - direct})["flat"] + direct
+    red = allreduce_grads({"flat": g - direct, "overflowed": torch.tensor([0.0 if good else 1.0], dtype=torch.float64)})
+    return red["flat"] + direct, float(red["overflowed"][0]) == 0.0
 
 
 _REFERENCE_STATES: dict = {}  # (ids of the trajectories' frame tensors, n_equilibration) -> (weak refs, sliced + concatenated states)
