@@ -53,6 +53,32 @@ prof = cProfile.Profile(); prof.enable(); step(); prof.disable()
 pstats.Stats(prof, stream=sys.stdout).sort_stats("tottime").print_stats(28)
 pstats.Stats(prof, stream=sys.stdout).sort_stats("cumulative").print_stats(45)
 
+# host timeline of one step without any profiler: entry / exit stamps of the main stages (no extra syncs)
+import functools
+from mythos_b200.energy import theta_tape, model as kmodel
+_stamps = []
+def _wrap(obj, name, label=None):
+    fn = getattr(obj, name)
+    @functools.wraps(fn)
+    def w(*a, **k):
+        _stamps.append((label or name, "in", time.perf_counter()))
+        try:
+            return fn(*a, **k)
+        finally:
+            _stamps.append((label or name, "out", time.perf_counter()))
+    setattr(obj, name, w)
+_wrap(objective, "compute_loss"); _wrap(theta_tape, "bind"); _wrap(objective, "sharded_map"); _wrap(functional, "_run")
+_wrap(functional.CellListPairs, "chunk"); _wrap(functional, "_launch"); _wrap(torch.autograd, "grad", "autograd.grad")
+_wrap(functional.deferred_verification, "ok", "checks.ok"); _wrap(functional.deferred_verification, "enqueue", "checks.enqueue")
+_wrap(theta_tape.FlatParams, "unflatten"); _wrap(objective, "compute_weights_and_neff")
+_wrap(kmodel.Plan, "pairs", "plan.pairs"); _wrap(kmodel.Plan, "topology", "plan.topology"); _wrap(kmodel.Plan, "device_params", "plan.device_params")
+_wrap(kmodel, "support_cutoffs"); _wrap(functional._FrameEnergy, "forward", "_FrameEnergy.forward"); _wrap(theta_tape.FlatParams, "__init__", "FlatParams()")
+for _ in range(3):
+    _stamps.clear(); torch.cuda.synchronize(); t0 = time.perf_counter(); step(); t1 = time.perf_counter()
+print(f"host timeline of one step ({1e3 * (t1 - t0):.2f} ms):")
+for name, io, t in _stamps:
+    print(f"  {1e6 * (t - t0):8.0f} us  {io:3s} {name}")
+
 # GPU timeline of one step (kineto): kernels in launch order with start offsets
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as p:
