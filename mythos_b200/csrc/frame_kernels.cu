@@ -76,31 +76,31 @@ struct FixedSmem {
   static constexpr unsigned cot = win + smem_up(sizeof(T) * 2 * 9);  // nine CosWin<T>
   static constexpr unsigned cst = cot + smem_up(sizeof(T) * MB_N_TERMS);  // loop-invariant scalars (squared cutoffs / windows)
   static constexpr unsigned bar = cst + smem_up(sizeof(T) * 16);          // mbarrier of the bulk (TMA) frame staging
-  static constexpr unsigned acc = bar + smem_up(sizeof(uint64_t));        // acc_rows copies of the parameter-gradient image
+  static constexpr unsigned c = bar + smem_up(sizeof(uint64_t));  // the frame's centres: first of the run-time sized arrays, so its offset is still a constant
 };
 struct FrameSmem {
   // byte offsets into dynamic shared memory of the run-time sized arrays; computed on the host, passed as a kernel parameter
-  unsigned c, q, back, flags, cstart, corder, excl, total;
+  unsigned q, back, flags, cstart, corder, excl, acc, total;
   int acc_rows;  // copies of the parameter-gradient image: warps are spread over them so that their shared-memory atomics do not collide
 };
 template <class T>
 inline FrameSmem frame_smem_layout(int n, bool wp, bool cache_back, bool cells, int acc_rows) {
   FrameSmem L;
-  unsigned off = FixedSmem<T>::acc;
+  unsigned off = FixedSmem<T>::c;
   auto take = [&](size_t bytes) {
     unsigned o = off;
     off += smem_up(bytes);
     return o;
   };
   L.acc_rows = acc_rows;
-  take(wp ? sizeof(T) * MB_P_COUNT * acc_rows : 0);
-  L.c = take(sizeof(T) * 3 * n);
+  take(sizeof(T) * 3 * n);  // centres at FixedSmem<T>::c
   L.q = take(sizeof(T) * 4 * n);
   L.back = take(cache_back ? sizeof(T) * 3 * n : 0);
   L.flags = take(n);
   L.cstart = take(cells ? sizeof(int) * (kMaxCells + 1) : 0);
   L.corder = take(cells ? sizeof(uint16_t) * n : 0);
   L.excl = take(cells ? sizeof(uint16_t) * kExcl * n : 0);
+  L.acc = take(wp ? sizeof(T) * MB_P_COUNT * acc_rows : 0);  // acc_rows copies of the parameter-gradient image
   L.total = off;
   return L;
 }
@@ -393,11 +393,11 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   extern __shared__ __align__(16) unsigned char smem[];
   using K = FixedSmem<T>;
   constexpr bool cells = CELLS;  // all-pairs mode (in-kernel cell list) vs an explicit pair list
-  T* sC = reinterpret_cast<T*>(smem + L.c);
+  T* sC = reinterpret_cast<T*>(smem + K::c);
   T* sQ = reinterpret_cast<T*>(smem + L.q);
   T* sB = reinterpret_cast<T*>(smem + L.back);
   T* sP = reinterpret_cast<T*>(smem + K::p);
-  T* sAcc = reinterpret_cast<T*>(smem + K::acc);
+  T* sAcc = reinterpret_cast<T*>(smem + L.acc);
   T* sE = reinterpret_cast<T*>(smem + K::e);
   unsigned char* sF = smem + L.flags;  // bits 0-1 seq, bit 2 is_end
   uint32_t* qNL = reinterpret_cast<uint32_t*>(smem + K::q_nl);
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   uint32_t* qCX = reinterpret_cast<uint32_t*>(smem + K::q_cx);
   uint32_t* qEV = reinterpret_cast<uint32_t*>(smem + K::q_ev);  // pairs with an excluded-volume site pair in range
   int* wcnt = reinterpret_cast<int*>(smem + K::wcnt);
-  int* ctr = reinterpret_cast<int*>(smem + K::ctr);  // [0] n_sr [1] n_bp (hydrogen bonding) [2] n_cx [3] n_nl [4] n_cr (cross stacking) [5] too many bonds [6] n_ev (excluded volume)
+  int* ctr = reinterpret_cast<int*>(smem + K::ctr);  // [0] n_sr [1] n_bp (hydrogen bonding) [2] n_cx [3] n_nl [4] n_cr (cross stacking) [5] n_ev (excluded volume) [6] too many bonds
   // packed cell coordinates (10 bits per axis): needed only while the cell list is built, aliases queues SR/BP/CX
   uint32_t* sCell = reinterpret_cast<uint32_t*>(smem + K::q_sr);
   int* sCstart = reinterpret_cast<int*>(smem + L.cstart);
@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
             old = prev;
           }
         }
-        if (!placed) ctr[5] = 1;  // more than kExcl bonded partners
+        if (!placed) ctr[6] = 1;  // more than kExcl bonded partners
       }
     }
     for (int i = threadIdx.x; i < n; i += kFB) {
@@ -770,7 +770,10 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
     const int n_rows = cells ? half_shell_rows(grid->S) : 0;
     bool flush = false;
     while (true) {
-      const int n_sr = ctr[0], n_bp = ctr[1], n_cx = ctr[2], n_nl = ctr[3], n_cr = ctr[4], n_ev = ctr[6];
+      // (the six queue counters in two vector loads: this head runs ~90 times per frame with every warp waiting on it)
+      const int4 c0 = *reinterpret_cast<const int4*>(ctr);
+      const int2 c1 = *reinterpret_cast<const int2*>(ctr + 4);
+      const int n_sr = c0.x, n_bp = c0.y, n_cx = c0.z, n_nl = c0.w, n_cr = c1.x, n_ev = c1.y;
       __syncthreads();  // everyone has read the counters before anyone updates them
       // at the end of the list the screening phase is drained FIRST: a partial batch of a downstream queue waits until nothing
       // can be appended to it any more (otherwise every downstream queue pays for two partial batches per frame)
@@ -884,7 +887,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
           ex += exc_site<T, false, false>(sP, 0, MB_P_UEXC_BASE_BACK_RSTAR, MB_P_UEXC_EPS, valid, disp(base_i, back_j, M.box), c, gs, nacc);
         }
         warp_energy_to(ex, &eW[MB_TERM_UEXC]);
-        if (threadIdx.x == 0) ctr[6] = n_ev - cnt;
+        if (threadIdx.x == 0) ctr[5] = n_ev - cnt;
         __syncthreads();
         MB_TICK(1)
         continue;
@@ -919,7 +922,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
           to_cx = valid && s2 > sP[MB_P_COAX_RCLOW] * sP[MB_P_COAX_RCLOW] && s2 < sP[MB_P_COAX_RCHIGH] * sP[MB_P_COAX_RCHIGH];
         }
         if (threadIdx.x == 0) ctr[0] = n_sr - cnt;
-        q_push4(qBP, &ctr[1], (to_bp & 1u) != 0u, qCR, &ctr[4], (to_bp & 2u) != 0u, qCX, &ctr[2], to_cx, qEV, &ctr[6], to_ev, wcnt, pk);
+        q_push4(qBP, &ctr[1], (to_bp & 1u) != 0u, qCR, &ctr[4], (to_bp & 2u) != 0u, qCX, &ctr[2], to_cx, qEV, &ctr[5], to_ev, wcnt, pk);
         MB_TICK(4)
         continue;
       }
@@ -1124,7 +1127,7 @@ __global__ void __launch_bounds__(kFB, 1) k_frame_energy(const EnergyDev<T> a, c
   if (WP) __threadfence();  // this thread's RED.ADDs are performed before the barrier releases the readers below
 #endif
   __syncthreads();
-  const bool poisoned = cells && ctr[5] != 0;
+  const bool poisoned = cells && ctr[6] != 0;
   if (threadIdx.x < MB_N_TERMS && a.terms) {
     T v = 0;
     for (int w = 0; w < kFWarps; ++w) v += sE[w * MB_N_TERMS + threadIdx.x];
