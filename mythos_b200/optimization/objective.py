@@ -162,6 +162,10 @@ def gather_frames(local: torch.Tensor, n_total: int) -> torch.Tensor:
     rank, world = _world()
     sizes = [hi - lo for lo, hi in (shard_bounds(n_total, r, world) for r in range(world))]
     width = max(sizes)
+    if min(sizes) == width and local.is_contiguous():  # equal blocks (the usual case): one collective straight into the result
+        out = torch.empty(width * world, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local)
+        return out
     padded = torch.zeros(width, dtype=local.dtype, device=local.device)
     padded[: local.shape[0]] = local
     chunks = [torch.empty(width, dtype=local.dtype, device=local.device) for _ in range(world)]
@@ -240,13 +244,38 @@ def compute_loss(opt_params, energy_fn: EnergyFunction, beta, loss_fn, ref_state
         functional.prefetch_frames(ref_states.center, ref_states.orientation.vec)
     # = energy_fn.with_params(opt_params); the theta -> parameter-bank chain is replayed from a tape recorded once per
     # energy function (what jit does for the reference) instead of ~700 eager autograd nodes per step
+    base_fn = energy_fn
     energy_fn = theta_tape.bind(energy_fn, opt_params)
     # observables the loss function declares (loss_fn.fused_observables = ObservableSet([...])) are evaluated by the epilogue of
     # the same kernel that computes the energies; loss_fn's own observable(ref_states) calls then find them ready
     new_energies = sharded_map(energy_fn, ref_states, observables=getattr(loss_fn, "fused_observables", None))
     weights, neff = compute_weights_and_neff(beta, new_energies, ref_energies)
-    loss, (measured_value, _) = loss_fn(ref_states, weights, energy_fn, opt_params, observables)
+    loss_params, loss_efn = opt_params, energy_fn
+    world = _world()[1]
+    if world > 1 and torch.is_grad_enabled():
+        # Frame sharding: the gradient that flows through the frames is this rank's share (the gather's backward keeps the
+        # rank's slice) and the shares are SUMMED over the ranks.  Whatever loss_fn takes from theta directly -- through
+        # opt_params or through the energy function it is handed -- is identical on every rank, so it is given to loss_fn
+        # with its gradient scaled by 1 / world: the same sum then returns it exactly once, without a second, frames-free
+        # pass over loss_fn.
+        loss_params = _scale_param_grads(opt_params, 1.0 / world)
+        loss_efn = _LazyWithParams(base_fn, loss_params)
+    loss, (measured_value, _) = loss_fn(ref_states, weights, loss_efn, loss_params, observables)
     return loss, (neff, measured_value, new_energies)
+
+
+def _scale_grad(t: torch.Tensor, s: float) -> torch.Tensor:
+    """Same value as ``t``, gradient scaled by ``s``."""
+    if not (isinstance(t, torch.Tensor) and t.requires_grad):
+        return t
+    d = t.detach()
+    return d + (t - d) * s
+
+
+def _scale_param_grads(opt_params, s: float):
+    if isinstance(opt_params, theta_tape.FlatParams):
+        return opt_params.like(_scale_grad(opt_params.flat, s))
+    return {k: _scale_grad(v, s) for k, v in opt_params.items()}
 
 
 def compute_loss_and_grad(opt_params: dict[str, torch.Tensor], energy_fn, beta, loss_fn, ref_states, ref_energies, observables):
@@ -271,11 +300,10 @@ def compute_loss_and_grad(opt_params: dict[str, torch.Tensor], energy_fn, beta, 
         good = checks.ok()
         g = torch.zeros_like(leaves.flat) if g is None else g
         if _world()[1] > 1:
-            # direct dependence of the loss on theta (through loss_fn) is identical on every rank; only the part that
-            # flows through this rank's frames differs.  Each rank's autograd result = direct + own-frames part, so
-            # sum over ranks = world*direct + total frames part; the direct part is recovered from a frames-free pass.
-            # The ranks' "my lists overflowed" flags ride in the same all-reduce (no collective + host read of their own).
-            g, good = _combine_sharded_grads(g, leaves, loss_fn, ref_states, energy_fn, beta, ref_energies, observables, aux, good)
+            # each rank holds (frames part of ITS block) + (direct part / world), see compute_loss: one SUM all-reduce.
+            # The ranks' "my lists overflowed" flags ride in the same collective (no collective + host read of their own).
+            red = allreduce_grads({"flat": g, "overflowed": torch.tensor([0.0 if good else 1.0], dtype=torch.float64)})
+            g, good = red["flat"], float(red["overflowed"][0]) == 0.0
         if good:
             break
     grads = leaves.unflatten(g)
@@ -327,21 +355,6 @@ class _LazyWithParams:
 
     def __call__(self, *args, **kwargs):
         return self._get()(*args, **kwargs)
-
-
-def _combine_sharded_grads(g, leaves, loss_fn, ref_states, energy_fn, beta, ref_energies, observables, aux, good=True):
-    # frames-free pass: weights held constant -> gradient of the loss through loss_fn's direct theta dependence only
-    neff, _, new_e = aux
-    w_const, _ = compute_weights_and_neff(beta, new_e.detach(), ref_energies)
-    l2 = leaves.like(leaves.flat.detach().clone().requires_grad_(True))
-    loss2, _ = loss_fn(ref_states, w_const.detach(), _LazyWithParams(energy_fn, l2), l2, observables)
-    direct = torch.zeros_like(g)
-    if isinstance(loss2, torch.Tensor) and loss2.requires_grad:
-        (gd,) = torch.autograd.grad(loss2, [l2.flat], allow_unused=True)
-        if gd is not None:
-            direct = gd
-    red = allreduce_grads({"flat": g - direct, "overflowed": torch.tensor([0.0 if good else 1.0], dtype=torch.float64)})
-    return red["flat"] + direct, float(red["overflowed"][0]) == 0.0
 
 
 _REFERENCE_STATES: dict = {}  # (ids of the trajectories' frame tensors, n_equilibration) -> (weak refs, sliced + concatenated states)

@@ -44,13 +44,12 @@ def _loss_fn(ref_states, weights, energy_fn, opt_params, observables):
     return (m - 0.3) ** 2 + 0.01 * opt_params["a"] ** 2 + 0.005 * energy_fn.theta["b"] ** 2, (("obs", m), None)
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, F=11):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         objective.compute_weights_and_neff = _cpu_weights  # the CUDA reweighting kernel is not under test here
         g = torch.Generator().manual_seed(0)
-        F = 11
         c = torch.randn((F, 5, 3), generator=g, dtype=torch.float64)
         q = torch.randn((F, 5, 4), generator=g, dtype=torch.float64)
         obs = torch.randn(F, generator=g, dtype=torch.float64)
@@ -76,15 +75,15 @@ def test_shard_bounds_cover_all_frames():
 
 
 @pytest.mark.timeout(120)
-def test_two_rank_gradient_equals_single_process():
-    port = 29500 + (os.getpid() % 1000)
+@pytest.mark.parametrize("F", [11, 12])  # blocks of 6 + 5 frames (padded gather) and 6 + 6 (single-collective gather)
+def test_two_rank_gradient_equals_single_process(F):
+    port = 29500 + (os.getpid() % 1000) + F
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+        mp.spawn(_worker, args=(2, port, out, F), nprocs=2, join=True)
         res = dict(out)
     # single-process answer
     g = torch.Generator().manual_seed(0)
-    F = 11
     c = torch.randn((F, 5, 3), generator=g, dtype=torch.float64)
     q = torch.randn((F, 5, 4), generator=g, dtype=torch.float64)
     obs = torch.randn(F, generator=g, dtype=torch.float64)
@@ -102,4 +101,4 @@ def test_two_rank_gradient_equals_single_process():
         assert np.isclose(l, float(loss), rtol=1e-12)
         assert np.isclose(grads["a"], float(ga), rtol=1e-10) and np.isclose(grads["b"], float(gb), rtol=1e-10)
         np.testing.assert_allclose(e_full, e.detach().numpy(), rtol=1e-13)
-    assert res[0][2] == (0, 6) and res[1][2] == (6, 11)
+    assert res[0][2] == (0, 6) and res[1][2] == (6, F)
