@@ -47,14 +47,20 @@ NCU_COUNTERS = {"source": "profiles/r02_k_frame_energy_details.csv", "sm__inst_e
 # f(x)*a+b against a chain of FMAs, profiles/r02_special_weights.json); bench re-measures them in every run and uses the
 # live numbers -- these are only the fallback.  (SURVEY 8d's provisional guesses were div 16 sqrt 16 exp 40 log 50 acos 70.)
 W_SPECIAL = {"div": 11.5, "sqrt": 12.2, "exp": 16.1, "log": 43.9, "acos": 27.5}
-# SURVEY 8d per-unit work: (flops, specials) of one unit of each kind, a term counted only inside its radial support
+# SURVEY 8d per-unit work: (flops, specials) of one unit of each kind.  STRICT accounting (round 2): a term is charged only
+# for the pairs on which it can be non-zero -- excluded volume per pair with a SITE pair inside its cutoff (1 short-range
+# pair in 100), hydrogen bonding per pair inside its radial AND six angular supports, cross stacking per pair inside its
+# radial and three plain angular supports; the other short-range pairs are charged the site screen they need (two
+# nucleotides' axes and sites, six squared distances).  Work a kernel skips because it is identically zero is not credited.
 WORK = {
     "nucleotide": (60, {}),
     "bonded": (290, {"acos": 3, "exp": 1, "log": 2, "sqrt": 7, "div": 3}),
     "screen": (30, {}),                                                   # centre-distance test of a listed pair
-    "debye": (65, {"exp": 1, "div": 1, "sqrt": 1}),                      # backbone sites inside r_cut
-    "exc": (200, {"div": 4, "sqrt": 2}),                                 # centres inside the short-range cutoff
-    "hbcr": (330, {"acos": 6, "exp": 1, "sqrt": 1, "div": 1}),           # base-site window: hydrogen bonding + cross stacking
+    "debye": (65, {"exp": 1, "sqrt": 1}),                                 # backbone sites inside r_cut (one reciprocal square root)
+    "sr_screen": (150, {}),                                               # site screen of a pair inside the short-range centre cutoff
+    "exc": (200, {"div": 4, "sqrt": 2}),                                 # a site pair inside its excluded-volume cutoff
+    "hb": (165, {"acos": 6, "exp": 1, "sqrt": 1}),                        # inside the hydrogen-bond radial + six angular supports
+    "cross": (165, {"acos": 6, "sqrt": 1}),                               # inside the cross-stacking radial + three angular supports
     "coax": (225, {"acos": 2, "sqrt": 1, "div": 1}),                     # stacking-site window
 }
 
@@ -291,11 +297,43 @@ def pair_support_counts(plan, center, quat, pairs, count):
     lo = min(P("hydrogen_bonding.dr_c_low_hb"), P("cross_stacking.dr_c_low_cross"))
     hi = max(P("hydrogen_bonding.dr_c_high_hb"), P("cross_stacking.dr_c_high_cross"))
     in_bp = in_sr & (bb > lo * lo) & (bb < hi * hi)
+    # strict supports of the three sparse short-range terms
+    def gat(x):
+        return (torch.gather(x, 1, i.unsqueeze(-1).expand(-1, -1, 3)), torch.gather(x, 1, j.unsqueeze(-1).expand(-1, -1, 3)))
+
+    (back_i, back_j), (base_i, base_j) = gat(back), gat(base)
+    rc = lambda nm: P("unbonded_excluded_volume." + nm) ** 2  # noqa: E731
+    in_ev = in_sr & ((db < rc("dr_c_backbone")) | (bb < rc("dr_c_base")) | ((back_i - base_j).square().sum(-1) < rc("dr_c_back_base")) |
+                     ((base_i - back_j).square().sum(-1) < rc("dr_c_base_back")))
+    (a1i, a1j), (a3i, a3j) = gat(a1), gat(a3)
+    dh = (base_j - base_i) / bb.clamp(min=1e-30).sqrt().unsqueeze(-1)
+    th = [torch.acos(x.clamp(-1, 1)) for x in (-(a1i * a1j).sum(-1), -(a1j * dh).sum(-1), (a1i * dh).sum(-1), (a3i * a3j).sum(-1),
+                                               -(a3j * dh).sum(-1))] + [torch.pi - torch.acos((a3i * dh).sum(-1).clamp(-1, 1))]
+
+    def window(term, angles):
+        ok = torch.ones_like(in_sr)
+        for k, t in zip(angles, th):
+            t0, dc = P(f"{term}.theta0_{term_tag[term]}_{k}"), P(f"{term}.delta_theta_{term_tag[term]}_{k}_c")
+            ok = ok & (t > t0 - dc) & (t < t0 + dc)
+        return ok
+
+    term_tag = {"hydrogen_bonding": "hb", "cross_stacking": "cross"}
+    seq = plan.topology(n, center.device).seq.long()
+    tab_w = torch.tensor([P(f"hydrogen_bonding.eps_hb_weights[{a},{b}]") if f"hydrogen_bonding.eps_hb_weights[{a},{b}]" in names else 1.0
+                          for a in range(4) for b in range(4)], device=center.device)
+    w_ok = tab_w[(seq[i] * 4 + seq[j])] != 0
+    try:
+        in_hb = in_sr & w_ok & (bb > P("hydrogen_bonding.dr_c_low_hb") ** 2) & (bb < P("hydrogen_bonding.dr_c_high_hb") ** 2) & \
+            window("hydrogen_bonding", ("1", "2", "3", "4", "7", "8"))
+        in_cr = in_sr & (bb > P("cross_stacking.dr_c_low_cross") ** 2) & (bb < P("cross_stacking.dr_c_high_cross") ** 2) & \
+            window("cross_stacking", ("1", "2", "3"))
+    except KeyError:  # (parameter naming differs: fall back to the radial window for both terms)
+        in_hb = in_cr = in_bp
     ss = d2(stack)
     in_cx = in_sr & (ss > P("coaxial_stacking.dr_c_low_coax") ** 2) & (ss < P("coaxial_stacking.dr_c_high_coax") ** 2)
     mean = lambda m: float(m.sum()) / F  # noqa: E731
     return {"listed": mean(valid), "debye_support": mean(in_db), "short_range": mean(in_sr), "hb_cross_window": mean(in_bp),
-            "coax_window": mean(in_cx)}
+            "exc_site_pair_in_range": mean(in_ev), "hb_support": mean(in_hb), "cross_support": mean(in_cr), "coax_window": mean(in_cx)}
 
 
 def slots_forward(n, n_b, u, screen: bool = True):
@@ -303,8 +341,8 @@ def slots_forward(n, n_b, u, screen: bool = True):
     charge the centre-distance test of every listed pair (done by the neighbour walk on the support-tagged route, so NOT
     credited to the frame kernel there)."""
     return (slot_cost("nucleotide") * n + slot_cost("bonded") * n_b + (slot_cost("screen") * u["listed"] if screen else 0.0) +
-            slot_cost("debye") * u["debye_support"] + slot_cost("exc") * u["short_range"] +
-            slot_cost("hbcr") * u["hb_cross_window"] + slot_cost("coax") * u["coax_window"])
+            slot_cost("debye") * u["debye_support"] + slot_cost("sr_screen") * u["short_range"] + slot_cost("exc") * u["exc_site_pair_in_range"] +
+            slot_cost("hb") * u["hb_support"] + slot_cost("cross") * u["cross_support"] + slot_cost("coax") * u["coax_window"])
 
 
 def force_benchmark(dev, n_dup: int, model: str, seed: int, peak_tflops: float, label: str, reps: int = 7):
@@ -659,8 +697,10 @@ def main():
         "slots_forward_per_frame": {"kernel": slots_forward(n, n_b, u, screen=False), "step": slots_forward(n, n_b, u, screen=True)},
         "hbm": {"algorithmic_gb_per_launch": alg_bytes / 1e9, "achieved_gbs": alg_bytes / 1e9 / (k_ms * 1e-3), "peak_gbs": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-        "work_model": "SURVEY 8d per-pair flop + special counts split per term, each term counted only inside its radial support "
-                      "(supports measured on 16 frames); slots = flop/2 + sum(special x measured weight); x2.5 for E + dE/dparams",
+        "work_model": "SURVEY 8d per-pair flop + special counts split per term; STRICT supports measured on 16 frames: excluded volume "
+                      "per pair with a site pair in range, hydrogen bonding inside radial + six angular supports, cross stacking inside "
+                      "radial + three angular supports, every other short-range pair its site screen (150 flop); "
+                      "slots = flop/2 + sum(special x measured weight); x2.5 for E + dE/dparams",
     }
 
     cpu_baseline = None

@@ -193,7 +193,14 @@ MB_HD void acc_add_group(Acc& acc, int bank, const int (&idx)[N], const T (&v)[N
 template <class T>
 MB_HD T inv_sqrt(T x) {
 #ifdef __CUDA_ARCH__
-  return rsqrt(x);
+  // float32 seed (relative error 2^-22) + two Newton steps in the working precision: 1e-13, then rounding level.  The
+  // library's rsqrt(double) measures 19 FMA slots (profiles/r02_special_weights.json), this sequence about 10; arguments
+  // here are squared distances of order 1e-3 .. 1e2, far from the float range limits.
+  T y = T(rsqrtf(float(x)));
+  const T hx = T(0.5) * x;
+  y = fma(y, fma(-hx * y, y, T(0.5)), y);
+  if (sizeof(T) > 4) y = fma(y, fma(-hx * y, y, T(0.5)), y);
+  return y;
 #else
   return T(1) / sqrt(x);
 #endif
