@@ -63,6 +63,7 @@ __device__ __forceinline__ void lq_push(pk_t* q, int* n, bool pred, pk_t val) {
 template <class T>
 struct BankCuts {
   T sr2, bp_lo2, bp_hi2, cx_lo2, cx_hi2;
+  T ev2[4];  // squared excluded-volume site cutoffs (backbone, base, back-base, base-back), formed as exc_site forms them
 };
 
 // bank / flavour selection of an unbonded pair, mythos/energy/na1/hydrogen_bonding.py:325-359
@@ -342,14 +343,16 @@ __global__ void __launch_bounds__(kLB, MB_LIST_MINBLOCKS) k_list_sr(const Energy
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nb = MULTI ? a.M.n_banks : 1;
   const int np = nb * MB_P_COUNT;
-  pk_t* qBP = reinterpret_cast<pk_t*>(smem_raw);  // queues first: 8-byte entries at 16-byte aligned offsets
-  pk_t* qCX = qBP + kLQCap;
-  T* sP = reinterpret_cast<T*>(qCX + kLQCap);
+  pk_t* qBP = reinterpret_cast<pk_t*>(smem_raw);  // queues first: 8-byte entries at 16-byte aligned offsets; hydrogen-bonding candidates
+  pk_t* qCX = qBP + kLQCap;                        // coaxial-stacking candidates
+  pk_t* qCR = qCX + kLQCap;                        // cross-stacking candidates
+  pk_t* qEV = qCR + kLQCap;                        // pairs with an excluded-volume site pair inside its cutoff
+  T* sP = reinterpret_cast<T*>(qEV + kLQCap);
   T* sAcc = sP + np;                            // np reals when WP
   T* sE = sAcc + (WP ? np : 0);                 // kLWarps x 8
   BankCuts<T>* sCut = reinterpret_cast<BankCuts<T>*>(sE + kLWarps * MB_N_TERMS);  // MB_MAX_BANKS
-  CosWin<T>* sWin = reinterpret_cast<CosWin<T>*>(sCut + MB_MAX_BANKS);             // 6 per bank: angular pre-screen of queue BP
-  int* ctr = reinterpret_cast<int*>(sWin + 6 * MB_MAX_BANKS);  // [1] n_bp [2] n_cx
+  CosWin<T>* sWin = reinterpret_cast<CosWin<T>*>(sCut + MB_MAX_BANKS);             // 9 per bank: angular pre-screens of queues BP / CR
+  int* ctr = reinterpret_cast<int*>(sWin + 9 * MB_MAX_BANKS);  // [1] n_bp (hydrogen bonding) [2] n_cx [3] n_cr (cross stacking) [4] n_ev
 
   const int frame = blockIdx.y;
   const int n = a.n;
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(kLB, MB_LIST_MINBLOCKS) k_list_sr(const Energy
     sP[k] = a.params[k];
     if (WP) sAcc[k] = T(0);
   }
-  if (threadIdx.x < 4) ctr[threadIdx.x] = 0;
+  if (threadIdx.x < 8) ctr[threadIdx.x] = 0;
   __syncthreads();
   if (threadIdx.x < nb) {
     const T* P = sP + threadIdx.x * MB_P_COUNT;
@@ -382,8 +385,12 @@ __global__ void __launch_bounds__(kLB, MB_LIST_MINBLOCKS) k_list_sr(const Energy
       c.cx_lo2 = P[MB_P_COAX_RCLOW] * P[MB_P_COAX_RCLOW];
       c.cx_hi2 = P[MB_P_COAX_RCHIGH] * P[MB_P_COAX_RCHIGH];
     }
+    c.ev2[0] = P[MB_P_UEXC_BACKBONE_RSTAR + 3] * P[MB_P_UEXC_BACKBONE_RSTAR + 3];
+    c.ev2[1] = P[MB_P_UEXC_BASE_RSTAR + 3] * P[MB_P_UEXC_BASE_RSTAR + 3];
+    c.ev2[2] = P[MB_P_UEXC_BACK_BASE_RSTAR + 3] * P[MB_P_UEXC_BACK_BASE_RSTAR + 3];
+    c.ev2[3] = P[MB_P_UEXC_BASE_BACK_RSTAR + 3] * P[MB_P_UEXC_BASE_BACK_RSTAR + 3];
     sCut[threadIdx.x] = c;
-    bp_windows(P, sWin + 6 * threadIdx.x);
+    bp_windows9(P, sWin + 9 * threadIdx.x);
   }
   __syncthreads();
 
@@ -396,8 +403,6 @@ __global__ void __launch_bounds__(kLB, MB_LIST_MINBLOCKS) k_list_sr(const Energy
   for (int t = 0; t < MB_N_TERMS; ++t) e[t] = T(0);
   SmemAcc<T> sacc{sAcc, MULTI};
   NullAcc nacc;
-  RegAcc<T, MB_P_UEXC_EPS, 17> xacc;
-  xacc.zero();
 
   const pk_t* sr_list = a.sr_list + (long long)frame * a.sr_capacity;
   const bool tagged = a.tagged != 0;
@@ -415,10 +420,10 @@ __global__ void __launch_bounds__(kLB, MB_LIST_MINBLOCKS) k_list_sr(const Energy
 
   while (true) {
     __syncthreads();
-    const int n_bp = ctr[1], n_cx = ctr[2];
+    const int n_bp = ctr[1], n_cx = ctr[2], n_cr = ctr[3], n_ev = ctr[4];
     __syncthreads();  // everyone has read the counters before anyone updates them
     if (n_bp >= kLB || (flush && n_bp > 0)) {
-      // ---------------- phase 3a: hydrogen bonding + cross stacking
+      // ---------------- phase 3a: hydrogen bonding (entries passed the term's radial and six angular windows: dense lanes)
       const int cnt = n_bp >= kLB ? kLB : n_bp;
       const bool valid = threadIdx.x < cnt;
       const pk_t pk = valid ? qBP[n_bp - cnt + threadIdx.x] : 0ull;
@@ -429,7 +434,7 @@ __global__ void __launch_bounds__(kLB, MB_LIST_MINBLOCKS) k_list_sr(const Energy
       NucGrad<T> Gi, Gj;
       Gi.zero();
       Gj.zero();
-      const unsigned m3 = mask & ((1u << MB_TERM_HB) | (1u << MB_TERM_CROSS));
+      const unsigned m3 = mask & (1u << MB_TERM_HB);
       if (WP)
         unbonded_pair<T, WF, true>(M, sP, valid, ni, nj, a.seq[i], a.seq[j], nti, ntj, T(1), m3, cot, e, Gi, Gj, sacc);
       else
@@ -441,8 +446,56 @@ __global__ void __launch_bounds__(kLB, MB_LIST_MINBLOCKS) k_list_sr(const Energy
       if (threadIdx.x == 0) ctr[1] = n_bp - cnt;
       continue;
     }
+    if (n_cr >= kLB || (flush && n_cr > 0)) {
+      // ---------------- phase 3b: cross stacking
+      const int cnt = n_cr >= kLB ? kLB : n_cr;
+      const bool valid = threadIdx.x < cnt;
+      const pk_t pk = valid ? qCR[n_cr - cnt + threadIdx.x] : 0ull;
+      const int i = int(pk & 0xffffffffu), j = int(pk >> 32);
+      T qi[4], qj[4];
+      const Nuc<T> ni = load_nuc(a.center, a.quat, fbase + i, qi), nj = load_nuc(a.center, a.quat, fbase + j, qj);
+      const int nti = MULTI ? a.nt_type[i] : 1, ntj = MULTI ? a.nt_type[j] : 1;
+      NucGrad<T> Gi, Gj;
+      Gi.zero();
+      Gj.zero();
+      const unsigned m3 = mask & (1u << MB_TERM_CROSS);
+      if (WP)
+        unbonded_pair<T, WF, true>(M, sP, valid, ni, nj, a.seq[i], a.seq[j], nti, ntj, T(1), m3, cot, e, Gi, Gj, sacc);
+      else
+        unbonded_pair<T, WF, false>(M, sP, valid, ni, nj, a.seq[i], a.seq[j], nti, ntj, T(1), m3, cot, e, Gi, Gj, nacc);
+      if (WF && valid) {
+        scatter_nuc_grad(a, fbase + i, Gi, qi);
+        scatter_nuc_grad(a, fbase + j, Gj, qj);
+      }
+      if (threadIdx.x == 0) ctr[3] = n_cr - cnt;
+      continue;
+    }
+    if (n_ev >= kLB || (flush && n_ev > 0)) {
+      // ---------------- phase 2b: excluded volume of the pairs with a site pair inside its cutoff (about 1 short-range pair in 100)
+      const int cnt = n_ev >= kLB ? kLB : n_ev;
+      const bool valid = threadIdx.x < cnt;
+      const pk_t pk = valid ? qEV[n_ev - cnt + threadIdx.x] : 0ull;
+      const int i = int(pk & 0xffffffffu), j = int(pk >> 32);
+      T qi[4], qj[4];
+      const Nuc<T> ni = load_nuc(a.center, a.quat, fbase + i, qi), nj = load_nuc(a.center, a.quat, fbase + j, qj);
+      const int nti = MULTI ? a.nt_type[i] : 1, ntj = MULTI ? a.nt_type[j] : 1;
+      NucGrad<T> Gi, Gj;
+      Gi.zero();
+      Gj.zero();
+      const unsigned m3 = mask & (1u << MB_TERM_UEXC);
+      if (WP)
+        unbonded_pair<T, WF, true>(M, sP, valid, ni, nj, 0, 0, nti, ntj, T(1), m3, cot, e, Gi, Gj, sacc);
+      else
+        unbonded_pair<T, WF, false>(M, sP, valid, ni, nj, 0, 0, nti, ntj, T(1), m3, cot, e, Gi, Gj, nacc);
+      if (WF && valid) {
+        scatter_nuc_grad(a, fbase + i, Gi, qi);
+        scatter_nuc_grad(a, fbase + j, Gj, qj);
+      }
+      if (threadIdx.x == 0) ctr[4] = n_ev - cnt;
+      continue;
+    }
     if (n_cx >= kLB || (flush && n_cx > 0)) {
-      // ---------------- phase 3b: coaxial stacking
+      // ---------------- phase 3c: coaxial stacking
       const int cnt = n_cx >= kLB ? kLB : n_cx;
       const bool valid = threadIdx.x < cnt;
       const pk_t pk = valid ? qCX[n_cx - cnt + threadIdx.x] : 0ull;
@@ -471,7 +524,9 @@ __global__ void __launch_bounds__(kLB, MB_LIST_MINBLOCKS) k_list_sr(const Energy
       continue;
     }
     {
-      // ---------------- phase 2: a CTA-full of SR: excluded volume; radial windows feed BP / CX
+      // ---------------- phase 2: SCREEN of a CTA-full of SR -- squared site distances against squared cutoffs / radial windows,
+      // cosine windows with a float32 rsqrt; no double-precision special function.  Survivors go to the queue of each term
+      // that can be non-zero for them (EV / HB / CR / CX), where they are evaluated with dense lanes.
       const long long k = base + threadIdx.x;
       base += (long long)gridDim.x * kLB;
       const bool valid = k < count;
@@ -481,51 +536,33 @@ __global__ void __launch_bounds__(kLB, MB_LIST_MINBLOCKS) k_list_sr(const Energy
       T qi[4], qj[4];
       const Nuc<T> ni = load_nuc(a.center, a.quat, fbase + i, qi), nj = load_nuc(a.center, a.quat, fbase + j, qj);
       const int nti = MULTI ? a.nt_type[i] : 1, ntj = MULTI ? a.nt_type[j] : 1;
-      const unsigned m2 = mask & (1u << MB_TERM_UEXC);
-      if (m2) {
-        NucGrad<T> Gi, Gj;
-        Gi.zero();
-        Gj.zero();
-        if (WP) {
-          if (MULTI)
-            unbonded_pair<T, WF, true>(M, sP, valid, ni, nj, 0, 0, nti, ntj, T(1), m2, cot, e, Gi, Gj, sacc);
-          else
-            unbonded_pair<T, WF, true>(M, sP, valid, ni, nj, 0, 0, nti, ntj, T(1), m2, cot, e, Gi, Gj, xacc);
-        } else {
-          unbonded_pair<T, WF, false>(M, sP, valid, ni, nj, 0, 0, nti, ntj, T(1), m2, cot, e, Gi, Gj, nacc);
-        }
-        if (WF && valid) {
-          scatter_nuc_grad(a, fbase + i, Gi, qi);
-          scatter_nuc_grad(a, fbase + j, Gj, qj);
-        }
-      }
       int bank, fi, fj;
       pair_bank(nb, nti, ntj, bank, fi, fj);
       const BankCuts<T> cut = sCut[bank];
       const Geom<T>&gi = M.geom[fi], &gj = M.geom[fj];
-      const V3<T> d_base = disp(site(nj, gj.base, T(0), T(0)), site(ni, gi.base, T(0), T(0)), M.box);
+      const V3<T> base_i = site(ni, gi.base, T(0), T(0)), base_j = site(nj, gj.base, T(0), T(0));
+      const V3<T> d_base = disp(base_j, base_i, M.box);
       const T r2 = dot(d_base, d_base);
-      bool to_bp = valid && r2 > cut.bp_lo2 && r2 < cut.bp_hi2;
-      if (to_bp)  // cosine tests of the three plain angles: can hydrogen bonding or cross stacking be non-zero at all?
-        to_bp = bp_screen(sP + bank * MB_P_COUNT, sWin + 6 * bank, mask, d_base, r2, ni.a1, nj.a1, (a.seq[i] & 3) * 4 + (a.seq[j] & 3));
+      bool to_ev = false;
+      if (mask & (1u << MB_TERM_UEXC)) {
+        const V3<T> back_i = site(ni, gi.back[0], gi.back[1], gi.back[2]), back_j = site(nj, gj.back[0], gj.back[1], gj.back[2]);
+        const V3<T> d_bb = disp(back_j, back_i, M.box), d_bh = disp(back_i, base_j, M.box), d_hb = disp(base_i, back_j, M.box);
+        to_ev = valid && (dot(d_bb, d_bb) < cut.ev2[0] || r2 < cut.ev2[1] || dot(d_bh, d_bh) < cut.ev2[2] || dot(d_hb, d_hb) < cut.ev2[3]);
+      }
+      unsigned to_bp = (valid && r2 > cut.bp_lo2 && r2 < cut.bp_hi2) ? 1u : 0u;
+      if (to_bp)  // bit 0: hydrogen bonding can be non-zero (six windows), bit 1: cross stacking (three)
+        to_bp = bp_screen2(sP + bank * MB_P_COUNT, sWin + 9 * bank, mask, d_base, r2, ni.a1, nj.a1, ni.a3, nj.a3, (a.seq[i] & 3) * 4 + (a.seq[j] & 3));
       const V3<T> ds = disp(site(nj, gj.stack, T(0), T(0)), site(ni, gi.stack, T(0), T(0)), M.box);
       const T s2 = dot(ds, ds);
       const bool to_cx = valid && s2 > cut.cx_lo2 && s2 < cut.cx_hi2;
-      lq_push(qBP, &ctr[1], to_bp, pk);
+      lq_push(qBP, &ctr[1], (to_bp & 1u) != 0u, pk);
+      lq_push(qCR, &ctr[3], (to_bp & 2u) != 0u, pk);
       lq_push(qCX, &ctr[2], to_cx, pk);
+      lq_push(qEV, &ctr[4], to_ev, pk);
     }
   }
 
   // ---------------------------------------------------------------- flush
-  if (WP && !MULTI) {
-#pragma unroll
-    for (int k = 0; k < 17; ++k) {
-      T v = xacc.r[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-      if (lane == 0 && v != T(0)) atomicAdd(&sAcc[MB_P_UEXC_EPS + k], v);
-    }
-  }
 #pragma unroll
   for (int t = 0; t < MB_N_TERMS; ++t) {
     T v = e[t];
@@ -563,8 +600,8 @@ template <class T, bool WF, bool WP, bool MULTI>
 static int launch_list(cudaStream_t s, const EnergyDev<T>& a) {
   const int nb = MULTI ? a.M.n_banks : 1;
   const size_t np = (size_t)nb * MB_P_COUNT;
-  const size_t smem = sizeof(pk_t) * (2 * kLQCap) + sizeof(T) * (np * (WP ? 2 : 1) + kLWarps * MB_N_TERMS) +
-                      sizeof(BankCuts<T>) * MB_MAX_BANKS + sizeof(CosWin<T>) * 6 * MB_MAX_BANKS + sizeof(int) * 8;
+  const size_t smem = sizeof(pk_t) * (4 * kLQCap) + sizeof(T) * (np * (WP ? 2 : 1) + kLWarps * MB_N_TERMS) +
+                      sizeof(BankCuts<T>) * MB_MAX_BANKS + sizeof(CosWin<T>) * 9 * MB_MAX_BANKS + sizeof(int) * 8;
   static int sms = 0;
   if (!sms) {
     int dev = 0;

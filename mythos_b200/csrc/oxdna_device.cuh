@@ -1247,11 +1247,12 @@ MB_HD void unbonded_pair(const ModelT<T>& M, const T* Pall, bool valid, const Nu
 
   if (mask & ((1u << MB_TERM_HB) | (1u << MB_TERM_CROSS))) {
     const T r2 = dot(d_base, d_base);
-    const T r = sqrt(r2);
+    const T ir = (valid && r2 > T(0)) ? inv_sqrt(r2) : T(0);  // one reciprocal square root instead of a square root and a division
+    const T r = r2 * ir;
     const bool in_hb = valid && (mask & (1u << MB_TERM_HB)) && P[MB_P_HB_RCLOW] < r && r < P[MB_P_HB_RCHIGH];
     const bool in_cr = valid && (mask & (1u << MB_TERM_CROSS)) && P[MB_P_CROSS_RCLOW] < r && r < P[MB_P_CROSS_RCHIGH];
     V3<T> dh = v3<T>(0, 0, 0);
-    if (in_hb || in_cr) dh = (T(1) / r) * d_base;
+    if (in_hb || in_cr) dh = ir * d_base;
     HbAngles<T> A;
     A.ready = false;
     HbGrad<T> G;
