@@ -41,8 +41,9 @@ sys.path.insert(0, str(ROOT))
 N_DUPLEX, PITCH, SEED = 17, 2.6, 1
 METRIC, UNIT = "DiffTRe frames/s (E+dE/dtheta)", "frames/s"
 # hardware counters of k_frame_energy<double,1,1,0> at 1184 frames x 2040 nt from the committed `ncu --set full` capture
-NCU_COUNTERS = {"source": "profiles/r02_k_frame_energy_details.csv", "sm__inst_executed_pipe_fp64_pct": 22.15,
-                "smsp__issue_active_pct": 35.93, "sm__warps_active_pct": 25.0, "dram_bytes": 0.7782e9, "duration_ms": 3.744}
+NCU_COUNTERS = {"source": "profiles/r02_final_k_frame_energy_details.csv", "sm__inst_executed_pipe_fp64_pct": 24.40,
+                "smsp__issue_active_pct": 39.39, "sm__warps_active_pct": 24.98, "dram_bytes": 0.7910e9, "duration_ms": 2.583,
+                "local_ld_st_inst": 13.8e6}
 # Issue cost of the special functions in FP64 FMA slots.  MEASURED (csrc/peaks.cu micro-kernels: a dependent chain of
 # f(x)*a+b against a chain of FMAs, profiles/r02_special_weights.json); bench re-measures them in every run and uses the
 # live numbers -- these are only the fallback.  (SURVEY 8d's provisional guesses were div 16 sqrt 16 exp 40 log 50 acos 70.)
