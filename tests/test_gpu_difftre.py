@@ -142,6 +142,46 @@ def test_frame_additivity_at_scale(workload):
     assert torch.isfinite(e_all).all()
 
 
+@pytest.mark.parametrize("model", ["dna1", "dna2"])
+def test_screens_are_supersets_on_disordered_frames(model):
+    """Strongly perturbed duplexes (positions +-0.12, rotations ~0.5 rad: base pairs half broken, excluded-volume overlaps,
+    angles all over their windows): the frame kernel's screens (squared cutoffs, float32-rsqrt cosine windows, six-window
+    hydrogen-bond queue, dense excluded-volume queue) may only drop pairs whose terms are exactly zero, so every route of the
+    frame-resident kernel must reproduce the one-thread-per-pair kernel term by term and J row by J row."""
+    from mythos_b200 import _lib
+    from mythos_b200.energy import dna1, functional
+    from mythos_b200.energy import model as kmodel
+
+    s = synthetic.assembly(4, seed=11)
+    rng = np.random.default_rng(5)
+    frames = [synthetic.jitter(s.center, s.quat, rng, sigma_pos=0.12, sigma_rot=0.5) for _ in range(5)]
+    c, q = np.stack([f[0] for f in frames]), np.stack([f[1] for f in frames])
+    from mythos_b200.input.topology import AllPairs
+
+    efn = (dna1 if model == "dna1" else dna2).create_default_energy_fn(s.topology).with_props(unbonded_neighbors=AllPairs(s.center.shape[0]))
+    plan = kmodel.plan_for(efn.energy_fns)
+    cd, qd = torch.tensor(c, device=DEV), torch.tensor(q, device=DEV)
+    topo = plan.topology(cd.shape[1], cd.device)
+    params = plan.device_params(cd.device, torch.float64)
+    cot = torch.tensor(np.random.default_rng(2).uniform(0.5, 1.5, size=(len(c), 8)), device=DEV)
+    outs = {}
+    for name, flags, in_kernel, tagged in (("pair kernel", _lib.FLAG_GENERIC_KERNEL, False, False), ("in-kernel cells", 0, True, False),
+                                           ("plain lists", 0, False, False), ("tagged lists", 0, False, True)):
+        src = plan.pairs(cd.device, topo)
+        src.in_kernel = in_kernel
+        if not tagged:
+            src.tag = None
+        terms, _, _, J = functional.energy_and_gradients(plan.model, topo, cd, qd, params, src, cot=cot, want_pos_grad=False,
+                                                         want_param_grad=True, per_frame_param_grad=True, flags=flags)
+        src.verify()
+        outs[name] = (terms.cpu().numpy(), J.cpu().numpy())
+    ref_t, ref_j = outs["pair kernel"]
+    assert np.isfinite(ref_t).all() and np.abs(ref_t[:, 3]).max() > 0 and np.abs(ref_t[:, 4]).max() > 0  # excluded volume and hydrogen bonding are active
+    for name in ("in-kernel cells", "plain lists", "tagged lists"):
+        np.testing.assert_allclose(outs[name][0], ref_t, rtol=1e-10, atol=1e-10 * np.abs(ref_t).max(), err_msg=name)
+        np.testing.assert_allclose(outs[name][1], ref_j, rtol=1e-9, atol=1e-10 * np.abs(ref_j).max(), err_msg=name)
+
+
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_frame_resident_kernel_equals_pair_kernel(workload, dtype):
     """The frame-resident kernel (one CTA per frame, queues in shared memory) and the one-thread-per-pair kernel are
