@@ -310,12 +310,17 @@ def interaction_range(plan: "Plan") -> float:
     return reach * (1.0 + 1e-9) + 1e-9
 
 
+@lru_cache(maxsize=1)
+def _param_index() -> dict:
+    return {n: i for i, n in enumerate(_lib.param_names())}
+
+
 def support_cutoffs(plan: "Plan") -> tuple[float, float]:
     """(centre cutoff of the short-range terms, backbone-site cutoff of Debye-Hueckel), maxima over banks and flavours: the
     supports the neighbour build tags pairs with (MB_NL_TAG_SUPPORTS).  Same formula as the kernels' own short-range cutoff."""
-    vec = plan.params_vector().detach()
+    vec = plan.params_vector().detach().tolist()  # (one host read: this runs in front of the first launch of every pass)
     P = _lib.param_count()
-    idx = {n: i for i, n in enumerate(_lib.param_names())}
+    idx = _param_index()
     ob = oh = os_ = 0.0
     for k in range(2 if plan.hybrid else 1):
         g = plan.model.geom[k]
