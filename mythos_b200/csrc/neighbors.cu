@@ -33,6 +33,8 @@
 // Rows mode (MB_NL_ROWS) replaces 6-8 by ONE walk that writes a fixed-width row per nucleotide with the unused slots set
 // to the padding value N: still a valid OrderedSparse list (consumers mask entries >= N wherever they are), at half the
 // cost -- the shape the energy kernels of this library are fed with.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mb {
@@ -158,11 +160,9 @@ __global__ void k_nl_bounds(NlDev<T> a) {
   }
 }
 
-// one thread per frame: grid dimensions
+// grid dimensions of one frame from its bounding box (free space) or the box (periodic)
 template <class T>
-__global__ void k_nl_grid(NlDev<T> a) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= a.n_frames) return;
+__device__ __forceinline__ NlGrid<T> make_grid(const NlDev<T>& a, const double lo[3], const double hi[3]) {
   NlGrid<T> g;
   T ext[3];
   for (int d = 0; d < 3; ++d) {
@@ -170,7 +170,7 @@ __global__ void k_nl_grid(NlDev<T> a) {
       g.origin[d] = T(0);
       ext[d] = a.box[d];
     } else {
-      const double l = ord_decode(a.bounds[6 * f + d]), h = ord_decode(a.bounds[6 * f + 3 + d]);
+      const double l = lo[d], h = hi[d];
       g.origin[d] = T(l);
       ext[d] = T(h - l);
       if (!(ext[d] >= T(0))) ext[d] = T(0);
@@ -206,7 +206,21 @@ __global__ void k_nl_grid(NlDev<T> a) {
     g.inv[d] = T(1) / g.width[d];
   }
   g._pad = 0;
-  a.grid[f] = g;
+  return g;
+}
+
+// one thread per frame: grid dimensions
+template <class T>
+__global__ void k_nl_grid(NlDev<T> a) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= a.n_frames) return;
+  double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  if (!a.periodic)
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = ord_decode(a.bounds[6 * f + d]);
+      hi[d] = ord_decode(a.bounds[6 * f + 3 + d]);
+    }
+  a.grid[f] = make_grid(a, lo, hi);
 }
 
 template <class T>
@@ -652,6 +666,277 @@ __global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ frame-resident build
+// Warp-slot builds of systems whose cell table and cell-ordered records fit in shared memory (free space): ONE launch does
+// what bounds / grid / bin / scan / scatter / rank / walk do above in eleven, a CTA per frame (persistent, two CTAs per SM):
+//   bounds (block reduction) -> grid -> cell histogram (shared atomics) -> in-place exclusive scan -> scatter (the same
+//   array is the cursor: after the scatter entry c+1 holds the end of cell c) -> rank by id inside the cell, records into
+//   shared memory -> walk out of shared memory.
+// The walk first collects a lane's non-empty candidate runs (rows of the forward half shell, unrolled for the stencil half
+// width S: no division, one row base) into shared memory, then runs ONE flat loop over its candidates: the lanes of a warp
+// stay together for max(total candidates) iterations instead of sum over rows of max(row candidates).
+// Same grid, same cell order, same warp partition, same order inside a slot as k_nl_walk<T,3,false>: identical lists.
+constexpr int kFrBlock = 256;
+constexpr int kFrRowsMax = 14;  // S = 2: 1 + 2 + 2 * 5 rows, + the sentinel
+
+template <class T>
+struct NlFrameLayout {
+  size_t off_rec, off_runs, off_stage, bytes;
+  __host__ __device__ NlFrameLayout(int n, int cmax, int lane_slots) {
+    size_t o = (sizeof(int32_t) * (size_t)(cmax + 2) + 15) & ~size_t(15);
+    off_rec = o;
+    o += sizeof(NlRec<T>) * (size_t)n;
+    off_runs = o;
+    const size_t runs = sizeof(uint32_t) * kFrRowsMax * kFrBlock, ids = sizeof(uint16_t) * 2 * (size_t)n;
+    o += ((runs > ids ? runs : ids) + 15) & ~size_t(15);  // cell / order ids are dead once the records are written
+    off_stage = o;
+    o += (sizeof(uint16_t) * (size_t)kFrBlock * lane_slots + 15) & ~size_t(15);
+    bytes = o;
+  }
+};
+
+template <class T, int S>
+__device__ __forceinline__ int frame_runs(const NlGrid<T>& g, const int32_t* arr, const int cc[3], int p, bool live, uint32_t* runs) {
+  // the lane's candidate runs [rs, re) in cell order, row by row of the forward half shell; non-empty ones are kept
+  const int n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+  const int xlo = cc[0] - S < 0 ? 0 : cc[0] - S, xhi1 = (cc[0] + S >= n0 ? n0 - 1 : cc[0] + S) + 1;
+  const int base0 = n0 * (cc[1] + n1 * cc[2]), zstride = n0 * n1;
+  int nruns = 0;
+#pragma unroll
+  for (int row = 0; row < 1 + S + S * (2 * S + 1); ++row) {
+    const int dz = row <= S ? 0 : 1 + (row - S - 1) / (2 * S + 1);
+    const int dy = row <= S ? row : (row - S - 1) % (2 * S + 1) - S;
+    const int by = cc[1] + dy, bz = cc[2] + dz;
+    if (live && by >= 0 && by < n1 && bz < n2) {
+      const int rb = base0 + dy * n0 + dz * zstride;
+      int rs = arr[rb + (row == 0 ? cc[0] : xlo)];
+      const int re = arr[rb + xhi1];
+      if (row == 0) rs = p + 1 > rs ? p + 1 : rs;  // own cell: ids ascend, partners come after
+      if (rs < re) {
+        runs[nruns * kFrBlock] = uint32_t(rs) | (uint32_t(re) << 16);
+        ++nruns;
+      }
+    }
+  }
+  runs[nruns * kFrBlock] = 0u;  // sentinel: an empty run ends the lane's walk
+  return nruns;
+}
+
+template <class T>
+__global__ void __launch_bounds__(kFrBlock, 2) k_nl_frame(NlDev<T> a) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  __shared__ double s_lo[kFrBlock / 32][3], s_hi[kFrBlock / 32][3];
+  __shared__ int32_t s_warp[kFrBlock / 32];
+  __shared__ int32_t s_stat[4];  // pairs written, longest lane row, largest warp total, overflow bits
+  const NlFrameLayout<T> lay(a.n, a.cmax, a.lane_slots);
+  int32_t* arr = reinterpret_cast<int32_t*>(fsm);  // arr[c] = start of cell c in cell order, arr[ncell] = n
+  int32_t* hist = arr + 1;
+  NlRec<T>* rec = reinterpret_cast<NlRec<T>*>(fsm + lay.off_rec);
+  uint32_t* runs = reinterpret_cast<uint32_t*>(fsm + lay.off_runs);
+  uint16_t* cell16 = reinterpret_cast<uint16_t*>(fsm + lay.off_runs);
+  uint16_t* order16 = cell16 + a.n;
+  uint16_t* stage_all = reinterpret_cast<uint16_t*>(fsm + lay.off_stage);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = a.n;
+  const int lane_slots = a.lane_slots, wpf = (n + 31) / 32;
+  const int tag_bits = int(a.tag_bits);
+
+  for (int f = blockIdx.x; f < a.n_frames; f += gridDim.x) {
+    const T* ctr = a.center + 3ll * f * n;
+    // ---- bounds
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = tid; i < n; i += kFrBlock) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double x = double(ctr[3 * i + d]);
+        lo[d] = x < lo[d] ? x : lo[d];
+        hi[d] = x > hi[d] ? x : hi[d];
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double l = __shfl_xor_sync(0xffffffffu, lo[d], o), h = __shfl_xor_sync(0xffffffffu, hi[d], o);
+        lo[d] = l < lo[d] ? l : lo[d];
+        hi[d] = h > hi[d] ? h : hi[d];
+      }
+      if (lane == 0) {
+        s_lo[warp][d] = lo[d];
+        s_hi[warp][d] = hi[d];
+      }
+    }
+    if (tid < 4) s_stat[tid] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = s_lo[0][d];
+      hi[d] = s_hi[0][d];
+#pragma unroll
+      for (int w = 1; w < kFrBlock / 32; ++w) {
+        lo[d] = s_lo[w][d] < lo[d] ? s_lo[w][d] : lo[d];
+        hi[d] = s_hi[w][d] > hi[d] ? s_hi[w][d] : hi[d];
+      }
+    }
+    const NlGrid<T> g = make_grid(a, lo, hi);
+    const int ncell = g.ncell;
+    // ---- histogram
+    for (int c = tid; c <= ncell; c += kFrBlock) arr[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kFrBlock) {
+      int cc[3];
+      const int cid = cell_id(a, g, ctr + 3 * i, cc);
+      cell16[i] = uint16_t(cid);
+      atomicAdd(&hist[cid], 1);
+    }
+    __syncthreads();
+    // ---- exclusive scan of hist[0 .. ncell) in place (a thread owns a contiguous piece)
+    {
+      const int per = (ncell + kFrBlock - 1) / kFrBlock, c0 = tid * per, c1 = c0 + per < ncell ? c0 + per : ncell;
+      int t = 0;
+      for (int c = c0; c < c1; ++c) t += hist[c];
+      int x = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) s_warp[warp] = x;
+      __syncthreads();
+      int run = x - t;
+      for (int w = 0; w < warp; ++w) run += s_warp[w];
+      for (int c = c0; c < c1; ++c) {
+        const int v = hist[c];
+        hist[c] = run;
+        run += v;
+      }
+    }
+    __syncthreads();
+    // ---- scatter: hist[c] walks from the start of cell c to its end, i.e. arr[c+1] becomes the start of cell c+1
+    for (int i = tid; i < n; i += kFrBlock) order16[atomicAdd(&hist[cell16[i]], 1)] = uint16_t(i);
+    __syncthreads();
+    // ---- rank inside the cell by id, cell-ordered records
+    for (int pos = tid; pos < n; pos += kFrBlock) {
+      const int id = order16[pos], c = cell16[id];
+      const int b = arr[c], e = arr[c + 1];
+      int rank = 0;
+      for (int q = b; q < e; ++q) rank += order16[q] < id;
+      NlRec<T> r{};
+      r.x = ctr[3 * id];
+      r.y = ctr[3 * id + 1];
+      r.z = ctr[3 * id + 2];
+      r.id = id;
+      rec[b + rank] = r;
+    }
+    __syncthreads();
+    // ---- walk: warp gw covers cell-order positions [32 gw, 32 gw + 32)
+    int w_pairs = 0, w_lane = 0, w_total = 0, w_flags = 0;
+    uint16_t* stage = stage_all + (size_t)tid * lane_slots;
+    const uint16_t* wstage = stage_all + (size_t)(warp * 32) * lane_slots;
+    for (int gw = warp; gw < wpf; gw += kFrBlock / 32) {
+      const int p = gw * 32 + lane;
+      const bool live = p < n;
+      const NlRec<T> me = rec[live ? p : 0];
+      const int i = me.id;
+      const T xi = me.x, yi = me.y, zi = me.z;
+      int cc[3];
+      {
+        const T c[3] = {xi, yi, zi};
+        cell_id(a, g, c, cc);
+      }
+      const int4 ex = *reinterpret_cast<const int4*>(a.excl + i * kMaxExcl);
+      const int nruns = g.S == 2 ? frame_runs<T, 2>(g, arr, cc, p, live, runs + tid)
+                                 : frame_runs<T, 1>(g, arr, cc, p, live, runs + tid);
+      int found = 0;
+      {
+        const T cut2 = a.cut2;
+        const uint32_t* rp = runs + tid;
+        uint32_t v = *rp;
+        int q = int(v & 0xffffu), qe = int(v >> 16);
+        while (q < qe) {
+          const NlRec<T> c = rec[q];
+          ++q;
+          const T ddx = xi - c.x, ddy = yi - c.y, ddz = zi - c.z;
+          const T d2 = add_rn(add_rn(mul_rn(ddx, ddx), mul_rn(ddy, ddy)), mul_rn(ddz, ddz));
+          const int j = c.id;
+          if (q == qe) {  // next run (the list ends with an empty one)
+            rp += kFrBlock;
+            v = *rp;
+            q = int(v & 0xffffu);
+            qe = int(v >> 16);
+          }
+          if (d2 < cut2 && j != ex.x && j != ex.y && j != ex.z && j != ex.w) {
+            if (found < lane_slots) stage[found] = uint16_t(j);
+            ++found;
+          }
+        }
+      }
+      // the warp's pairs into its slot in lane-major order (owner by owner), the rest of the slot padded with n
+      const int mine = found < lane_slots ? found : lane_slots;
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int longest = found;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const int y = __shfl_xor_sync(0xffffffffu, longest, o);
+        longest = y > longest ? y : longest;
+      }
+      int32_t* o0 = a.pairs + (long long)f * 2 * a.capacity + a.slot_base + (long long)gw * a.slot_width;
+      int32_t* o1 = o0 + a.capacity;
+      const int sw = int(a.slot_width);
+      const int excl_before = incl - mine;
+      __syncwarp();
+      // four owners at a time, eight lanes each: an owner's partners are one contiguous run of the slot
+      {
+        const int grp = lane >> 3, gl = lane & 7;
+#pragma unroll 2
+        for (int m = 0; m < 8; ++m) {
+          const int L = 4 * m + grp;
+          const int cnt = __shfl_sync(0xffffffffu, mine, L), off = __shfl_sync(0xffffffffu, excl_before, L);
+          const int iL = __shfl_sync(0xffffffffu, i, L);
+          const uint16_t* src = wstage + L * lane_slots;
+          for (int k = gl; k < cnt; k += 8) {
+            if (off + k < sw) {
+              const int j = src[k];
+              o0[off + k] = iL < j ? iL : j;
+              o1[off + k] = (iL < j ? j : iL) | tag_bits;
+            }
+          }
+        }
+        for (int k = total + lane; k < sw; k += 32) {
+          o0[k] = n;
+          o1[k] = n;
+        }
+      }
+      __syncwarp();
+      w_pairs += total < sw ? total : sw;
+      w_lane = longest > w_lane ? longest : w_lane;
+      w_total = total > w_total ? total : w_total;
+      w_flags |= (total > sw ? 1 : 0) | (longest > lane_slots ? 4 : 0);
+    }
+    if (lane == 0) {
+      atomicAdd(&s_stat[0], w_pairs);
+      atomicMax(&s_stat[1], w_lane);
+      atomicMax(&s_stat[2], w_total);
+      if (w_flags) atomicOr(&s_stat[3], w_flags);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      a.count[f] = (a.slot_base == 0 ? 0 : a.count[f]) + s_stat[0];
+      if (a.max_row) {
+        a.max_row[2 * f] = s_stat[1];
+        a.max_row[2 * f + 1] = s_stat[2];
+      }
+      if (s_stat[3]) atomicOr(a.overflow, s_stat[3]);
+    }
+    __syncthreads();  // s_stat, the cell table and the records are reused by the next frame
+  }
+}
+
 // rows mode: entries beyond N * row_width (capacity not a multiple of N) are padding
 template <class T>
 __global__ void k_nl_rows_tail(NlDev<T> a) {
@@ -733,6 +1018,12 @@ static size_t carve(NlDev<T>* a, void* ws, int n, int F) {
   return off;
 }
 
+// MYTHOS_B200_NL_FRAME=0 keeps the multi-launch route for warp-slot builds (A/B tests compare the two routes' lists)
+static bool frame_build_enabled() {
+  const char* e = getenv("MYTHOS_B200_NL_FRAME");
+  return !(e && e[0] == '0');
+}
+
 template <class T>
 static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
   MB_REQUIRE(x, MB_EINVAL_SHAPE, "nl_build: null args");
@@ -774,6 +1065,36 @@ static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
 
   const int F = x->n_frames, n = x->n;
   const long long R = (long long)F * n, FC = (long long)F * a.cmax;
+  if ((x->flags & MB_NL_WARP_SLOTS) && !periodic && n < 32768 && frame_build_enabled()) {
+    // frame-resident route: cell table + records of a frame in shared memory, one launch (see k_nl_frame)
+    const long long wpf = (n + 31) / 32;
+    MB_REQUIRE(x->lane_slots > 0 && x->lane_slots <= 256 && x->slot_width > 0 && x->slot_base >= 0 &&
+                   x->slot_base + wpf * x->slot_width <= x->capacity,
+               MB_EINVAL_SHAPE, "nl_build: warp-slot mode needs 0 < lane_slots <= 256 and slot_base + ceil(n/32) * slot_width <= capacity");
+    const NlFrameLayout<T> lay(n, a.cmax, x->lane_slots);
+    int dev = 0, smem_max = 0, sms = 0;
+    MB_CUDA_CHECK(cudaGetDevice(&dev));
+    MB_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    MB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (lay.bytes <= (size_t)smem_max) {
+      a.lane_slots = x->lane_slots;
+      a.slot_base = x->slot_base;
+      a.slot_width = x->slot_width;
+      a.max_row = x->max_row;
+      a.tag_bits = x->tag_bits & 0xe0000000u;
+      k_nl_excl_init<<<ceil_div((long long)n * kMaxExcl, 256), 256, 0, s>>>(a.excl, n);
+      if (x->n_bonded > 0)
+        k_nl_excl_fill<<<ceil_div(x->n_bonded, 256), 256, 0, s>>>(a.excl, a.bonded, x->n_bonded, n, a.overflow);
+      MB_CUDA_CHECK(cudaFuncSetAttribute(k_nl_frame<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
+      int per_sm = 0;
+      MB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nl_frame<T>, kFrBlock, lay.bytes));
+      if (per_sm < 1) per_sm = 1;
+      const int blocks = F < per_sm * sms ? F : per_sm * sms;
+      k_nl_frame<T><<<blocks, kFrBlock, lay.bytes, s>>>(a);
+      MB_CUDA_CHECK(cudaGetLastError());
+      return MB_OK;
+    }
+  }
   MB_CUDA_CHECK(cudaMemsetAsync(a.cstart, 0, sizeof(int32_t) * (size_t)(FC + 1), s));
   MB_CUDA_CHECK(cudaMemsetAsync(a.cursor, 0, sizeof(int32_t) * (size_t)FC, s));
   k_nl_excl_init<<<ceil_div((long long)n * kMaxExcl, 256), 256, 0, s>>>(a.excl, n);

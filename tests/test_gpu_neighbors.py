@@ -133,6 +133,46 @@ def test_warp_slot_layout_same_pair_set(periodic, dtype):
     assert int(ov3.item()) & 4
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("n_duplex,cutoff", [(17, 2.1), (17, 1.0), (3, 3.4), (40, 1.6)])
+def test_frame_resident_build_writes_the_multi_launch_lists(dtype, n_duplex, cutoff, monkeypatch):
+    """Free-space warp-slot builds run as ONE launch (k_nl_frame: cell table and records of a frame in shared memory); the
+    multi-launch route (MYTHOS_B200_NL_FRAME=0) is the referee: lists, counts, slot statistics and flags are identical."""
+    s = synthetic.assembly(n_duplex, seed=11)
+    rng = np.random.default_rng(2)
+    frames = np.stack([s.center] + [synthetic.jitter(s.center, s.quat, rng)[0] for _ in range(6)])
+    frames[3] += 40.0  # a frame far from the origin
+    c = torch.tensor(frames, dtype=dtype, device=DEV)
+    bonded = torch.tensor(s.topology.bonded_neighbors)
+    n, F = s.center.shape[0], frames.shape[0]
+    wpf = (n + 31) // 32
+    out = {}
+    for route in ("0", "1"):
+        monkeypatch.setenv("MYTHOS_B200_NL_FRAME", route)
+        for lane_slots, W in ((96, 32 * 48), (9, 200)):  # roomy, and too small on purpose (overflow flags, truncation)
+            cap = wpf * W + 8
+            pairs = torch.full((F, 2, cap), -7, dtype=torch.int32, device=DEV)
+            count = torch.empty((F,), dtype=torch.int32, device=DEV)
+            ov = torch.zeros((1,), dtype=torch.int32, device=DEV)
+            mr = torch.empty((F, 2), dtype=torch.int32, device=DEV)
+            neighbors.build_pairs(c, bonded, (0.0, 0.0, 0.0), cutoff, 0.1, cap, None, tag_bits=1 << 30, out=(pairs, count, ov),
+                                  max_row=mr, warp_slots=(lane_slots, 0, W))
+            out[(route, lane_slots)] = (pairs.cpu(), count.cpu(), ov.cpu(), mr.cpu())
+    for lane_slots in (96, 9):
+        a, b = out[("0", lane_slots)], out[("1", lane_slots)]
+        for x, y, what in zip(a, b, ("pairs", "count", "overflow", "max_row")):
+            assert torch.equal(x, y), (what, lane_slots)
+    assert int(out[("1", 96)][2].item()) == 0 and int(out[("1", 96)][1].min()) > 0
+    want = brute_force(np.asarray(c[4].cpu()), s.topology.bonded_neighbors,
+                       (np.float64 if dtype == torch.float64 else np.float32)(cutoff) + (np.float64 if dtype == torch.float64 else np.float32)(0.1),
+                       None, np.float64 if dtype == torch.float64 else np.float32) if n <= 2100 else None
+    if want is not None:
+        p = out[("1", 96)][0][4].numpy()
+        valid = (p[0] < n) & (p[0] >= 0)  # (the 8 entries behind the last slot are never written)
+        got = set(zip(p[0][valid].tolist(), (p[1][valid] & 0x1FFFFFFF).tolist()))
+        assert got == want
+
+
 def test_capacity_overflow_is_reported_and_list_truncated():
     s = synthetic.assembly(2, seed=1)
     c = torch.tensor(s.center[None], device=DEV)
