@@ -852,20 +852,27 @@ __global__ void __launch_bounds__(kFrBlock, 2) k_nl_frame(NlDev<T> a) {
         const uint32_t* rp = runs + tid;
         uint32_t v = *rp;
         int q = int(v & 0xffffu), qe = int(v >> 16);
-        while (q < qe) {
-          const NlRec<T> c = rec[q];
-          ++q;
-          const T ddx = xi - c.x, ddy = yi - c.y, ddz = zi - c.z;
-          const T d2 = add_rn(add_rn(mul_rn(ddx, ddx), mul_rn(ddy, ddy)), mul_rn(ddz, ddz));
-          const int j = c.id;
+        while (q < qe) {  // two candidates of the current run per turn (independent loads and distance chains)
+          const bool two = q + 1 < qe;
+          const NlRec<T> c0 = rec[q], c1 = rec[two ? q + 1 : q];
+          q += two ? 2 : 1;
           if (q == qe) {  // next run (the list ends with an empty one)
             rp += kFrBlock;
             v = *rp;
             q = int(v & 0xffffu);
             qe = int(v >> 16);
           }
-          if (d2 < cut2 && j != ex.x && j != ex.y && j != ex.z && j != ex.w) {
-            if (found < lane_slots) stage[found] = uint16_t(j);
+          const T ax = xi - c0.x, ay = yi - c0.y, az = zi - c0.z;
+          const T bx = xi - c1.x, by = yi - c1.y, bz = zi - c1.z;
+          const T d2a = add_rn(add_rn(mul_rn(ax, ax), mul_rn(ay, ay)), mul_rn(az, az));
+          const T d2b = add_rn(add_rn(mul_rn(bx, bx), mul_rn(by, by)), mul_rn(bz, bz));
+          const int ja = c0.id, jb = c1.id;
+          if (d2a < cut2 && ja != ex.x && ja != ex.y && ja != ex.z && ja != ex.w) {
+            if (found < lane_slots) stage[found] = uint16_t(ja);
+            ++found;
+          }
+          if (two && d2b < cut2 && jb != ex.x && jb != ex.y && jb != ex.z && jb != ex.w) {
+            if (found < lane_slots) stage[found] = uint16_t(jb);
             ++found;
           }
         }
