@@ -676,10 +676,9 @@ __global__ void __launch_bounds__(kNlBlock) k_nl_walk(NlDev<T> a) {
 // width S: no division, one row base) into shared memory, then runs ONE flat loop over its candidates: the lanes of a warp
 // stay together for max(total candidates) iterations instead of sum over rows of max(row candidates).
 // Same grid, same cell order, same warp partition, same order inside a slot as k_nl_walk<T,3,false>: identical lists.
-constexpr int kFrBlock = 256;
 constexpr int kFrRowsMax = 14;  // S = 2: 1 + 2 + 2 * 5 rows, + the sentinel
 
-template <class T>
+template <class T, int kFrBlock>
 struct NlFrameLayout {
   size_t off_rec, off_runs, off_stage, bytes;
   __host__ __device__ NlFrameLayout(int n, int cmax, int lane_slots) {
@@ -695,7 +694,7 @@ struct NlFrameLayout {
   }
 };
 
-template <class T, int S>
+template <class T, int S, int kFrBlock>
 __device__ __forceinline__ int frame_runs(const NlGrid<T>& g, const int32_t* arr, const int cc[3], int p, bool live, uint32_t* runs) {
   // the lane's candidate runs [rs, re) in cell order, row by row of the forward half shell; non-empty ones are kept
   const int n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
@@ -722,13 +721,13 @@ __device__ __forceinline__ int frame_runs(const NlGrid<T>& g, const int32_t* arr
   return nruns;
 }
 
-template <class T>
+template <class T, int kFrBlock>
 __global__ void __launch_bounds__(kFrBlock, 2) k_nl_frame(NlDev<T> a) {
   extern __shared__ __align__(16) unsigned char fsm[];
   __shared__ double s_lo[kFrBlock / 32][3], s_hi[kFrBlock / 32][3];
   __shared__ int32_t s_warp[kFrBlock / 32];
   __shared__ int32_t s_stat[4];  // pairs written, longest lane row, largest warp total, overflow bits
-  const NlFrameLayout<T> lay(a.n, a.cmax, a.lane_slots);
+  const NlFrameLayout<T, kFrBlock> lay(a.n, a.cmax, a.lane_slots);
   int32_t* arr = reinterpret_cast<int32_t*>(fsm);  // arr[c] = start of cell c in cell order, arr[ncell] = n
   int32_t* hist = arr + 1;
   NlRec<T>* rec = reinterpret_cast<NlRec<T>*>(fsm + lay.off_rec);
@@ -844,8 +843,8 @@ __global__ void __launch_bounds__(kFrBlock, 2) k_nl_frame(NlDev<T> a) {
         cell_id(a, g, c, cc);
       }
       const int4 ex = *reinterpret_cast<const int4*>(a.excl + i * kMaxExcl);
-      const int nruns = g.S == 2 ? frame_runs<T, 2>(g, arr, cc, p, live, runs + tid)
-                                 : frame_runs<T, 1>(g, arr, cc, p, live, runs + tid);
+      const int nruns = g.S == 2 ? frame_runs<T, 2, kFrBlock>(g, arr, cc, p, live, runs + tid)
+                                 : frame_runs<T, 1, kFrBlock>(g, arr, cc, p, live, runs + tid);
       int found = 0;
       {
         const T cut2 = a.cut2;
@@ -1031,6 +1030,12 @@ static bool frame_build_enabled() {
   return !(e && e[0] == '0');
 }
 
+static int frame_block_override() {  // MYTHOS_B200_NL_FRAME_BLOCK=256|384|512: development switch
+  const char* e = getenv("MYTHOS_B200_NL_FRAME_BLOCK");
+  const int v = e ? atoi(e) : 0;
+  return (v == 256 || v == 384 || v == 512) ? v : 0;
+}
+
 template <class T>
 static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
   MB_REQUIRE(x, MB_EINVAL_SHAPE, "nl_build: null args");
@@ -1078,12 +1083,18 @@ static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
     MB_REQUIRE(x->lane_slots > 0 && x->lane_slots <= 256 && x->slot_width > 0 && x->slot_base >= 0 &&
                    x->slot_base + wpf * x->slot_width <= x->capacity,
                MB_EINVAL_SHAPE, "nl_build: warp-slot mode needs 0 < lane_slots <= 256 and slot_base + ceil(n/32) * slot_width <= capacity");
-    const NlFrameLayout<T> lay(n, a.cmax, x->lane_slots);
-    int dev = 0, smem_max = 0, sms = 0;
+    int dev = 0, smem_max = 0, smem_sm = 0, sms = 0;
     MB_CUDA_CHECK(cudaGetDevice(&dev));
     MB_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    MB_CUDA_CHECK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
     MB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (lay.bytes <= (size_t)smem_max) {
+    // widest CTA of which two fit on an SM (the walk is latency bound: warps in flight are what counts)
+    const size_t b512 = NlFrameLayout<T, 512>(n, a.cmax, x->lane_slots).bytes, b384 = NlFrameLayout<T, 384>(n, a.cmax, x->lane_slots).bytes,
+                 b256 = NlFrameLayout<T, 256>(n, a.cmax, x->lane_slots).bytes;
+    const size_t two = ((size_t)smem_sm - 2 * 1024) / 2;
+    const int blk = frame_block_override() ? frame_block_override() : (b512 <= two ? 512 : (b384 <= two ? 384 : 256));
+    const size_t bytes = blk == 512 ? b512 : (blk == 384 ? b384 : b256);
+    if (bytes <= (size_t)smem_max) {
       a.lane_slots = x->lane_slots;
       a.slot_base = x->slot_base;
       a.slot_width = x->slot_width;
@@ -1092,12 +1103,17 @@ static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
       k_nl_excl_init<<<ceil_div((long long)n * kMaxExcl, 256), 256, 0, s>>>(a.excl, n);
       if (x->n_bonded > 0)
         k_nl_excl_fill<<<ceil_div(x->n_bonded, 256), 256, 0, s>>>(a.excl, a.bonded, x->n_bonded, n, a.overflow);
-      MB_CUDA_CHECK(cudaFuncSetAttribute(k_nl_frame<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
-      int per_sm = 0;
-      MB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nl_frame<T>, kFrBlock, lay.bytes));
-      if (per_sm < 1) per_sm = 1;
-      const int blocks = F < per_sm * sms ? F : per_sm * sms;
-      k_nl_frame<T><<<blocks, kFrBlock, lay.bytes, s>>>(a);
+      auto launch = [&](auto kern, int threads) -> int {
+        MB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        int per_sm = 0;
+        MB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, bytes));
+        if (per_sm < 1) per_sm = 1;
+        const int blocks = F < per_sm * sms ? F : per_sm * sms;
+        kern<<<blocks, threads, bytes, s>>>(a);
+        return MB_OK;
+      };
+      const int rc = blk == 512 ? launch(k_nl_frame<T, 512>, 512) : (blk == 384 ? launch(k_nl_frame<T, 384>, 384) : launch(k_nl_frame<T, 256>, 256));
+      if (rc != MB_OK) return rc;
       MB_CUDA_CHECK(cudaGetLastError());
       return MB_OK;
     }

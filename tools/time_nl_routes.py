@@ -21,8 +21,9 @@ for r_cut, lane_slots, W in ((float(sys.argv[2]) if len(sys.argv) > 2 else 1.68,
     ov = torch.zeros((1,), dtype=torch.int32, device=dev)
     mr = torch.empty((F, 2), dtype=torch.int32, device=dev)
     ws = None
-    for route in ("0", "1"):
+    for route, blk in (("0", ""), ("1", "256"), ("1", "384"), ("1", "512"), ("1", "")):
         os.environ["MYTHOS_B200_NL_FRAME"] = route
+        os.environ["MYTHOS_B200_NL_FRAME_BLOCK"] = blk
         fn = lambda: neighbors.build_pairs(c32, bonded, (0.0, 0.0, 0.0), r_cut, 0.0, cap, ws, tag_bits=1 << 30, out=(pairs, count, ov), max_row=mr, warp_slots=(lane_slots, 0, W))
         ws = fn()[3]; fn(); torch.cuda.synchronize()
         ts = []
@@ -30,5 +31,5 @@ for r_cut, lane_slots, W in ((float(sys.argv[2]) if len(sys.argv) > 2 else 1.68,
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
-        print(f"cutoff {r_cut}: route {route}: {np.median(ts):.3f} ms per {F} frames; pairs/frame {float(count.float().mean()):.0f} "
+        print(f"cutoff {r_cut}: route {route} block {blk or 'auto'}: {np.median(ts):.3f} ms per {F} frames; pairs/frame {float(count.float().mean()):.0f} "
               f"max lane/warp {mr.max(0).values.tolist()} overflow {int(ov.item())}")
