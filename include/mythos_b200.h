@@ -473,6 +473,15 @@ typedef struct mb_nl_args {
   int32_t _pad3;
   int64_t slot_base;      /* MB_NL_WARP_SLOTS: first entry of this build's slots in each frame's list               */
   int64_t slot_width;     /* MB_NL_WARP_SLOTS: entries per warp slot; slot_base + ceil(n/32)*slot_width <= capacity */
+  /* Conditional rebuild on the device (the update() of jax_md's NeighborList, mythos/utils/neighbors.py:12-59 and
+   * simulators/jax_md/jaxmd.py:82-94, without the host round trip): with `reference` the build of a frame happens only if
+   * some nucleotide moved farther than move_threshold (= dr_threshold / 2) from its reference position; then
+   * reference <- center and rebuilds[frame] += 1.  Otherwise the frame's list, count and max_row stay as they are.  One
+   * launch, no host synchronisation, CUDA-graph capturable.  Free-space MB_NL_WARP_SLOTS builds on the frame-resident
+   * route only (mythos_b200_nl_conditional_supported); anything else returns MB_EINVAL_SHAPE.                            */
+  void* reference;        /* (F,N,3) in/out, dtype of center, or NULL (unconditional build)                          */
+  double move_threshold;
+  int32_t* rebuilds;      /* (F) or NULL                                                                              */
 } mb_nl_args;
 #define MB_NL_TAG_SUPPORTS 0x2u /* internal contract with mythos_b200_energy_* (MB_FLAG_TAGGED_PAIRS): `tag_bits` are OR-ed
                          * into pairs[1][k] (the index is pairs[1][k] & 0x1fffffff) and the build may append to a list.  The
@@ -489,6 +498,11 @@ typedef struct mb_nl_args {
                          * padding value); *overflow bit 0 is set if a row is too narrow; count = pairs found.  Consumers
                          * must scan the whole capacity (pair_count = NULL).                                            */
 size_t mythos_b200_nl_workspace_bytes(int32_t n, int32_t n_frames);
+#define MB_NL_REUSE_EXCLUSIONS 0x8u /* the exclusion table in `workspace` is that of an earlier build with the same bonded list
+                         * (same workspace, same n): skip its two launches (per-step conditional rebuilds of an MD run)   */
+/* 1 if a free-space MB_NL_WARP_SLOTS build of n nucleotides with these slots runs on the frame-resident route (one launch,
+ * cell table and records in shared memory) on the current device, i.e. if mb_nl_args.reference may be used */
+int mythos_b200_nl_conditional_supported(int32_t n, int32_t lane_slots, int32_t real_bytes /* 4 or 8 */);
 int mythos_b200_nl_build_f64(void* cuda_stream, const mb_nl_args* a);
 int mythos_b200_nl_build_f32(void* cuda_stream, const mb_nl_args* a);
 

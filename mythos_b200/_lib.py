@@ -35,6 +35,7 @@ FLAG_LIST_KERNEL = 0x4
 NL_ROWS = 0x1
 NL_TAG_SUPPORTS = 0x2
 NL_WARP_SLOTS = 0x4
+NL_REUSE_EXCLUSIONS = 0x8
 FLAG_TAGGED_PAIRS = 0x8
 MAX_BANKS = 3
 STATUS = {0: "MB_OK", 1: "MB_EINVAL_SHAPE", 2: "MB_EINVAL_MODEL", 3: "MB_ECAPACITY", 4: "MB_ECUDA"}
@@ -156,6 +157,9 @@ class NlArgs(C.Structure):
         ("_pad3", C.c_int32),
         ("slot_base", C.c_int64),
         ("slot_width", C.c_int64),
+        ("reference", C.c_void_p),
+        ("move_threshold", C.c_double),
+        ("rebuilds", C.c_void_p),
     ]
 
 
@@ -217,6 +221,7 @@ _SIGNATURES = {
     "mythos_b200_support_points_f64": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int32, C.c_int32] + [C.c_void_p] * 6),
     "mythos_b200_support_points_f32": (C.c_int, [C.c_void_p, C.POINTER(Model), C.c_int32, C.c_int32] + [C.c_void_p] * 6),
     "mythos_b200_nl_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "mythos_b200_nl_conditional_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     "mythos_b200_nl_build_f64": (C.c_int, [C.c_void_p, C.POINTER(NlArgs)]),
     "mythos_b200_nl_build_f32": (C.c_int, [C.c_void_p, C.POINTER(NlArgs)]),
     "mythos_b200_langevin_f64": (C.c_int, [C.c_void_p, C.POINTER(LangevinArgs)]),

@@ -34,6 +34,9 @@
 // to the padding value N: still a valid OrderedSparse list (consumers mask entries >= N wherever they are), at half the
 // cost -- the shape the energy kernels of this library are fed with.
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -84,6 +87,9 @@ struct NlDev {
   long long slot_base, slot_width;  // warp-slot mode: this build's slots start at slot_base of each frame's list
   uint32_t tag_bits;             // OR-ed into the second index of every pair written (MB_NL_TAG_SUPPORTS)
   const int32_t* append_count;   // (F) entries already in each frame's list: this build appends after them, or nullptr
+  T* reference;                  // (F,N,3) centres at the last build: conditional rebuild (k_nl_frame), or nullptr
+  T move2;                       // squared displacement beyond which a frame is rebuilt
+  int32_t* rebuilds;             // (F) rebuild counters, or nullptr
   // workspace
   int32_t* excl;       // (N, kMaxExcl)
   unsigned long long* bounds;  // (F, 6) ordered-integer min / max corners
@@ -741,6 +747,30 @@ __global__ void __launch_bounds__(kFrBlock, 2) k_nl_frame(NlDev<T> a) {
 
   for (int f = blockIdx.x; f < a.n_frames; f += gridDim.x) {
     const T* ctr = a.center + 3ll * f * n;
+    if (a.reference) {
+      // conditional rebuild: has any nucleotide moved farther than the threshold since the frame's last build?
+      T* ref = a.reference + 3ll * f * n;
+      T m = T(0);
+      for (int i = tid; i < n; i += kFrBlock) {
+        const T dx = ctr[3 * i] - ref[3 * i], dy = ctr[3 * i + 1] - ref[3 * i + 1], dz = ctr[3 * i + 2] - ref[3 * i + 2];
+        const T d2 = dx * dx + dy * dy + dz * dz;
+        m = d2 > m ? d2 : m;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const T y = __shfl_xor_sync(0xffffffffu, m, o);
+        m = y > m ? y : m;
+      }
+      if (lane == 0) s_lo[warp][0] = double(m);
+      __syncthreads();
+      double mm = s_lo[0][0];
+#pragma unroll
+      for (int w = 1; w < kFrBlock / 32; ++w) mm = s_lo[w][0] > mm ? s_lo[w][0] : mm;
+      __syncthreads();  // s_lo is reused by the bounds below
+      if (!(mm > double(a.move2))) continue;  // (the same decision in every thread of the CTA)
+      for (int i = tid; i < 3 * n; i += kFrBlock) ref[i] = ctr[i];
+      if (tid == 0 && a.rebuilds) a.rebuilds[f] += 1;
+    }
     // ---- bounds
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int i = tid; i < n; i += kFrBlock) {
@@ -1073,6 +1103,9 @@ static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
   MB_REQUIRE(!tag || (x->n < (1 << 29) && !(x->tag_bits & 0x1fffffffu)), MB_EINVAL_SHAPE, "nl_build: tag bits must be in the top 3 bits, n < 2^29");
   a.tag_bits = tag ? x->tag_bits : 0u;
   a.append_count = tag ? x->append_count : nullptr;
+  a.reference = static_cast<T*>(x->reference);
+  a.move2 = T(x->move_threshold) * T(x->move_threshold);
+  a.rebuilds = x->rebuilds;
   carve<T>(&a, x->workspace, x->n, x->n_frames);
 
   const int F = x->n_frames, n = x->n;
@@ -1100,14 +1133,37 @@ static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
       a.slot_width = x->slot_width;
       a.max_row = x->max_row;
       a.tag_bits = x->tag_bits & 0xe0000000u;
-      k_nl_excl_init<<<ceil_div((long long)n * kMaxExcl, 256), 256, 0, s>>>(a.excl, n);
-      if (x->n_bonded > 0)
-        k_nl_excl_fill<<<ceil_div(x->n_bonded, 256), 256, 0, s>>>(a.excl, a.bonded, x->n_bonded, n, a.overflow);
+      if (!(x->flags & MB_NL_REUSE_EXCLUSIONS)) {
+        k_nl_excl_init<<<ceil_div((long long)n * kMaxExcl, 256), 256, 0, s>>>(a.excl, n);
+        if (x->n_bonded > 0)
+          k_nl_excl_fill<<<ceil_div(x->n_bonded, 256), 256, 0, s>>>(a.excl, a.bonded, x->n_bonded, n, a.overflow);
+      }
       auto launch = [&](auto kern, int threads) -> int {
-        MB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        // (the attribute only ever grows, the occupancy is remembered per size: nothing but the launch while a graph is captured)
+        static std::mutex mu;
+        // (the three block widths share one function-pointer type, hence one set of statics: the kernel is part of the key)
+        static std::map<std::pair<const void*, int>, size_t> granted;
+        static std::map<std::pair<std::pair<const void*, int>, size_t>, int> known;
+        const std::pair<const void*, int> kd{reinterpret_cast<const void*>(kern), dev};
         int per_sm = 0;
-        MB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, bytes));
-        if (per_sm < 1) per_sm = 1;
+        bool raise = false;
+        {
+          std::lock_guard<std::mutex> lock(mu);
+          auto it = known.find({kd, bytes});
+          if (it != known.end()) per_sm = it->second;
+          raise = granted[kd] < bytes;
+        }
+        if (raise) {
+          MB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+          std::lock_guard<std::mutex> lock(mu);
+          if (granted[kd] < bytes) granted[kd] = bytes;
+        }
+        if (!per_sm) {
+          MB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, bytes));
+          if (per_sm < 1) per_sm = 1;
+          std::lock_guard<std::mutex> lock(mu);
+          known[{kd, bytes}] = per_sm;
+        }
         const int blocks = F < per_sm * sms ? F : per_sm * sms;
         kern<<<blocks, threads, bytes, s>>>(a);
         return MB_OK;
@@ -1118,6 +1174,7 @@ static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
       return MB_OK;
     }
   }
+  MB_REQUIRE(!x->reference, MB_EINVAL_SHAPE, "nl_build: the conditional rebuild (reference) needs a free-space warp-slot build on the frame-resident route");
   MB_CUDA_CHECK(cudaMemsetAsync(a.cstart, 0, sizeof(int32_t) * (size_t)(FC + 1), s));
   MB_CUDA_CHECK(cudaMemsetAsync(a.cursor, 0, sizeof(int32_t) * (size_t)FC, s));
   k_nl_excl_init<<<ceil_div((long long)n * kMaxExcl, 256), 256, 0, s>>>(a.excl, n);
@@ -1180,6 +1237,15 @@ static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
 extern "C" size_t mythos_b200_nl_workspace_bytes(int32_t n, int32_t n_frames) {
   if (n <= 0 || n_frames <= 0) return 0;
   return mb::carve<double>(nullptr, nullptr, n, n_frames);
+}
+extern "C" int mythos_b200_nl_conditional_supported(int32_t n, int32_t lane_slots, int32_t real_bytes) {
+  if (n <= 0 || n >= 32768 || lane_slots <= 0 || lane_slots > 256 || !mb::frame_build_enabled()) return 0;
+  int dev = 0, smem_max = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+  const int cmax = mb::cells_per_frame(n);
+  const size_t b = real_bytes == 4 ? mb::NlFrameLayout<float, 256>(n, cmax, lane_slots).bytes : mb::NlFrameLayout<double, 256>(n, cmax, lane_slots).bytes;
+  return b <= (size_t)smem_max ? 1 : 0;
 }
 extern "C" int mythos_b200_nl_build_f64(void* stream, const mb_nl_args* a) {
   return mb::nl_impl<double>(static_cast<cudaStream_t>(stream), a);

@@ -237,7 +237,9 @@ class MDSimulator:
         dev, dtype = init_state.center.device, init_state.center.dtype
         n = init_state.center.shape[0]
         traj = (torch.empty((n_steps, n, 3), device=dev, dtype=dtype), torch.empty((n_steps, n, 4), device=dev, dtype=dtype))
-        static_list = isinstance(neighbors, NoNeighborList)
+        # a list that never changes, or one that updates itself on the device in place (utils.neighbors: warp-slot layout
+        # with the conditional rebuild): both are fixed launch sequences, so the step is captured in a CUDA graph
+        static_list = isinstance(neighbors, NoNeighborList) or getattr(neighbors, "slots", None) is not None
         if self.use_cuda_graph and static_list and hasattr(step_fn, "launch"):
             self._run_graph(step_fn, state, neighbors, traj, n_steps)
         else:
@@ -260,9 +262,12 @@ class MDSimulator:
             # kernel (bonded + unbonded blocks in one grid, accumulating (dE/dcenter, dE/dquat) into the state's buffers)
             step_fn.launch(state, 2 if one_step.started else 0, traj=traj, advance=True, zero_forces=True)
             one_step.started = True
+            if dynamic:  # third launch: displacement test + (rarely) the rebuild of the list, in place, on the device
+                neighbors.update(c)
             f.accumulate_into(c, q, state.force.center, state.force.orientation.vec)
 
         one_step.started = False
+        dynamic = getattr(neighbors, "slots", None) is not None
         stream = torch.cuda.Stream(device=c.device)
         stream.wait_stream(torch.cuda.current_stream(c.device))
         with torch.cuda.stream(stream):

@@ -35,6 +35,10 @@ def build_pairs(
     out: tuple | None = None,
     append_count: torch.Tensor | None = None,
     warp_slots: tuple[int, int, int] | None = None,
+    reference: torch.Tensor | None = None,
+    move_threshold: float = 0.0,
+    rebuilds: torch.Tensor | None = None,
+    reuse_exclusions: bool = False,
 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """Raw batched build.  center (F,N,3) on the device -> (pairs (F,2,capacity) int32, count (F,), overflow (1,), workspace).
 
@@ -77,10 +81,20 @@ def build_pairs(
         a.flags |= _lib.NL_TAG_SUPPORTS
         a.tag_bits = int(tag_bits)
         a.append_count = append_count.data_ptr() if append_count is not None else None
+    if reference is not None:  # conditional rebuild on the device: (F,N,3) centres at the last build, in/out
+        if reference.shape != center.shape or reference.dtype != center.dtype or not reference.is_contiguous() or reference.device != dev:
+            raise _lib.MythosB200Error("reference must be a contiguous (F,N,3) tensor like center")
+        a.reference, a.move_threshold = reference.data_ptr(), float(move_threshold)
+        a.rebuilds = rebuilds.data_ptr() if rebuilds is not None else None
+    if reuse_exclusions:
+        a.flags |= _lib.NL_REUSE_EXCLUSIONS
     fn = getattr(_lib.lib(), f"mythos_b200_nl_build_{_lib.suffix(center.dtype)}")
     with torch.cuda.device(dev):
         _lib.check(fn(_lib.current_stream(dev), C.byref(a)), "mythos_b200_nl_build")
     return pairs, count, overflow, workspace
+
+
+DEVICE_SIDE_UPDATE = True  # False: always the compact list + host-checked update (the reference's control flow)
 
 
 @dc.dataclass
@@ -93,6 +107,11 @@ class NeighborList:
     count: torch.Tensor  # (1,) pairs found at the last rebuild
     fns: "NeighborListFns"
     workspace: torch.Tensor | None = None
+    # device-side update (free space, small systems): the list lives in the one-pass warp-slot layout (a padded OrderedSparse
+    # list like any other) and update() is ONE conditional launch that rebuilds it in place -- no host round trip per step
+    slots: tuple[int, int] | None = None  # (lane_slots, slot_width)
+    rebuilds: torch.Tensor | None = None  # (1,) int32 on the device: rebuilds since allocate()
+    max_row: torch.Tensor | None = None  # (1,2) int32: longest lane row / warp total of the last rebuild
 
     def update(self, position: torch.Tensor, force_rebuild: bool = False) -> "NeighborList":
         return self.fns.update(position, self, force_rebuild=force_rebuild)
@@ -107,6 +126,14 @@ class NeighborListFns:
     dr_threshold: float
     capacity_multiplier: float = 1.25
 
+    def _bonded_on(self, device) -> torch.Tensor:
+        """The bonded list on the device (cached: update() runs every MD step, also while a CUDA graph is captured)."""
+        cache = self.__dict__.setdefault("_bonded_dev", {})
+        b = cache.get(str(device))
+        if b is None:
+            b = cache[str(device)] = self.bonded_neighbors.to(device=device, dtype=torch.int32).contiguous().reshape(-1, 2)
+        return b
+
     def _centers(self, position) -> torch.Tensor:
         c = position.center if hasattr(position, "center") else position
         return c
@@ -114,6 +141,9 @@ class NeighborListFns:
     def allocate(self, position, extra_capacity: int = 0) -> NeighborList:
         """Size the list from the current configuration (host sync, like jax_md's allocate) and build it."""
         c = self._centers(position)
+        nl = self._allocate_on_device(c, extra_capacity)
+        if nl is not None:
+            return nl
         probe, count, overflow, ws = build_pairs(c.unsqueeze(0), self.bonded_neighbors, self.box, self.r_cutoff, self.dr_threshold, 1)
         n_found = int(count.item())
         capacity = (max(int(n_found * self.capacity_multiplier) + extra_capacity, 1) + 3) // 4 * 4  # multiple of 4: 128-bit pair stores
@@ -122,10 +152,50 @@ class NeighborListFns:
         )
         return NeighborList(idx=pairs[0], reference_position=c.detach().clone(), did_buffer_overflow=overflow, count=count, fns=self, workspace=ws)
 
+    def _allocate_on_device(self, c: torch.Tensor, extra_capacity: int) -> NeighborList | None:
+        """The list in the warp-slot layout with a device-side conditional update, where the frame-resident build applies
+        (free space, cell table and records of the system fit in shared memory); None otherwise."""
+        if not DEVICE_SIDE_UPDATE or any(self.box) or not c.is_cuda or c.dim() != 2:
+            return None
+        with torch.cuda.device(c.device):
+            if not _lib.lib().mythos_b200_nl_conditional_supported(c.shape[0], 256, c.element_size()):
+                return None
+        n = c.shape[0]
+        wpf = (n + 31) // 32
+        cc = c.detach().contiguous().unsqueeze(0)
+        mr = torch.zeros((1, 2), dtype=torch.int32, device=c.device)
+        _, _, _, ws = build_pairs(cc, self._bonded_on(c.device), self.box, self.r_cutoff, self.dr_threshold, wpf * 32 * 256, None,
+                                  max_row=mr, warp_slots=(256, 0, 32 * 256))  # probe with the widest slots: sizes only
+        lane_max, warp_max = (int(v) for v in mr[0].tolist())
+        lane_slots = min(int(lane_max * self.capacity_multiplier) + 4, 256)
+        slot_width = (int(warp_max * self.capacity_multiplier) + -(-extra_capacity // wpf) + 16 + 3) // 4 * 4
+        capacity = wpf * slot_width
+        pairs = torch.empty((1, 2, capacity), dtype=torch.int32, device=c.device)
+        count = torch.zeros((1,), dtype=torch.int32, device=c.device)
+        overflow = torch.zeros((1,), dtype=torch.int32, device=c.device)
+        build_pairs(cc, self._bonded_on(c.device), self.box, self.r_cutoff, self.dr_threshold, capacity, ws, max_row=mr,
+                    out=(pairs, count, overflow), warp_slots=(lane_slots, 0, slot_width))
+        return NeighborList(idx=pairs[0], reference_position=cc.clone()[0], did_buffer_overflow=overflow, count=count, fns=self,
+                            workspace=ws, slots=(lane_slots, slot_width), rebuilds=torch.zeros((1,), dtype=torch.int32, device=c.device),
+                            max_row=mr)
+
     def update(self, position, nbrs: NeighborList, force_rebuild: bool = False) -> NeighborList:
         """Rebuild if any nucleotide moved more than dr_threshold/2 since the last build (checked on the device;
         the rebuild itself is enqueued unconditionally when ``force_rebuild`` or dr_threshold == 0)."""
         c = self._centers(position)
+        if nbrs.slots is not None:
+            # one launch: displacement test, reference update and rebuild all happen on the device, in place (the object
+            # handed back is the same one; bit 0 / 2 of did_buffer_overflow report slots that became too small)
+            cc = c.detach().contiguous().unsqueeze(0)
+            capacity = nbrs.idx.shape[-1]
+            build_pairs(cc, self._bonded_on(c.device), self.box, self.r_cutoff, self.dr_threshold, capacity, nbrs.workspace,
+                        max_row=nbrs.max_row, out=(nbrs.idx.unsqueeze(0), nbrs.count, nbrs.did_buffer_overflow),
+                        warp_slots=(nbrs.slots[0], 0, nbrs.slots[1]),
+                        reference=None if force_rebuild else nbrs.reference_position.unsqueeze(0),
+                        move_threshold=0.5 * self.dr_threshold, rebuilds=nbrs.rebuilds, reuse_exclusions=True)
+            if force_rebuild:
+                nbrs.reference_position.copy_(cc[0])
+            return nbrs
         if not force_rebuild and self.dr_threshold > 0:
             d = space.Displacement(self.box if any(self.box) else None)(c, nbrs.reference_position)
             moved = (d * d).sum(-1).max() > (0.5 * self.dr_threshold) ** 2

@@ -182,7 +182,8 @@ def test_capacity_overflow_is_reported_and_list_truncated():
     assert np.all(p[0] < p[1]) and p.max() < s.center.shape[0]
 
 
-def test_listed_pairs_give_all_pairs_energy_and_update_protocol():
+def test_listed_pairs_give_all_pairs_energy_and_update_protocol(monkeypatch):
+    monkeypatch.setattr(neighbors, "DEVICE_SIDE_UPDATE", False)  # the reference's control flow: host-checked update, new object
     s = synthetic.assembly(2, seed=4)
     top = s.topology
     efn = dna2.create_default_energy_fn(top)  # N=240 < 512: explicit all-pairs list
@@ -203,6 +204,51 @@ def test_listed_pairs_give_all_pairs_energy_and_update_protocol():
     e_nl2 = efn.with_props(unbonded_neighbors=nbrs2.idx).compute_terms(moved)
     if int(nbrs2.did_buffer_overflow.item()) == 0:
         np.testing.assert_allclose(e_nl2.cpu().numpy(), e_all2.cpu().numpy(), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_device_side_update_rebuilds_in_place_only_after_a_move(dtype):
+    """Free-space lists of small systems live in the warp-slot layout and update() is ONE conditional launch: no rebuild
+    below dr_threshold/2 (list, reference and counter untouched), a rebuild in place above it (reference <- positions,
+    counter + 1, energies of the listed pairs = energies of all pairs); a slot that became too small is flagged."""
+    s = synthetic.assembly(2, seed=4)
+    top = s.topology
+    efn = dna2.create_default_energy_fn(top)
+    body = RigidBody(torch.tensor(s.center, device=DEV, dtype=dtype), Quaternion(torch.tensor(s.quat, device=DEV, dtype=dtype)))
+    tol = 1e-12 if dtype == torch.float64 else 2e-4
+    e_all = efn.compute_terms(body)
+    fns = neighbors.get_neighbor_list_fn(top.bonded_neighbors, top.n_nucleotides, space.free()[0], None, r_cutoff=3.3, dr_threshold=0.2)
+    nbrs = fns.allocate(body)
+    assert nbrs.slots is not None and nbrs.idx.shape[0] == 2 and int(nbrs.did_buffer_overflow.item()) == 0
+    assert nbrs.reference_position.shape == body.center.shape
+    n = top.n_nucleotides
+    want = brute_force(np.asarray(body.center.cpu()), top.bonded_neighbors, np.asarray(body.center.cpu()).dtype.type(3.3) + np.asarray(body.center.cpu()).dtype.type(0.2),
+                       None, np.asarray(body.center.cpu()).dtype.type)
+    assert to_set(nbrs.idx, n) == want and int(nbrs.count.item()) == len(want)
+    e_nl = efn.with_props(unbonded_neighbors=nbrs.idx).compute_terms(body)
+    np.testing.assert_allclose(e_nl.cpu().numpy(), e_all.cpu().numpy(), rtol=tol, atol=tol)
+    before, ref_before = nbrs.idx.clone(), nbrs.reference_position.clone()
+    # 0.09 < dr_threshold / 2: nothing happens
+    same = nbrs.update(body.center + torch.tensor([0.09, 0.0, 0.0], device=DEV, dtype=dtype))
+    assert same is nbrs and int(nbrs.rebuilds.item()) == 0
+    assert torch.equal(nbrs.idx, before) and torch.equal(nbrs.reference_position, ref_before)
+    # every other nucleotide moves by 0.5: rebuilt in place
+    moved = RigidBody(body.center + torch.tensor([0.5, 0.0, 0.0], device=DEV, dtype=dtype)
+                      * (torch.arange(n, device=DEV) % 2).unsqueeze(1).to(dtype), body.orientation)
+    again = nbrs.update(moved.center)
+    assert again is nbrs and int(nbrs.rebuilds.item()) == 1
+    assert torch.equal(nbrs.reference_position, moved.center)
+    if int(nbrs.did_buffer_overflow.item()) == 0:
+        e_nl2 = efn.with_props(unbonded_neighbors=nbrs.idx).compute_terms(moved)
+        np.testing.assert_allclose(e_nl2.cpu().numpy(), efn.compute_terms(moved).cpu().numpy(), rtol=tol, atol=tol)
+    nbrs.update(moved.center)  # same positions again: no second rebuild
+    assert int(nbrs.rebuilds.item()) == 1
+    nbrs.update(moved.center, force_rebuild=True)
+    assert int(nbrs.did_buffer_overflow.item()) in (0, 1, 4, 5)
+    # a collapse of the structure overflows the slots: reported, not silently truncated
+    squeezed = moved.center * 0.3
+    nbrs.update(squeezed)
+    assert int(nbrs.did_buffer_overflow.item()) & 5
 
 
 def test_invalid_bonded_index_raises():
