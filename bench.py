@@ -184,6 +184,36 @@ def md_benchmark(dev, n_steps: int = 10000):
     e_last = float(efn(RigidBody(traj.center[-1], Quaternion(traj.orientation.vec[-1]))))
     us_step = 1e3 * ms / n_steps
 
+    # neighbour-list variant: the same run with a cell-list neighbour list at the model's interaction range
+    # (+ 0.2 skin) that updates itself on the device -- displacement test and conditional rebuild are the third launch of
+    # the captured step, no host round trip (utils.neighbors.NeighborListFns on the frame-resident build)
+    md_nl = None
+    try:
+        from mythos_b200.energy import model as kmodel
+        from mythos_b200.utils import neighbors as nbmod
+
+        rng_cut = kmodel.interaction_range(kmodel.plan_for(efn.energy_fns))
+        fns = nbmod.get_neighbor_list_fn(top.bonded_neighbors, top.n_nucleotides, space.free()[0], None, r_cutoff=rng_cut, dr_threshold=0.2)
+        sim_nl = md.MDSimulator(energy_fn=efn, simulator_params=params, space=space.free(), neighbors=fns)
+        sim_nl.run({}, body, 200, key=1)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        traj_nl = sim_nl.run({}, body, n_steps, key=2)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms_nl = e0.elapsed_time(e1)
+        probe = fns.allocate(body)
+        for k in range(0, n_steps, 10):  # rebuild frequency along the produced trajectory (every 10th step replayed)
+            probe.update(traj_nl.center[k])
+        md_nl = {"us_per_step": 1e3 * ms_nl / n_steps, "value": 120 * n_steps / (ms_nl * 1e-3), "unit": "nucleotide-steps/s",
+                 "r_cutoff": rng_cut, "dr_threshold": 0.2, "list_entries": int(probe.idx.shape[-1]), "pairs_listed": int(probe.count.item()),
+                 "device_side_update": probe.slots is not None,
+                 "rebuilds_seen_replaying_every_10th_step": int(probe.rebuilds.item()) if probe.rebuilds is not None else None,
+                 "max_abs_deviation_from_all_pairs_run_first_100_steps": float((traj_nl.center[:100] - traj.center[:100]).abs().max()),
+                 "launches_per_step": 3}
+    except Exception as err:  # noqa: BLE001
+        md_nl = {"unavailable": repr(err)[:200]}
+
     # Roofline of this leg: N = 120 is LAUNCH / DEPENDENCY bound, not FP or HBM bound (each step is two dependent kernels of
     # one wave: 280 B x 120 of state, ~1e5 flop).  The floor measured here is the same replay structure with empty work:
     # CUDA graphs of 16 steps x 2 dependent one-thread kernels, i.e. what the device needs just to sequence the step's two
@@ -248,7 +278,8 @@ def md_benchmark(dev, n_steps: int = 10000):
         cpu = {"unavailable": repr(err)[:200]}
     return {"metric": "MD nucleotide-steps/s", "value": 120 * n_steps / (ms * 1e-3), "unit": "nucleotide-steps/s",
             "workload": "configs[1]: oxDNA1 Langevin MD, 60-bp duplex (N=120), 10^4 steps, all-pairs list (U=7021), float64",
-            "ms_total": ms, "us_per_step": us_step, "final_energy_per_nt": e_last / 120, "roofline": roofline, "cpu_baseline": cpu}
+            "ms_total": ms, "us_per_step": us_step, "final_energy_per_nt": e_last / 120, "roofline": roofline, "cpu_baseline": cpu,
+            "neighbour_list_variant": md_nl}
 
 
 # Work model: SURVEY 8d's per-pair counts, split per term so that a term counts for a pair only
