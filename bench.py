@@ -743,7 +743,7 @@ def main():
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                         "sample": f"{args.cpu_frames} frames of the same workload (oracle: torch-f64 restatement of the reference algorithm, autograd for dE/dparams)"}
 
-    n_chunks = -(-(hi - lo) // functional.FRAME_CHUNK)  # per chunk: support points + 2 x (2 exclusion-table kernels + k_nl_frame) + 1 frame kernel
+    n_chunks = -(-(hi - lo) // functional.FRAME_CHUNK)  # per chunk: support points + 2 exclusion-table kernels + 2 x k_nl_frame + 1 frame kernel
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -758,7 +758,7 @@ def main():
         "warm": {"value": F / (ms_warm * 1e-3), "ms_per_step": ms_warm, "e2e_value": F / (ms_warm_e2e * 1e-3), "e2e_ms_per_step": ms_warm_e2e,
                  "unit": UNIT, "pair_list_cache_bytes_per_gpu": cache_bytes,
                  "what": "pair lists remembered per frame tensor (built once with a 1% cutoff margin); no neighbour kernels in the timed step"},
-        "gpu_launches": args.steps * (n_chunks * 8 + 1),  # k_support_points + k_nl_* + k_frame_energy per chunk, k_weights per step (torch glue not counted)
+        "gpu_launches": args.steps * (n_chunks * 6 + 1),  # k_support_points + k_nl_* + k_frame_energy per chunk, k_weights per step (torch glue not counted)
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "md": md_line, "forces_8k": forces_8k,
         "forces_100k": forces_100k,
     }

@@ -333,8 +333,9 @@ class CellListPairs:
                                                             tag_bits=1 << 30, out=(pairs, count, overflow), max_row=mra,
                                                             warp_slots=(ka, 0, wa))
             if ss is not None:
+                # (same workspace, same bonded list as the build just enqueued: its exclusion table is reused)
                 neighbors.build_pairs(ss, self.bonded, self.box, r_db, 0.0, cap, self.workspace, tag_bits=1 << 29,
-                                      out=(pairs, count, overflow), max_row=mrb, warp_slots=(kb, wpf * wa, wb))
+                                      out=(pairs, count, overflow), max_row=mrb, warp_slots=(kb, wpf * wa, wb), reuse_exclusions=True)
             self.last_valid_count = count  # (F) pairs actually written (the kernels scan the whole padded capacity)
             return pairs, cap, overflow, mra, mrb
 

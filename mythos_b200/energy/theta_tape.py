@@ -326,16 +326,19 @@ class FlatParams(Mapping):
         # (built once per optimiser step on the critical path in front of the first kernel launch: python floats / one
         # torch.tensor call instead of a hundred as_tensor + reshape + cat calls, 0.28 -> 0.05 ms for 103 parameters)
         self.names = tuple(sorted(source))
-        vals = [source[k] for k in self.names]
-        if flat is None and vals and all(isinstance(v, torch.Tensor) and v.dim() == 0 and v.dtype == torch.float64 and not v.is_cuda
-                                          for v in vals):
-            # the common case (every parameter a float64 scalar tensor): one stack
-            n = len(vals)
-            self.shapes, self.sizes = ((),) * n, (1,) * n
-            self.offsets = {k: i for i, k in enumerate(self.names)}
-            self.flat = torch.stack([v.detach() for v in vals])
-            self._views = {}
-            return
+        if flat is None and source:
+            # the common case (every parameter a float64 scalar tensor on the host): one stack, checked on its result
+            try:
+                stacked = torch.stack([source[k] for k in self.names])
+            except (TypeError, RuntimeError):  # python floats, tables, mixed shapes or devices: the general path below
+                stacked = None
+            if stacked is not None and stacked.dim() == 1 and stacked.dtype == torch.float64 and not stacked.is_cuda:
+                n = len(self.names)
+                self.shapes, self.sizes = ((),) * n, (1,) * n
+                self.offsets = dict(zip(self.names, range(n)))
+                self.flat = stacked.detach()
+                self._views = {}
+                return
         shapes, sizes, data = [], [], []
         for k in self.names:
             v = source[k]
