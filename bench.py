@@ -674,7 +674,8 @@ def main():
     tagged = src.tag is not None
     tpairs, tstride, tcount = src.chunk(slice(0, chunk), cc, qq, tagged=True, slots=True)
     u["kept_by_tagged_build"] = float(src.last_valid_count.double().mean())
-    u["list_entries_with_slot_padding"] = tstride // 2
+    # entries the frame kernel's producer reads per frame: the packed slots' valid entries, or the padded capacity
+    u["list_entries_read_by_consumer"] = float(tcount.double().mean()) if tcount is not None else tstride // 2
     for _ in range(5):
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         torch.cuda.synchronize(dev)
@@ -712,7 +713,7 @@ def main():
         "achieved_kernel": kernel_achieved, "frac_kernel": kernel_achieved / best if best else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of the kernel at this shape from the committed ncu capture, in bytes;
         # other shapes have no capture.  It exceeds the algorithmic bytes by the padding entries of the one-pass warp-slot
-        # lists (64 000 entries per frame for 42 600 pairs): read once, skipped, never re-read.
+        # lists (padded slots: 64 000 entries per frame for 42 600 pairs; packed slots, the default on the frame-resident route: none).
         "traffic": ncu["dram_bytes"] if ncu else None,
         "ncu": ncu,
         "model_vs_counter": (None if not ncu else

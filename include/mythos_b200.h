@@ -498,6 +498,11 @@ typedef struct mb_nl_args {
                          * padding value); *overflow bit 0 is set if a row is too narrow; count = pairs found.  Consumers
                          * must scan the whole capacity (pair_count = NULL).                                            */
 size_t mythos_b200_nl_workspace_bytes(int32_t n, int32_t n_frames);
+#define MB_NL_PACKED_SLOTS 0x10u /* with MB_NL_WARP_SLOTS on the frame-resident route (mythos_b200_nl_conditional_supported): the
+                         * warps' slots are packed back to back in warp order -- a compact list, count[f] valid entries at the
+                         * head of the frame's list, nothing behind them written; slot_width is ignored, slot_base != 0 means
+                         * "append behind the count[f] entries an earlier build left"; *overflow bit 0: capacity exceeded.
+                         * Same pairs in the same order as the padded slots with the padding removed.                      */
 #define MB_NL_REUSE_EXCLUSIONS 0x8u /* the exclusion table in `workspace` is that of an earlier build with the same bonded list
                          * (same workspace, same n): skip its two launches (per-step conditional rebuilds of an MD run)   */
 /* 1 if a free-space MB_NL_WARP_SLOTS build of n nucleotides with these slots runs on the frame-resident route (one launch,

@@ -36,6 +36,7 @@ NL_ROWS = 0x1
 NL_TAG_SUPPORTS = 0x2
 NL_WARP_SLOTS = 0x4
 NL_REUSE_EXCLUSIONS = 0x8
+NL_PACKED_SLOTS = 0x10
 FLAG_TAGGED_PAIRS = 0x8
 MAX_BANKS = 3
 STATUS = {0: "MB_OK", 1: "MB_EINVAL_SHAPE", 2: "MB_EINVAL_MODEL", 3: "MB_ECAPACITY", 4: "MB_ECUDA"}

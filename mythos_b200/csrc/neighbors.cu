@@ -90,6 +90,7 @@ struct NlDev {
   T* reference;                  // (F,N,3) centres at the last build: conditional rebuild (k_nl_frame), or nullptr
   T move2;                       // squared displacement beyond which a frame is rebuilt
   int32_t* rebuilds;             // (F) rebuild counters, or nullptr
+  int packed;                    // k_nl_frame: warp slots packed back to back (MB_NL_PACKED_SLOTS)
   // workspace
   int32_t* excl;       // (N, kMaxExcl)
   unsigned long long* bounds;  // (F, 6) ordered-integer min / max corners
@@ -733,6 +734,7 @@ __global__ void __launch_bounds__(kFrBlock, 2) k_nl_frame(NlDev<T> a) {
   __shared__ double s_lo[kFrBlock / 32][3], s_hi[kFrBlock / 32][3];
   __shared__ int32_t s_warp[kFrBlock / 32];
   __shared__ int32_t s_stat[4];  // pairs written, longest lane row, largest warp total, overflow bits
+  __shared__ int32_t s_tot[2][kFrBlock / 32];  // packed slots: the warps' totals of a round (double buffered)
   const NlFrameLayout<T, kFrBlock> lay(a.n, a.cmax, a.lane_slots);
   int32_t* arr = reinterpret_cast<int32_t*>(fsm);  // arr[c] = start of cell c in cell order, arr[ncell] = n
   int32_t* hist = arr + 1;
@@ -861,7 +863,13 @@ __global__ void __launch_bounds__(kFrBlock, 2) k_nl_frame(NlDev<T> a) {
     int w_pairs = 0, w_lane = 0, w_total = 0, w_flags = 0;
     uint16_t* stage = stage_all + (size_t)tid * lane_slots;
     const uint16_t* wstage = stage_all + (size_t)(warp * 32) * lane_slots;
-    for (int gw = warp; gw < wpf; gw += kFrBlock / 32) {
+    // rounds of one task per warp (task gw = 32 consecutive cell-order positions).  Packed slots need the totals of all
+    // earlier tasks: one barrier per round, every warp takes part in every round (a warp without a task has no live lane)
+    const bool packed = a.packed != 0;
+    int run_base = packed ? (a.slot_base == 0 ? 0 : a.count[f]) : 0;  // packed: where this build's first entry goes
+    for (int r0 = 0, rr = 0; r0 < wpf; r0 += kFrBlock / 32, ++rr) {
+      const int gw = r0 + warp;
+      if (!packed && gw >= wpf) break;
       const int p = gw * 32 + lane;
       const bool live = p < n;
       const NlRec<T> me = rec[live ? p : 0];
@@ -921,10 +929,26 @@ __global__ void __launch_bounds__(kFrBlock, 2) k_nl_frame(NlDev<T> a) {
         const int y = __shfl_xor_sync(0xffffffffu, longest, o);
         longest = y > longest ? y : longest;
       }
-      int32_t* o0 = a.pairs + (long long)f * 2 * a.capacity + a.slot_base + (long long)gw * a.slot_width;
+      int32_t* o0 = a.pairs + (long long)f * 2 * a.capacity + (packed ? 0 : a.slot_base + (long long)gw * a.slot_width);
       int32_t* o1 = o0 + a.capacity;
-      const int sw = int(a.slot_width);
+      int sw = int(a.slot_width);
       const int excl_before = incl - mine;
+      if (packed) {
+        if (lane == 0) s_tot[rr & 1][warp] = total;
+        __syncthreads();
+        int before = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < kFrBlock / 32; ++w) {
+          const int t = s_tot[rr & 1][w];
+          before += w < warp ? t : 0;
+          all += t;
+        }
+        const long long room = a.capacity - (long long)(run_base + before);
+        o0 += run_base + before;
+        o1 += run_base + before;
+        sw = room < 0 ? 0 : (room < total ? int(room) : total);  // entries of this task that fit; no padding behind them
+        run_base += all;
+      }
       __syncwarp();
       // four owners at a time, eight lanes each: an owner's partners are one contiguous run of the slot
       {
@@ -1113,9 +1137,12 @@ static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
   if ((x->flags & MB_NL_WARP_SLOTS) && !periodic && n < 32768 && frame_build_enabled()) {
     // frame-resident route: cell table + records of a frame in shared memory, one launch (see k_nl_frame)
     const long long wpf = (n + 31) / 32;
-    MB_REQUIRE(x->lane_slots > 0 && x->lane_slots <= 256 && x->slot_width > 0 && x->slot_base >= 0 &&
-                   x->slot_base + wpf * x->slot_width <= x->capacity,
+    const bool packed = (x->flags & MB_NL_PACKED_SLOTS) != 0;
+    MB_REQUIRE(x->lane_slots > 0 && x->lane_slots <= 256 && x->slot_base >= 0 &&
+                   (packed || (x->slot_width > 0 && x->slot_base + wpf * x->slot_width <= x->capacity)),
                MB_EINVAL_SHAPE, "nl_build: warp-slot mode needs 0 < lane_slots <= 256 and slot_base + ceil(n/32) * slot_width <= capacity");
+    MB_REQUIRE(!packed || !x->reference, MB_EINVAL_SHAPE, "nl_build: packed slots cannot be rebuilt conditionally (a second build appends behind the first)");
+    a.packed = packed ? 1 : 0;
     int dev = 0, smem_max = 0, smem_sm = 0, sms = 0;
     MB_CUDA_CHECK(cudaGetDevice(&dev));
     MB_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -1175,6 +1202,8 @@ static int nl_impl(cudaStream_t s, const mb_nl_args* x) {
     }
   }
   MB_REQUIRE(!x->reference, MB_EINVAL_SHAPE, "nl_build: the conditional rebuild (reference) needs a free-space warp-slot build on the frame-resident route");
+  MB_REQUIRE(!(x->flags & MB_NL_PACKED_SLOTS), MB_EINVAL_SHAPE, "nl_build: packed slots need the frame-resident route (mythos_b200_nl_conditional_supported)");
+  a.packed = 0;
   MB_CUDA_CHECK(cudaMemsetAsync(a.cstart, 0, sizeof(int32_t) * (size_t)(FC + 1), s));
   MB_CUDA_CHECK(cudaMemsetAsync(a.cursor, 0, sizeof(int32_t) * (size_t)FC, s));
   k_nl_excl_init<<<ceil_div((long long)n * kMaxExcl, 256), 256, 0, s>>>(a.excl, n);

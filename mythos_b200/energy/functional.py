@@ -168,6 +168,9 @@ def _launch(
     return terms, d_center, d_quat, d_params
 
 
+PACKED_SLOTS = True  # False: padded warp slots also on the frame-resident route (A/B tests)
+
+
 @dc.dataclass(frozen=True)
 class StaticPairs:
     """An explicit unbonded list: (2,U) shared by all frames, or (F,2,U) one list per frame."""
@@ -329,15 +332,22 @@ class CellListPairs:
             mra = torch.empty((F, 2), dtype=torch.int32, device=cc.device)
             mrb = torch.empty((F, 2), dtype=torch.int32, device=cc.device) if ss is not None else None
             self.workspace = _scratch_nl_workspace(cc.device, cc.shape[1], F)
+            # frame-resident builds (free space, a frame's cell table and records in shared memory) pack the warps' slots back
+            # to back: the consumer reads count[f] entries instead of the padded capacity (a third fewer producer steps)
+            packed = PACKED_SLOTS and not any(self.box)
+            if packed:
+                with torch.cuda.device(cc.device):
+                    packed = bool(_lib.lib().mythos_b200_nl_conditional_supported(n, max(ka, kb if ss is not None else 0), cc.element_size()))
             _, _, _, self.workspace = neighbors.build_pairs(cc, self.bonded, self.box, max(r_sr, 1e-6), 0.0, cap, self.workspace,
                                                             tag_bits=1 << 30, out=(pairs, count, overflow), max_row=mra,
-                                                            warp_slots=(ka, 0, wa))
+                                                            warp_slots=(ka, 0, wa), packed_slots=packed)
             if ss is not None:
                 # (same workspace, same bonded list as the build just enqueued: its exclusion table is reused)
                 neighbors.build_pairs(ss, self.bonded, self.box, r_db, 0.0, cap, self.workspace, tag_bits=1 << 29,
-                                      out=(pairs, count, overflow), max_row=mrb, warp_slots=(kb, wpf * wa, wb), reuse_exclusions=True)
-            self.last_valid_count = count  # (F) pairs actually written (the kernels scan the whole padded capacity)
-            return pairs, cap, overflow, mra, mrb
+                                      out=(pairs, count, overflow), max_row=mrb, warp_slots=(kb, wpf * wa, wb), reuse_exclusions=True,
+                                      packed_slots=packed)
+            self.last_valid_count = count  # (F) pairs actually written
+            return pairs, cap, overflow, mra, mrb, (count if packed else None)
 
         def sized(lane_max, warp_max):
             return min(max(int(lane_max * 1.5) + 4, 8), 256), (max(int(warp_max * 1.35) + 16, 32) + 3) // 4 * 4
@@ -345,15 +355,15 @@ class CellListPairs:
         # slot sizes are remembered per system (_SizingMemo): a fresh pair source must not pay a probe -- or worse, an
         # overflow and a repeated pass -- on every step
         if self.slot_geometry is None:  # probe the first frame with generous slots, size from what it needed
-            _, _, _, mra, mrb = run(c[:1], None if sites is None else sites[:1], ((256, 32 * 128), (256, 32 * 128)))
+            _, _, _, mra, mrb, _ = run(c[:1], None if sites is None else sites[:1], ((256, 32 * 128), (256, 32 * 128)))
             a_l, a_w = (int(v) for v in mra.max(0).values.tolist())
             b_l, b_w = (int(v) for v in mrb.max(0).values.tolist()) if mrb is not None else (0, 0)
             self.slot_geometry = (sized(a_l, a_w), sized(b_l, b_w))
             self._store_memo()
-        pairs, cap, overflow, mra, mrb = run(c, sites, self.slot_geometry)
+        pairs, cap, overflow, mra, mrb, count = run(c, sites, self.slot_geometry)
         self._pending.append((torch.zeros((1,), dtype=torch.int32, device=c.device), overflow))
         self._slot_stats.append((mra, mrb))
-        return pairs, 2 * cap, None
+        return pairs, 2 * cap, count  # (count: packed slots -- valid entries at the head; None: padded slots, scan the capacity)
 
     def chunk(self, sl: slice, center: torch.Tensor, quat: torch.Tensor | None = None, tagged: bool = False, slots: bool = False):
         """Enqueue the build for one chunk of frames; overflow is checked once per pass by ``verify`` (one host sync).

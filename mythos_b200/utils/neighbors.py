@@ -39,6 +39,7 @@ def build_pairs(
     move_threshold: float = 0.0,
     rebuilds: torch.Tensor | None = None,
     reuse_exclusions: bool = False,
+    packed_slots: bool = False,
 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """Raw batched build.  center (F,N,3) on the device -> (pairs (F,2,capacity) int32, count (F,), overflow (1,), workspace).
 
@@ -88,6 +89,8 @@ def build_pairs(
         a.rebuilds = rebuilds.data_ptr() if rebuilds is not None else None
     if reuse_exclusions:
         a.flags |= _lib.NL_REUSE_EXCLUSIONS
+    if packed_slots:  # warp slots packed back to back: a compact list, count[f] valid entries at its head (frame-resident route only)
+        a.flags |= _lib.NL_PACKED_SLOTS
     fn = getattr(_lib.lib(), f"mythos_b200_nl_build_{_lib.suffix(center.dtype)}")
     with torch.cuda.device(dev):
         _lib.check(fn(_lib.current_stream(dev), C.byref(a)), "mythos_b200_nl_build")

@@ -207,6 +207,51 @@ def test_listed_pairs_give_all_pairs_energy_and_update_protocol(monkeypatch):
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_packed_slots_are_the_padded_slots_without_the_padding(dtype):
+    """MB_NL_PACKED_SLOTS (frame-resident route): two tagged builds into one list, the warps' slots back to back -- exactly the
+    entries of the padded layout in the same order, count[f] of them at the head; too small a capacity is flagged."""
+    s = synthetic.assembly(17, seed=11)
+    rng = np.random.default_rng(3)
+    frames = np.stack([synthetic.jitter(s.center, s.quat, rng)[0] for _ in range(5)])
+    c = torch.tensor(frames, dtype=dtype, device=DEV)
+    bonded = torch.tensor(s.topology.bonded_neighbors)
+    n, F = s.center.shape[0], frames.shape[0]
+    wpf = (n + 31) // 32
+    W1, W2, K = 400, 900, 80
+    cap = wpf * (W1 + W2)
+
+    def build(packed):
+        pairs = torch.full((F, 2, cap), -7, dtype=torch.int32, device=DEV)
+        count = torch.empty((F,), dtype=torch.int32, device=DEV)
+        ov = torch.zeros((1,), dtype=torch.int32, device=DEV)
+        mr1, mr2 = (torch.empty((F, 2), dtype=torch.int32, device=DEV) for _ in range(2))
+        _, _, _, ws = neighbors.build_pairs(c, bonded, (0.0, 0.0, 0.0), 1.7, 0.0, cap, None, tag_bits=1 << 30, out=(pairs, count, ov), max_row=mr1,
+                                            warp_slots=(K, 0, W1), packed_slots=packed)
+        neighbors.build_pairs(c, bonded, (0.0, 0.0, 0.0), 2.4, 0.0, cap, ws, tag_bits=1 << 29, out=(pairs, count, ov), max_row=mr2,
+                              warp_slots=(K, wpf * W1, W2), packed_slots=packed, reuse_exclusions=True)
+        return pairs.cpu().numpy(), count.cpu().numpy(), int(ov.item()), mr1.cpu(), mr2.cpu()
+
+    pad, pad_count, pad_ov, a1, a2 = build(False)
+    pk, pk_count, pk_ov, b1, b2 = build(True)
+    assert pad_ov == 0 and pk_ov == 0 and np.array_equal(pad_count, pk_count) and torch.equal(a1, b1) and torch.equal(a2, b2)
+    for f in range(F):
+        valid = pad[f, 0] < n
+        assert int(valid.sum()) == int(pk_count[f])
+        assert np.array_equal(pk[f][:, : pk_count[f]], pad[f][:, valid])
+        assert np.all(pk[f][:, pk_count[f]:] == -7)  # nothing is written behind the packed entries
+    # capacity one entry short of what frame 0 needs: flagged, count clamped
+    small = int(pk_count.max()) - 1
+    pairs = torch.empty((F, 2, small), dtype=torch.int32, device=DEV)
+    count = torch.empty((F,), dtype=torch.int32, device=DEV)
+    ov = torch.zeros((1,), dtype=torch.int32, device=DEV)
+    _, _, _, ws = neighbors.build_pairs(c, bonded, (0.0, 0.0, 0.0), 1.7, 0.0, small, None, tag_bits=1 << 30, out=(pairs, count, ov),
+                                        warp_slots=(K, 0, W1), packed_slots=True)
+    neighbors.build_pairs(c, bonded, (0.0, 0.0, 0.0), 2.4, 0.0, small, ws, tag_bits=1 << 29, out=(pairs, count, ov),
+                          warp_slots=(K, 1, W2), packed_slots=True)
+    assert int(ov.item()) & 1 and int(count.max()) <= small
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_device_side_update_rebuilds_in_place_only_after_a_move(dtype):
     """Free-space lists of small systems live in the warp-slot layout and update() is ONE conditional launch: no rebuild
     below dr_threshold/2 (list, reference and counter untouched), a rebuild in place above it (reference <- positions,
