@@ -41,9 +41,9 @@ sys.path.insert(0, str(ROOT))
 N_DUPLEX, PITCH, SEED = 17, 2.6, 1
 METRIC, UNIT = "DiffTRe frames/s (E+dE/dtheta)", "frames/s"
 # hardware counters of k_frame_energy<double,1,1,0> at 1184 frames x 2040 nt from the committed `ncu --set full` capture
-NCU_COUNTERS = {"source": "profiles/r02_final_k_frame_energy_details.csv", "sm__inst_executed_pipe_fp64_pct": 24.40,
-                "smsp__issue_active_pct": 39.39, "sm__warps_active_pct": 24.98, "dram_bytes": 0.7910e9, "duration_ms": 2.583,
-                "local_ld_st_inst": 13.8e6}
+NCU_COUNTERS = {"source": "profiles/r02_packed_k_frame_energy_details.csv", "sm__inst_executed_pipe_fp64_pct": 26.50,
+                "smsp__issue_active_pct": 40.68, "sm__warps_active_pct": 24.99, "dram_bytes": 0.5614e9, "duration_ms": 2.390,
+                "local_ld_st_inst": 11.1e6}
 # Issue cost of the special functions in FP64 FMA slots.  MEASURED (csrc/peaks.cu micro-kernels: a dependent chain of
 # f(x)*a+b against a chain of FMAs, profiles/r02_special_weights.json); bench re-measures them in every run and uses the
 # live numbers -- these are only the fallback.  (SURVEY 8d's provisional guesses were div 16 sqrt 16 exp 40 log 50 acos 70.)
@@ -712,8 +712,8 @@ def main():
         "scope": "whole cold step per GPU (neighbour builds + frame kernel + reweighting + theta chain); frac_kernel is the dominant kernel alone",
         "achieved_kernel": kernel_achieved, "frac_kernel": kernel_achieved / best if best else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of the kernel at this shape from the committed ncu capture, in bytes;
-        # other shapes have no capture.  It exceeds the algorithmic bytes by the padding entries of the one-pass warp-slot
-        # lists (padded slots: 64 000 entries per frame for 42 600 pairs; packed slots, the default on the frame-resident route: none).
+        # other shapes have no capture.  With packed slots (the default on the frame-resident neighbour route) the list holds
+        # no padding: 561 MB against 541 MB algorithmic (the padded slots read 791 MB).
         "traffic": ncu["dram_bytes"] if ncu else None,
         "ncu": ncu,
         "model_vs_counter": (None if not ncu else
@@ -750,7 +750,7 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": workload_name(F), "frames_per_gpu": hi - lo, "n_nucleotides": n,
-                   "l2": "inputs larger than L2 (frames 936 MB + 0.8 GB of pair lists per 1184-frame chunk)", "n_theta": len(theta),
+                   "l2": "inputs larger than L2 (frames 936 MB + 0.4 GB of pair lists per 1184-frame chunk)", "n_theta": len(theta),
                    "loss": loss, "n_eff": float(neff.detach()), "grad_norm": float(grad_host.norm()),
                    "pass": "cold: the per-frame pair lists are rebuilt in every timed step (pair-list cache off)",
                    "step": "objective.compute_loss_and_grad (theta -> bank, E + dE/dparams rows, gather, weights/n_eff, loss, g @ J, theta VJP, all-reduce)"},
