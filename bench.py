@@ -750,7 +750,7 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": workload_name(F), "frames_per_gpu": hi - lo, "n_nucleotides": n,
-                   "l2": "inputs larger than L2 (frames 936 MB + 0.4 GB of pair lists per 1184-frame chunk)", "n_theta": len(theta),
+                   "l2": "inputs larger than L2 (frames 936 MB + 0.7 GB of pair lists per 2072-frame chunk)", "n_theta": len(theta),
                    "loss": loss, "n_eff": float(neff.detach()), "grad_norm": float(grad_host.norm()),
                    "pass": "cold: the per-frame pair lists are rebuilt in every timed step (pair-list cache off)",
                    "step": "objective.compute_loss_and_grad (theta -> bank, E + dE/dparams rows, gather, weights/n_eff, loss, g @ J, theta VJP, all-reduce)"},
