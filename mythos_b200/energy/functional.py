@@ -12,6 +12,7 @@ device it raises.
 from __future__ import annotations
 
 import ctypes as C
+import collections
 import dataclasses as dc
 import os
 import threading
@@ -605,24 +606,30 @@ STREAM_CHUNK = int(os.environ.get("MYTHOS_B200_STREAM_CHUNK", "1184"))
 
 
 STREAM_FIRST_CHUNK = 148  # frames of the first chunk of a pass over pinned HOST frames (one wave of one CTA per SM)
+STREAM_RAMP = (1, 2, 3, 5, 7, 10, 14)  # chunk sizes of a streamed pass in units of the first chunk, then the regular size
+STREAM_AHEAD_BYTES = int(float(os.environ.get("MYTHOS_B200_STREAM_AHEAD_GB", "2")) * 2**30)  # host -> device copies queued ahead of the kernels
 
 
 def _chunks(n_frames: int, source, streamed: bool = False) -> list[slice]:
-    """Frame ranges of one pass.  Frames streamed from pinned host memory start with a one-wave chunk and double from
-    there up to the regular chunk size: the copy of a frame takes about half the time of its evaluation, so after the
-    first small chunk (the only copy the kernels ever wait for) every later chunk is on the device before it is needed --
-    also when a rank's whole block is smaller than one regular chunk (8 GPUs: 1024 frames each)."""
+    """Frame ranges of one pass.  Frames streamed from pinned host memory start with a one-wave chunk and grow by about
+    1.4x per chunk up to the regular size: the copies of ALL chunks are queued on the copy stream ahead of the kernels
+    (``STREAM_AHEAD_BYTES``), a frame's copy takes ~0.75 of its evaluation, so a chunk that is at most ~1.33x the frames
+    evaluated before it has arrived by the time the kernels get to it (doubling, the earlier ramp, left the kernels waiting
+    for the copy at every step of the ramp) -- also when a rank's whole block is smaller than one regular chunk."""
     step = FRAME_CHUNK if (isinstance(source, CellListPairs) or source is CellListPairs) else 65535
     if not streamed:
         return [slice(lo, min(lo + step, n_frames)) for lo in range(0, n_frames, step)]
     step = min(step, STREAM_CHUNK)
-    out, lo, size = [], 0, min(STREAM_FIRST_CHUNK, step)
+    first = min(STREAM_FIRST_CHUNK, step)
+    sizes = [min(w * first, step) for w in STREAM_RAMP if w * first < step] + [step]
+    out, lo, k = [], 0, 0
     while lo < n_frames:
+        size = sizes[min(k, len(sizes) - 1)]
         hi = min(lo + size, n_frames)
         if n_frames - hi < size // 2:  # do not leave a sliver for a chunk of its own
             hi = n_frames if n_frames - lo <= step else hi
         out.append(slice(lo, hi))
-        lo, size = hi, min(2 * size, step)
+        lo, k = hi, k + 1
     return out
 
 
@@ -693,11 +700,28 @@ def _run(model, topo, center, quat, params, source, term_mask, cot, want_terms, 
                     source.r_cutoff = built[0]
             if isinstance(source, CellListPairs):
                 source.keep_lists = bool(cacheable)
-            nxt = _fetch(center, quat, chunks[0], dev) if streamed else None
+            # streamed frames: the copies run ahead of the kernels on the copy stream, as many chunks as STREAM_AHEAD_BYTES
+            # allows (the copy engine never idles; a chunk's kernels wait only for that chunk's own event)
+            ahead, queued, in_flight = collections.deque(), 0, 0
+            per_frame = (center[0].numel() + quat[0].numel()) * center.element_size() if streamed and center.shape[0] else 0
+
+            def top_up():
+                nonlocal queued, in_flight
+                while queued < len(chunks):
+                    nb = (chunks[queued].stop - chunks[queued].start) * per_frame
+                    if ahead and in_flight + nb > STREAM_AHEAD_BYTES:
+                        break
+                    ahead.append((_fetch(center, quat, chunks[queued], dev), nb))
+                    in_flight += nb
+                    queued += 1
+
+            if streamed:
+                top_up()
             for k, sl in enumerate(chunks):
                 if streamed:
-                    c_sl, q_sl, ready = nxt
-                    nxt = _fetch(center, quat, chunks[k + 1], dev) if k + 1 < len(chunks) else None
+                    (c_sl, q_sl, ready), nb = ahead.popleft()
+                    in_flight -= nb
+                    top_up()
                     torch.cuda.current_stream(dev).wait_event(ready)
                     c_sl.record_stream(torch.cuda.current_stream(dev))
                     q_sl.record_stream(torch.cuda.current_stream(dev))
