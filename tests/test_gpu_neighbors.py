@@ -296,6 +296,45 @@ def test_device_side_update_rebuilds_in_place_only_after_a_move(dtype):
     assert int(nbrs.did_buffer_overflow.item()) & 5
 
 
+def test_conditional_rebuild_decides_frame_by_frame():
+    """mb_nl_args.reference with several frames: every frame is tested against its own reference positions; only the
+    frames that moved are rebuilt (list, count, reference, counter), the others are left exactly as they were."""
+    s = synthetic.assembly(3, seed=6)
+    bonded = torch.tensor(s.topology.bonded_neighbors)
+    n = s.center.shape[0]
+    wpf = (n + 31) // 32
+    rng = np.random.default_rng(8)
+    frames = np.stack([synthetic.jitter(s.center, s.quat, rng)[0] for _ in range(4)])
+    c = torch.tensor(frames, device=DEV)
+    K, W = 64, 32 * 40
+    cap = wpf * W
+    pairs = torch.empty((4, 2, cap), dtype=torch.int32, device=DEV)
+    count = torch.empty((4,), dtype=torch.int32, device=DEV)
+    ov = torch.zeros((1,), dtype=torch.int32, device=DEV)
+    mr = torch.empty((4, 2), dtype=torch.int32, device=DEV)
+    _, _, _, ws = neighbors.build_pairs(c, bonded, (0.0, 0.0, 0.0), 2.0, 0.2, cap, None, out=(pairs, count, ov), max_row=mr, warp_slots=(K, 0, W))
+    ref = c.clone()
+    rebuilds = torch.zeros((4,), dtype=torch.int32, device=DEV)
+    before, count_before = pairs.clone(), count.clone()
+    moved = c.clone()
+    moved[1] += torch.tensor([0.3, 0.0, 0.0], device=DEV) * (torch.arange(n, device=DEV) % 3 == 0).unsqueeze(1)  # beyond 0.1
+    moved[3, 5, 2] += 0.11                                                                                      # one nucleotide, just beyond
+    moved[2] += 0.05                                                                                            # rigid shift below the threshold
+    neighbors.build_pairs(moved, bonded, (0.0, 0.0, 0.0), 2.0, 0.2, cap, ws, out=(pairs, count, ov), max_row=mr, warp_slots=(K, 0, W),
+                          reference=ref, move_threshold=0.1, rebuilds=rebuilds, reuse_exclusions=True)
+    assert rebuilds.tolist() == [0, 1, 0, 1] and int(ov.item()) == 0
+    for f in (0, 2):
+        assert torch.equal(pairs[f], before[f]) and torch.equal(ref[f], c[f]) and int(count[f]) == int(count_before[f])
+    for f in (1, 3):
+        assert torch.equal(ref[f], moved[f])
+        want = brute_force(np.asarray(moved[f].cpu()), s.topology.bonded_neighbors, np.float64(2.0) + np.float64(0.2), None, np.float64)
+        assert to_set(pairs[f], n) == want and int(count[f]) == len(want)
+    # conditional rebuilds are refused where the frame-resident route does not apply (periodic box)
+    with pytest.raises(Exception):
+        neighbors.build_pairs(moved, bonded, (30.0, 30.0, 60.0), 2.0, 0.2, cap, ws, out=(pairs, count, ov), max_row=mr, warp_slots=(K, 0, W),
+                              reference=ref, move_threshold=0.1, rebuilds=rebuilds)
+
+
 def test_invalid_bonded_index_raises():
     with pytest.raises(ValueError):
         neighbors.get_neighbor_list_fn(np.array([[0, 5]]), 3, space.free()[0], None)
