@@ -338,13 +338,14 @@ template <class T>
 __global__ void k_support_points(Geom<T> g0, Geom<T> g1, const int32_t* __restrict__ nt_type, int n, long long n_total,
                                  const T* __restrict__ center, const T* __restrict__ quat, T bx, T by, T bz,
                                  float* __restrict__ out_c, float* __restrict__ out_s, float* __restrict__ extent) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // grid = (blocks over the nucleotides of a frame, frames): no 64-bit division per thread
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long first = (long long)blockIdx.y * n, idx = first + i;
   float m = 0.f;
-  if (idx < n_total) {
-    const long long first = idx - idx % n;
+  if (i < n && idx < n_total) {
     T q[4], q0[4];
     const Nuc<T> nu = load_nuc(center, quat, idx, q);
-    const Geom<T>& g = (nt_type && nt_type[idx % n] == 2) ? g1 : g0;
+    const Geom<T>& g = (nt_type && nt_type[i] == 2) ? g1 : g0;
     V3<T> c = nu.c, b = site(nu, g.back[0], g.back[1], g.back[2]);
     const T box[3] = {bx, by, bz};
     if (bx > T(0)) {
@@ -387,7 +388,8 @@ static int support_points_impl(cudaStream_t s, const mb_model* m, int32_t n, int
   g0.load(m->geom[0]);
   g1.load(m->geom[1]);
   const long long total = (long long)n * n_frames;
-  k_support_points<T><<<ceil_div(total, 256), 256, 0, s>>>(g0, g1, m->n_banks > 1 ? nt_type : nullptr, n, total,
+  MB_REQUIRE(n_frames <= 65535, MB_EINVAL_SHAPE, "support_points: at most 65535 frames per call");
+  k_support_points<T><<<dim3((unsigned)ceil_div(n, 256), (unsigned)n_frames), 256, 0, s>>>(g0, g1, m->n_banks > 1 ? nt_type : nullptr, n, total,
                                                             static_cast<const T*>(center), static_cast<const T*>(quat), T(m->box[0]),
                                                             T(m->box[1]), T(m->box[2]), static_cast<float*>(out_center),
                                                             static_cast<float*>(out_site), static_cast<float*>(extent));
