@@ -674,6 +674,7 @@ int mythos_b200_param_index(const char* name);     /* -1 if unknown             
 const char* mythos_b200_last_error(void);          /* thread-local message of the last failure */
 size_t mythos_b200_sizeof_model(void);
 size_t mythos_b200_sizeof_energy_args(void);
+size_t mythos_b200_sizeof_nl_args(void);
 
 #ifdef __cplusplus
 }

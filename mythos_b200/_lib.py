@@ -250,6 +250,7 @@ _SIGNATURES = {
     "mythos_b200_last_error": (C.c_char_p, []),
     "mythos_b200_sizeof_model": (C.c_size_t, []),
     "mythos_b200_sizeof_energy_args": (C.c_size_t, []),
+    "mythos_b200_sizeof_nl_args": (C.c_size_t, []),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -267,7 +268,8 @@ def lib() -> C.CDLL:
         fn = getattr(handle, name)
         fn.restype = res
         fn.argtypes = args
-    if handle.mythos_b200_sizeof_model() != C.sizeof(Model) or handle.mythos_b200_sizeof_energy_args() != C.sizeof(EnergyArgs):
+    if (handle.mythos_b200_sizeof_model() != C.sizeof(Model) or handle.mythos_b200_sizeof_energy_args() != C.sizeof(EnergyArgs)
+            or handle.mythos_b200_sizeof_nl_args() != C.sizeof(NlArgs)):
         raise MythosB200Error("ctypes struct layout does not match include/mythos_b200.h")
     return handle
 

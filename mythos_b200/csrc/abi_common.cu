@@ -33,4 +33,5 @@ int mythos_b200_param_index(const char* name) {
 const char* mythos_b200_last_error(void) { return mb::g_err; }
 size_t mythos_b200_sizeof_model(void) { return sizeof(mb_model); }
 size_t mythos_b200_sizeof_energy_args(void) { return sizeof(mb_energy_args); }
+size_t mythos_b200_sizeof_nl_args(void) { return sizeof(mb_nl_args); }
 }

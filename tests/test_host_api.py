@@ -54,6 +54,7 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert lib.mythos_b200_param_index(names[i].encode()) == i
     assert lib.mythos_b200_param_index(b"no.such_param") == -1
     assert lib.mythos_b200_sizeof_model() == C.sizeof(_lib.Model)
+    assert lib.mythos_b200_sizeof_nl_args() == C.sizeof(_lib.NlArgs)
     assert lib.mythos_b200_nl_workspace_bytes(0, 1) == 0 and lib.mythos_b200_nl_workspace_bytes(100, 2) > 0
 
 
